@@ -1,0 +1,671 @@
+// libfftconv.so — C ABI + host schedule of the B200-native FFT-convolution engine.
+// See include/fftconv.h for the contract and the reference lines each entry point replaces.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fftconv.h"
+#include "kernels_generic.cuh"
+#include "kernels_tile16.cuh"
+
+namespace fftconv {
+
+// ------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail(FFTCONV_ERR_CUDA, "CUDA error %d (%s) at %s:%d: %s", (int)e_,      \
+                        cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                     \
+    do {                                                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        CU(cudaGetLastError());                                                            \
+    } while (0)
+
+static const char* kMsgThread =
+    "CUDA Thread Size must be 4 integers : THREAD_PER_BLOCK_H, THREAD_PER_BLOCK_W, "
+    "THREAD_PER_BLOCK_D, THREAD_PER_BLOCK_2D\nYou must choose size such that total thread will "
+    "not be larger than MaxThreadsPerBlock";
+static const char* kMsgKernelShape =
+    "Kernel and Data must have the same number of features and kernel size should be smaller "
+    "than data size";
+
+// ------------------------------------------------------------------------------ plans
+static LinePlan make_line_plan(int n) {
+    LinePlan p;
+    p.n = n;
+    p.nstages = 0;
+    int m = n;
+    auto push = [&](int r) { p.radix[p.nstages++] = r; m /= r; };
+    while (m % 16 == 0) push(16);
+    if (m % 8 == 0) push(8);
+    if (m % 4 == 0) push(4);
+    if (m % 2 == 0) push(2);
+    while (m % 9 == 0) push(9);
+    const int small[] = {3, 5, 7, 11, 13, 17};
+    for (int r : small)
+        while (m % r == 0) push(r);
+    for (int r = 19; m > 1; r += 2)
+        while (m % r == 0) push(r);
+    return p;
+}
+
+static const size_t kMaxSmem = 227 * 1024;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Ctx {
+    int dev = -1;
+    bool inited = false;
+    std::map<int, cpx*> tw;          // n -> device twiddle table e^{-2 pi i j / n}
+    DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
+    void* pinned = nullptr;          // host staging (descriptors, packed kernels)
+    size_t pinned_cap = 0;
+    cudaEvent_t pinned_free = nullptr;   // recorded after the last async copy out of `pinned`
+    cudaStream_t side = nullptr;         // copy stream for the chunk pipeline
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int sm_count = 148;
+};
+
+static std::mutex g_mu;
+static std::map<int, Ctx> g_ctx;
+
+static int dev_reserve(DevBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    size_t cap = bytes + bytes / 8 + 256;
+    CU(cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return 0;
+}
+
+static int pinned_reserve(Ctx& c, size_t bytes) {
+    if (bytes <= c.pinned_cap) return 0;
+    if (c.pinned) {
+        CU(cudaEventSynchronize(c.pinned_free));
+        CU(cudaFreeHost(c.pinned));
+    }
+    c.pinned = nullptr; c.pinned_cap = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    CU(cudaMallocHost(&c.pinned, cap));
+    c.pinned_cap = cap;
+    return 0;
+}
+
+template <typename K>
+static int opt_in_smem(K kernel) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    return 0;
+}
+
+static int ctx_get(int device, Ctx** out) {
+    Ctx& c = g_ctx[device];
+    if (!c.inited) {
+        c.dev = device;
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(FFTCONV_ERR_CUDA, "fftconv-b200 is built for sm_100a only; device %d is sm_%d%d",
+                        device, prop.major, prop.minor);
+        c.sm_count = prop.multiProcessorCount;
+        // odd-radix coefficient table (cos, sin)(2 pi j / R)
+        static float2 h_tw[32][32];
+        for (int r = 1; r < 32; ++r)
+            for (int j = 0; j < 32; ++j) {
+                const double a = 2.0 * M_PI * (double)(j % r) / (double)r;
+                h_tw[r][j] = make_float2((float)cos(a), (float)sin(a));
+            }
+        CU(cudaMemcpyToSymbol(c_odd_tw, h_tw, sizeof h_tw));
+        CU(cudaEventCreateWithFlags(&c.pinned_free, cudaEventDisableTiming));
+        for (auto& e : c.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+        if (opt_in_smem(fwd_h_pass<PAD_ZERO>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(fwd_h_pass<PAD_CLAMP>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(fwd_w_pass)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(conv_w_pass_generic<false>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(conv_w_pass_generic<true>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(inv_h_pass)) return FFTCONV_ERR_CUDA;
+        if (tile16_opt_in()) return fail(FFTCONV_ERR_CUDA, "cudaFuncSetAttribute failed for the tile16 kernels");
+        c.inited = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+static int get_twiddles(Ctx& c, int n, cudaStream_t st, const cpx** out) {
+    auto it = c.tw.find(n);
+    if (it == c.tw.end()) {
+        std::vector<float2> h(n);
+        for (int j = 0; j < n; ++j) {
+            const double a = -2.0 * M_PI * (double)j / (double)n;
+            h[j] = make_float2((float)cos(a), (float)sin(a));
+        }
+        cpx* d = nullptr;
+        CU(cudaMalloc(&d, sizeof(float2) * (size_t)n));
+        CU(cudaMemcpy(d, h.data(), sizeof(float2) * (size_t)n, cudaMemcpyHostToDevice));
+        it = c.tw.emplace(n, d).first;
+    }
+    (void)st;
+    *out = it->second;
+    return 0;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static inline int odd_ld(int n) { return n | 1; }   // line stride (float2) avoiding bank conflicts
+
+// lines per CTA for the h passes, sized to ~64 KB of shared memory and <= 16
+static int pick_lines(int n, int want_max) {
+    const size_t per_line = 2 * (size_t)odd_ld(n) * sizeof(cpx);
+    int nl = (int)((64 * 1024) / per_line);
+    if (nl < 1) nl = 1;
+    if (nl > want_max) nl = want_max;
+    return nl;
+}
+
+// ------------------------------------------------------------------ data spectrum (cudaFFTData)
+// d_data: device [F][W][H].  Writes the compat spectrum [F][FW][CH].
+static int run_fft_data(Ctx& c, const float* d_data, int H, int W, int F, int FH, int FW,
+                        int pad_mode, int kernel_y, int kernel_x, cpx* d_spec, cudaStream_t st) {
+    const int CH = FH / 2 + 1;
+    const cpx *twH, *twW;
+    if (int e = get_twiddles(c, FH, st, &twH)) return e;
+    if (int e = get_twiddles(c, FW, st, &twW)) return e;
+    const LinePlan pH = make_line_plan(FH), pW = make_line_plan(FW);
+    const int ldH = odd_ld(FH), ldW = odd_ld(FW);
+    if (2 * (size_t)ldH * sizeof(cpx) > kMaxSmem || 2 * (size_t)ldW * sizeof(cpx) > kMaxSmem)
+        return fail(FFTCONV_ERR_UNSUPPORTED, "FFT plane %dx%d exceeds the shared-memory line limit", FH, FW);
+
+    const int ncols = pad_mode == PAD_CLAMP ? FW : W;
+    if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)F * ncols * CH)) return e;
+    // one SrcDesc through pinned staging
+    if (int e = pinned_reserve(c, sizeof(SrcDesc))) return e;
+    if (int e = dev_reserve(c.desc, sizeof(SrcDesc))) return e;
+    CU(cudaEventSynchronize(c.pinned_free));
+    SrcDesc* hd = reinterpret_cast<SrcDesc*>(c.pinned);
+    hd->ptr = d_data; hd->rows = H; hd->cols = W;
+    CU(cudaMemcpyAsync(c.desc.p, hd, sizeof(SrcDesc), cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c.pinned_free, st));
+
+    const int NL = pick_lines(FH, 8);
+    const long long nlines = (long long)F * ((ncols + 1) / 2);
+    const unsigned grid = (unsigned)((nlines + NL - 1) / NL);
+    const size_t smemH = 2 * (size_t)NL * ldH * sizeof(cpx);
+    if (pad_mode == PAD_CLAMP)
+        fwd_h_pass<PAD_CLAMP><<<grid, 256, smemH, st>>>((const SrcDesc*)c.desc.p, 1, F, W, FH, CH, pH, twH,
+                                                         (cpx*)c.T.p, NL, ldH, kernel_y, kernel_x, FW);
+    else
+        fwd_h_pass<PAD_ZERO><<<grid, 256, smemH, st>>>((const SrcDesc*)c.desc.p, 1, F, W, FH, CH, pH, twH,
+                                                        (cpx*)c.T.p, NL, ldH, 0, 0, W);
+    LAUNCH_CHECK();
+
+    int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
+    TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
+    dim3 g2((CH + TU - 1) / TU, F);
+    fwd_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>((const cpx*)c.T.p, ncols, FW, CH, pW, twW,
+                                                                     d_spec, TU, ldW);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------ conv core
+struct KernelRef {
+    const float* ptr;
+    int kh, kw;
+    bool on_device;
+};
+
+struct ConvArgs {
+    const cpx* d_spec;
+    int CH, FW, F, K;
+    const KernelRef* kernels;      // K entries
+    float* const* outs;            // K entries (host or device pointers)
+    bool out_on_device;
+    fftconv_options opt;
+    bool pipelined;                // use the side copy stream (Streams entry point)
+};
+
+static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* d_descs, const int* d_kcols,
+                              int nk, int maxcols, float* const* d_outptrs, cudaStream_t st) {
+    const int CH = a.CH, FW = a.FW, F = a.F;
+    const cpx *twH, *twW;
+    if (int e = get_twiddles(c, FH, st, &twH)) return e;
+    if (int e = get_twiddles(c, FW, st, &twW)) return e;
+    const LinePlan pH = make_line_plan(FH), pW = make_line_plan(FW);
+    const int ldH = odd_ld(FH), ldW = odd_ld(FW);
+
+    // 1. kernel half transforms (pad fused)
+    {
+        const int NL = pick_lines(FH, 8);
+        const long long nlines = (long long)nk * F * ((maxcols + 1) / 2);
+        const unsigned grid = (unsigned)((nlines + NL - 1) / NL);
+        fwd_h_pass<PAD_ZERO><<<grid, 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
+            d_descs, nk, F, maxcols, FH, CH, pH, twH, (cpx*)c.T.p, NL, ldH, 0, 0, maxcols);
+        LAUNCH_CHECK();
+    }
+    // 2. w pass: forward, multiply-accumulate over channels, one inverse
+    {
+        int TU = (int)((160 * 1024) / (3 * (size_t)ldW * sizeof(cpx)));
+        TU = TU < 1 ? 1 : (TU > 8 ? 8 : TU);
+        dim3 grid((CH + TU - 1) / TU, nk);
+        const size_t smem = 3 * (size_t)TU * ldW * sizeof(cpx);
+        if (a.opt.correlate)
+            conv_w_pass_generic<true><<<grid, 256, smem, st>>>((const cpx*)c.T.p, d_kcols, maxcols, a.d_spec, F, FW, CH,
+                                                               pW, twW, (cpx*)c.Z.p, TU, ldW);
+        else
+            conv_w_pass_generic<false><<<grid, 256, smem, st>>>((const cpx*)c.T.p, d_kcols, maxcols, a.d_spec, F, FW, CH,
+                                                                pW, twW, (cpx*)c.Z.p, TU, ldW);
+        LAUNCH_CHECK();
+    }
+    // 3. C2R along h + scale + (crop) store
+    {
+        const int NL = pick_lines(FH, 8);
+        const long long nlines = (long long)nk * (FW / 2);
+        const unsigned grid = (unsigned)((nlines + NL - 1) / NL);
+        const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
+        const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : FW;
+        const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
+        inv_h_pass<<<grid, 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
+            (const cpx*)c.Z.p, nk, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_outptrs, crop_h, crop_w,
+            out_ld, NL, ldH);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static size_t plane_floats(const ConvArgs& a, int FH) {
+    const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
+    const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : a.FW;
+    const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
+    return (size_t)crop_w * out_ld;
+}
+
+// Convolve the spectrum with the whole bank, chunk by chunk.
+static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
+    const int CH = a.CH, FW = a.FW, F = a.F, K = a.K;
+    const int FH = (CH - 1) * 2;                                   // src/cudaConvFFTData.cu:95
+    if (K == 0) return 0;
+    const int ldH = odd_ld(FH), ldW = odd_ld(FW);
+    if (2 * (size_t)ldH * sizeof(cpx) > kMaxSmem || 3 * (size_t)ldW * sizeof(cpx) > kMaxSmem)
+        return fail(FFTCONV_ERR_UNSUPPORTED, "FFT plane %dx%d exceeds the shared-memory line limit", FH, FW);
+    if (a.opt.crop_h > FH || a.opt.crop_w > FW || (a.opt.out_ld > 0 && a.opt.out_ld < (a.opt.crop_h > 0 ? a.opt.crop_h : FH)))
+        return fail(FFTCONV_ERR_INVALID_INPUT, "crop larger than the FFT plane or out_ld too small");
+
+    int maxkh = 1, maxkw = 1;
+    for (int k = 0; k < K; ++k) {
+        maxkh = std::max(maxkh, std::min(a.kernels[k].kh, FH));
+        maxkw = std::max(maxkw, std::min(a.kernels[k].kw, FW));
+    }
+    const bool tile16 = !a.opt.force_generic && tile16_supported(FH, FW, maxkh, maxkw);
+
+    // ---- chunking: bound the scratch held per chunk
+    const size_t plane = plane_floats(a, FH);
+    size_t per_kernel = 0;
+    if (tile16) per_kernel = tile16_scratch_per_kernel(FH, FW, F, maxkh, maxkw);
+    else per_kernel = sizeof(cpx) * ((size_t)F * maxkw * CH + (size_t)FW * CH);
+    if (!a.out_on_device) per_kernel += plane * sizeof(float);
+    const size_t budget = (size_t)96 << 20;    // keep a chunk's intermediates L2-resident (126 MB L2)
+    int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
+    if (tile16) KC = tile16_round_chunk(KC, K);
+
+    if (tile16) {
+        if (int e = tile16_reserve(c.Ag, c.Wg, FH, FW, F, maxkh, maxkw, KC)) return e;
+        if (int e = tile16_prepare_spectrum(c.priv, a.d_spec, FH, FW, F, st)) return e;
+    } else {
+        if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)KC * F * maxkw * CH)) return e;
+        if (int e = dev_reserve(c.Z, sizeof(cpx) * (size_t)KC * FW * CH)) return e;
+    }
+    if (!a.out_on_device)
+        if (int e = dev_reserve(c.outstage, sizeof(float) * plane * KC * 2)) return e;
+
+    // descriptors / kcols / out pointers for ALL kernels go through pinned staging once
+    const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int) + sizeof(float*)) * (size_t)K + 64;
+    size_t host_kernel_bytes = 0;
+    for (int k = 0; k < K; ++k)
+        if (!a.kernels[k].on_device) host_kernel_bytes += sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
+    if (int e = pinned_reserve(c, desc_bytes)) return e;
+    if (int e = dev_reserve(c.desc, desc_bytes)) return e;
+    if (host_kernel_bytes)
+        if (int e = dev_reserve(c.stage, host_kernel_bytes)) return e;
+
+    CU(cudaEventSynchronize(c.pinned_free));
+    SrcDesc* h_desc = reinterpret_cast<SrcDesc*>(c.pinned);
+    float** h_outp = reinterpret_cast<float**>(h_desc + K);
+    int* h_kcols = reinterpret_cast<int*>(h_outp + K);
+    SrcDesc* d_desc = reinterpret_cast<SrcDesc*>(c.desc.p);
+    float** d_outp = reinterpret_cast<float**>(d_desc + K);
+    int* d_kcols = reinterpret_cast<int*>(d_outp + K);
+
+    // upload host kernels: contiguous runs are coalesced into single copies
+    {
+        size_t off = 0;
+        int k = 0;
+        while (k < K) {
+            if (a.kernels[k].on_device) {
+                h_desc[k].ptr = a.kernels[k].ptr;
+                ++k;
+                continue;
+            }
+            const float* run_src = a.kernels[k].ptr;
+            const size_t run_off = off;
+            size_t run_bytes = 0;
+            int j = k;
+            while (j < K && !a.kernels[j].on_device &&
+                   reinterpret_cast<const char*>(a.kernels[j].ptr) == reinterpret_cast<const char*>(run_src) + run_bytes) {
+                const size_t b = sizeof(float) * (size_t)a.kernels[j].kh * a.kernels[j].kw * F;
+                h_desc[j].ptr = reinterpret_cast<const float*>(reinterpret_cast<char*>(c.stage.p) + off);
+                off += b; run_bytes += b;
+                ++j;
+            }
+            CU(cudaMemcpyAsync(reinterpret_cast<char*>(c.stage.p) + run_off, run_src, run_bytes,
+                               cudaMemcpyHostToDevice, st));
+            k = j;
+        }
+    }
+    for (int k = 0; k < K; ++k) {
+        h_desc[k].rows = a.kernels[k].kh;
+        h_desc[k].cols = a.kernels[k].kw;
+        h_kcols[k] = a.kernels[k].kw;
+        h_outp[k] = a.out_on_device ? a.outs[k]
+                                    : reinterpret_cast<float*>(c.outstage.p) + plane * (size_t)((k % KC) + ((k / KC) & 1) * KC);
+    }
+    CU(cudaMemcpyAsync(c.desc.p, c.pinned, desc_bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(c.pinned_free, st));
+
+    // ---- chunk loop.  Device outputs: one stream.  Host outputs: the D2H of chunk i runs on the
+    // side stream while chunk i+1 computes (double-buffered out staging).
+    int chunk = 0;
+    for (int k0 = 0; k0 < K; k0 += KC, ++chunk) {
+        const int nk = std::min(KC, K - k0);
+        if (!a.out_on_device && chunk >= 2) CU(cudaStreamWaitEvent(st, c.ev[chunk & 1], 0));   // staging half free?
+        int e;
+        if (tile16)
+            e = tile16_chunk(c.Ag, c.Wg, c.priv, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0,
+                             a.opt, c.sm_count, st);
+        else
+            e = conv_generic_chunk(c, a, FH, d_desc + k0, d_kcols + k0, nk, maxkw, d_outp + k0, st);
+        if (e) return e;
+        if (!a.out_on_device) {
+            CU(cudaEventRecord(c.ev[2 + (chunk & 1)], st));
+            CU(cudaStreamWaitEvent(c.side, c.ev[2 + (chunk & 1)], 0));
+            // contiguous host planes -> one copy
+            int k = k0;
+            while (k < k0 + nk) {
+                int j = k + 1;
+                while (j < k0 + nk && a.outs[j] == a.outs[j - 1] + plane) ++j;
+                CU(cudaMemcpyAsync(a.outs[k], h_outp[k], sizeof(float) * plane * (size_t)(j - k),
+                                   cudaMemcpyDeviceToHost, c.side));
+                k = j;
+            }
+            CU(cudaEventRecord(c.ev[chunk & 1], c.side));
+        }
+    }
+    if (!a.out_on_device) {
+        CU(cudaStreamSynchronize(c.side));
+        CU(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
+static int check_threads(const double* threads, int nthreads) {
+    if (threads != nullptr && nthreads != 4) return fail(FFTCONV_ERR_THREAD_SIZE, "%s", kMsgThread);
+    if (threads == nullptr && nthreads != 0 && nthreads != 4) return fail(FFTCONV_ERR_THREAD_SIZE, "%s", kMsgThread);
+    return 0;
+}
+
+static int build_kernel_refs(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                             const unsigned char* on_dev, int F, int FH, int FW, std::vector<KernelRef>& refs) {
+    if (K < 0 || (K > 0 && (!kernels || !kh || !kw)))
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    refs.resize(K);
+    for (int k = 0; k < K; ++k) {
+        if (!kernels[k] || kh[k] <= 0 || kw[k] <= 0) return fail(FFTCONV_ERR_KERNEL_TYPE,
+            "Kernels must be of type float and have features larger than 1");
+        // src/cudaConvFFTData.cu:229
+        if ((kf && kf[k] != F) || kw[k] > FW || kh[k] > FH) return fail(FFTCONV_ERR_KERNEL_SHAPE, "%s", kMsgKernelShape);
+        refs[k].ptr = kernels[k];
+        refs[k].kh = kh[k];
+        refs[k].kw = kw[k];
+        refs[k].on_device = on_dev ? on_dev[k] != 0 : false;
+    }
+    return 0;
+}
+
+}  // namespace fftconv
+
+using namespace fftconv;
+
+// =================================================================================== C ABI
+extern "C" {
+
+int fftconv_fft_size16(int n) {            // src/cudaConvFFTData.h:96-102
+    const int mod = n / 16, rem = n % 16;
+    return mod * 16 + (rem > 0 ? 16 : 0);
+}
+
+int fftconv_fft_size_pow2(int n) {         // src/cudaConvFFTData.h:67-94
+    n = (n % 16 != 0) ? (n - n % 16 + 16) : n;
+    int hi;
+    for (hi = 31; hi >= 0; --hi)
+        if ((unsigned)n & (1u << hi)) break;
+    const unsigned low = 1u << hi;
+    if (low == (unsigned)n) return n;
+    return (int)(1u << (hi + 1));
+}
+
+static int fft_data_impl(const float* data, int data_on_device, int H, int W, int F, int KH, int KW,
+                         int pad_mode, int kernel_y, int kernel_x, fftconv_float2* d_spec, int device, void* stream) {
+    g_err.clear();
+    if (!data || !d_spec || H <= 0 || W <= 0 || F <= 0 || KH <= 0 || KW <= 0)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    Ctx* c;
+    if (int e = ctx_get(device, &c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int FH = fftconv_fft_size16(H + KH - 1), FW = fftconv_fft_size16(W + KW - 1);
+    const float* d_data = data;
+    if (!data_on_device) {
+        const size_t bytes = sizeof(float) * (size_t)H * W * F;
+        if (int e = dev_reserve(c->ddata, bytes)) return e;
+        CU(cudaMemcpyAsync(c->ddata.p, data, bytes, cudaMemcpyHostToDevice, st));
+        d_data = (const float*)c->ddata.p;
+    }
+    if (int e = run_fft_data(*c, d_data, H, W, F, FH, FW, pad_mode, kernel_y, kernel_x, (cpx*)d_spec, st)) return e;
+    if (!data_on_device) CU(cudaStreamSynchronize(st));    // src/cudaFFTData.cu:147
+    return 0;
+}
+
+int fftconv_fft_data(const float* data, int data_on_device, int H, int W, int F, int KH, int KW,
+                     fftconv_float2* d_spec, int device, void* stream) {
+    return fft_data_impl(data, data_on_device, H, W, F, KH, KW, PAD_ZERO, 0, 0, d_spec, device, stream);
+}
+
+int fftconv_fft_data_clamp(const float* data, int data_on_device, int H, int W, int F, int KH, int KW,
+                           int kernel_y, int kernel_x, fftconv_float2* d_spec, int device, void* stream) {
+    if (kernel_y < 0 || kernel_x < 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    return fft_data_impl(data, data_on_device, H, W, F, KH, KW, PAD_CLAMP, kernel_y, kernel_x, d_spec, device, stream);
+}
+
+static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* const* kernels,
+                     const int* kh, const int* kw, const int* kf, const unsigned char* kernel_on_device,
+                     float* const* outs, int out_on_device, const double* threads, int nthreads,
+                     const fftconv_options* opt, int device, void* stream, bool pipelined) {
+    g_err.clear();
+    if (!d_spec) return fail(FFTCONV_ERR_NOT_GPU_ARRAY, "The data must be FFT-ed real array in GPU");
+    if (CH < 2 || FW <= 0 || F <= 0 || (K > 0 && !outs)) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    if (int e = check_threads(threads, nthreads)) return e;
+    const int FH = (CH - 1) * 2;
+    if (FH % 16 != 0 || FW % 16 != 0)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "spectrum dims (%d x %d) do not come from computeFFTsize16", CH, FW);
+    std::vector<KernelRef> refs;
+    if (int e = build_kernel_refs(K, kernels, kh, kw, kf, kernel_on_device, F, FH, FW, refs)) return e;
+    for (int k = 0; k < K; ++k)
+        if (!outs[k]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    Ctx* c;
+    if (int e = ctx_get(device, &c)) return e;
+    ConvArgs a;
+    a.d_spec = (const cpx*)d_spec; a.CH = CH; a.FW = FW; a.F = F; a.K = K;
+    a.kernels = refs.data(); a.outs = outs; a.out_on_device = out_on_device != 0;
+    a.opt = opt ? *opt : fftconv_options{};
+    a.pipelined = pipelined;
+    return run_conv(*c, a, (cudaStream_t)stream);
+}
+
+int fftconv_conv_fft_data(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* const* kernels,
+                          const int* kh, const int* kw, const int* kf, const unsigned char* kernel_on_device,
+                          float* const* outs, int out_on_device, const double* threads, int nthreads,
+                          const fftconv_options* opt, int device, void* stream) {
+    return conv_impl(d_spec, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs, out_on_device, threads,
+                     nthreads, opt, device, stream, false);
+}
+
+int fftconv_conv_fft_data_streams(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
+                                  const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                                  float* const* outs, const double* threads, int nthreads,
+                                  const fftconv_options* opt, int device) {
+    return conv_impl(d_spec, CH, FW, F, K, kernels, kh, kw, kf, nullptr, outs, 0, threads, nthreads, opt, device,
+                     nullptr, true);
+}
+
+int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W, int F, int maxKH, int maxKW, int K,
+                            const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                            const unsigned char* kernel_on_device, float* const* outs, int out_on_device,
+                            const double* threads, int nthreads, const fftconv_options* opt, int device, void* stream) {
+    g_err.clear();
+    if (!data || H <= 0 || W <= 0 || F <= 0 || maxKH <= 0 || maxKW <= 0)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
+    if (int e = check_threads(threads, nthreads)) return e;
+    const int FH = fftconv_fft_size16(H + maxKH - 1), FW = fftconv_fft_size16(W + maxKW - 1);   // :109-112
+    const int CH = FH / 2 + 1;
+    void* spec = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        DeviceGuard guard(device);
+        if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+        Ctx* c;
+        if (int e = ctx_get(device, &c)) return e;
+        if (int e = dev_reserve(c->dspec, sizeof(cpx) * (size_t)CH * FW * F)) return e;
+        spec = c->dspec.p;
+    }
+    // stream-ordered: no sync between the data transform and the bank loop (the reference
+    // synchronises the device here, src/cudaConvolutionFFT.cu:168)
+    int e = fft_data_impl(data, data_on_device, H, W, F, maxKH, maxKW, PAD_ZERO, 0, 0, (fftconv_float2*)spec, device, stream);
+    if (e) return e;
+    return conv_impl((const fftconv_float2*)spec, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs,
+                     out_on_device, threads, nthreads, opt, device, stream, false);
+}
+
+int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* d_bank, int kh, int kw,
+                      float* d_out, const fftconv_options* opt, int device, void* stream) {
+    g_err.clear();
+    if (!d_bank || !d_out || K < 0 || kh <= 0 || kw <= 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    const int FH = (CH - 1) * 2;
+    fftconv_options o = opt ? *opt : fftconv_options{};
+    const int crop_h = o.crop_h > 0 ? o.crop_h : FH, crop_w = o.crop_w > 0 ? o.crop_w : FW;
+    const size_t plane = (size_t)crop_w * (o.out_ld > 0 ? o.out_ld : crop_h);
+    std::vector<const float*> kp(K);
+    std::vector<float*> op(K);
+    std::vector<int> khs(K, kh), kws(K, kw);
+    std::vector<unsigned char> od(K, 1);
+    for (int k = 0; k < K; ++k) {
+        kp[k] = d_bank + (size_t)k * kh * kw * F;
+        op[k] = d_out + (size_t)k * plane;
+    }
+    return conv_impl(d_spec, CH, FW, F, K, kp.data(), khs.data(), kws.data(), nullptr, od.data(), op.data(), 1,
+                     nullptr, 0, &o, device, stream, false);
+}
+
+int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b, long long n, int device, void* stream) {
+    g_err.clear();
+    if (!d_a || !d_b || n < 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    Ctx* c;
+    if (int e = ctx_get(device, &c)) return e;
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 8);
+    modulate_and_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((cpx*)d_a, (const cpx*)d_b, n, 1.0f / (float)n);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+long long fftconv_launch_count(void) { return g_launches.load(); }
+
+long long fftconv_workspace_bytes(int device) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctx.find(device);
+    if (it == g_ctx.end()) return 0;
+    const Ctx& c = it->second;
+    size_t s = c.T.cap + c.Z.cap + c.stage.cap + c.desc.cap + c.outstage.cap + c.dspec.cap + c.ddata.cap +
+               c.priv.cap + c.Ag.cap + c.Wg.cap;
+    for (auto& kv : c.tw) s += sizeof(cpx) * (size_t)kv.first;
+    return (long long)s;
+}
+
+void fftconv_release(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (auto& kv : g_ctx) {
+        Ctx& c = kv.second;
+        if (!c.inited) continue;
+        cudaSetDevice(c.dev);
+        cudaDeviceSynchronize();
+        for (auto& t : c.tw) cudaFree(t.second);
+        for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg})
+            if (b->p) cudaFree(b->p);
+        if (c.pinned) cudaFreeHost(c.pinned);
+        if (c.pinned_free) cudaEventDestroy(c.pinned_free);
+        for (auto& e : c.ev) if (e) cudaEventDestroy(e);
+        if (c.side) cudaStreamDestroy(c.side);
+    }
+    g_ctx.clear();
+    if (prev >= 0) cudaSetDevice(prev);
+}
+
+const char* fftconv_last_error(void) { return g_err.c_str(); }
+const char* fftconv_version(void) { return "fftconv-b200 0.1.0 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,401 @@
+"""Host-side mirror of the reference's MEX interface over the C ABI of libfftconv.so.
+
+Same function names, argument order, argument meaning and error behaviour as the MEX entry
+points of chrischoy/CUDA-FFT-Convolution:
+
+    cudaFFTData(data, kernelH, kernelW)                       src/cudaFFTData.cu:18-160
+    cudaConvFFTData(fftData, kernelCell[, threads])           src/cudaConvFFTData.cu:24-306
+    cudaConvolutionFFT(data, maxKH, maxKW, kernelCell[, threads[, gpuId]])
+                                                              src/cudaConvolutionFFT.cu:27-311
+    cudaConvFFTDataStreams(fftData, kernelCell[, threads])    src/cudaConvFFTDataStreams.cu:121-522
+
+MATLAB arrays ``A(h, w, f)`` are numpy arrays of shape ``(H, W, F)`` (any memory order; they are
+marshalled to the reference's column-major memory = C-order ``[F][W][H]``).  A MATLAB ``gpuArray``
+is a :class:`GpuArray` (device memory held by a torch tensor — torch is only the allocator here).
+A cell array is a Python list.
+
+There is no CPU fallback: importing works without a GPU (so the symbol table can be checked),
+but every compute call needs the CUDA library and a B200 and raises otherwise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+__all__ = [
+    "FFTConvError", "GpuArray", "gpuArray", "gather", "computeFFTsize16", "computeFFTsize",
+    "cudaFFTData", "cudaConvFFTData", "cudaConvolutionFFT", "cudaConvFFTDataStreams",
+    "cudaFFTDataClamp", "modulateAndNormalize", "Options", "conv_bank", "fft_data_device",
+    "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS",
+]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfftconv.so")
+
+EXPORTED_SYMBOLS = [
+    "fftconv_fft_size16", "fftconv_fft_size_pow2", "fftconv_fft_data", "fftconv_fft_data_clamp",
+    "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
+    "fftconv_conv_bank", "fftconv_modulate_and_normalize", "fftconv_launch_count",
+    "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
+]
+
+# error ids / messages of the reference
+ERRID_FFTDATA = "parallel:gpu:mexGPUExample:InvalidInput"      # src/cudaFFTData.cu:28
+ERRID_CONV = "cudaConvFFTData:InvalidInput"                     # src/cudaConvFFTData.cu:47
+MSG_INVALID = "Invalid input to MEX file."                      # src/cudaFFTData.cu:29
+MSG_NOT_GPU = "The data must be FFT-ed real array in GPU"       # src/cudaConvFFTData.cu:69
+MSG_NOT_CELL = "Kernel must be a cell array"                    # src/cudaConvFFTData.cu:107
+MSG_KERNEL_TYPE = "Kernels must be of type float and have features larger than 1"   # :198
+MSG_WRONG_NARGS = "Wrong number of inputs"                      # src/cudaConvolutionFFT.cu:46
+MSG_INVALID_DATA = "Invalid data input"                         # src/cudaConvolutionFFT.cu:54
+
+
+class FFTConvError(RuntimeError):
+    """Raised where the MEX would call mexErrMsgIdAndTxt / mexErrMsgTxt (and for CUDA errors,
+    where the reference prints and calls exit(), src/cudaConvFFTData.h:6-29)."""
+
+    def __init__(self, identifier: str, message: str, code: int = -1):
+        super().__init__(f"{identifier}: {message}" if identifier else message)
+        self.identifier = identifier
+        self.message = message
+        self.code = code
+
+
+class Options(ctypes.Structure):
+    """fftconv_options (include/fftconv.h) — all zero = exact reference behaviour."""
+    _fields_ = [("correlate", ctypes.c_int), ("crop_h", ctypes.c_int), ("crop_w", ctypes.c_int),
+                ("out_ld", ctypes.c_int), ("force_generic", ctypes.c_int), ("reserved", ctypes.c_int * 3)]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load libfftconv.so (in-tree build).  Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FFTConvError("fftconv:LibraryMissing",
+                               f"{LIB_PATH} not found — build it with `make -C cuda-fft-convolution_b200/csrc` "
+                               "(or __graft_entry__.build()); there is no CPU fallback")
+        L = ctypes.CDLL(LIB_PATH)
+        c_int, c_vp, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong
+        L.fftconv_fft_size16.argtypes = [c_int]
+        L.fftconv_fft_size_pow2.argtypes = [c_int]
+        L.fftconv_fft_data.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
+        L.fftconv_fft_data_clamp.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
+        L.fftconv_conv_fft_data.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                            c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_conv_fft_data_streams.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                                    c_vp, c_vp, c_int, c_vp, c_int]
+        L.fftconv_convolution_fft.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                              c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_conv_bank.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]
+        L.fftconv_modulate_and_normalize.argtypes = [c_vp, c_vp, c_ll, c_int, c_vp]
+        L.fftconv_launch_count.restype = c_ll
+        L.fftconv_workspace_bytes.argtypes = [c_int]
+        L.fftconv_workspace_bytes.restype = c_ll
+        L.fftconv_release.restype = None
+        L.fftconv_last_error.restype = ctypes.c_char_p
+        L.fftconv_version.restype = ctypes.c_char_p
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().fftconv_last_error().decode()
+
+
+def launch_count() -> int:
+    return int(lib().fftconv_launch_count())
+
+
+def _check(rc: int, errid: str):
+    if rc != 0:
+        raise FFTConvError(errid if rc > -9 else "fftconv:CudaError", last_error(), rc)
+
+
+def computeFFTsize16(n: int) -> int:
+    """computeFFTsize16 — src/cudaConvFFTData.h:96-102 (through the C ABI)."""
+    return int(lib().fftconv_fft_size16(int(n)))
+
+
+def computeFFTsize(n: int) -> int:
+    """computeFFTsize — src/cudaConvFFTData.h:67-94."""
+    return int(lib().fftconv_fft_size_pow2(int(n)))
+
+
+# ----------------------------------------------------------------------------- gpuArray
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise FFTConvError("fftconv:NoGpu", "no CUDA device available — this engine has no CPU fallback")
+    return torch
+
+
+class GpuArray:
+    """Stand-in for a MATLAB gpuArray: `shape` is the MATLAB size, `tensor` the device memory in
+    column-major order (a torch tensor of the reversed shape)."""
+
+    def __init__(self, tensor, shape, is_complex: bool):
+        self.tensor = tensor
+        self.shape = tuple(int(s) for s in shape)
+        self.is_complex = is_complex
+
+    @property
+    def device_index(self) -> int:
+        return int(self.tensor.device.index or 0)
+
+    def data_ptr(self) -> int:
+        return int(self.tensor.data_ptr())
+
+    def gather(self) -> np.ndarray:
+        a = self.tensor.cpu().numpy()
+        return np.asfortranarray(a.transpose(*range(a.ndim - 1, -1, -1)))
+
+
+def gpuArray(a: np.ndarray, device: int = 0) -> GpuArray:
+    """MATLAB gpuArray(a): upload a host array, keeping MATLAB (column-major) semantics."""
+    torch = _torch()
+    a = np.asarray(a)
+    mem = np.ascontiguousarray(a.transpose(*range(a.ndim - 1, -1, -1)))
+    t = torch.from_numpy(mem).to(f"cuda:{device}")
+    return GpuArray(t, a.shape, np.iscomplexobj(a))
+
+
+def gather(g: GpuArray) -> np.ndarray:
+    return g.gather()
+
+
+def _as_single_3d(a, errid, msg) -> np.ndarray:
+    """MEX type/shape check (mxSINGLE_CLASS, 3 dims, not a gpuArray) then marshal to [F][W][H]."""
+    if isinstance(a, GpuArray) or not isinstance(a, np.ndarray) or a.ndim != 3 or a.dtype != np.float32:
+        raise FFTConvError(errid, msg)
+    return np.ascontiguousarray(a.transpose(2, 1, 0))
+
+
+def _stream_ptr(stream) -> Optional[int]:
+    if stream is None:
+        return None
+    return int(getattr(stream, "cuda_stream", stream))
+
+
+# --------------------------------------------------------------------------- cudaFFTData
+def cudaFFTData(*args) -> GpuArray:
+    """fftData = cudaFFTData(data, kernelH, kernelW)   — src/cudaFFTData.cu:18-160.
+
+    data: host single H x W x F (3-D required, gpuArray rejected, :49-54).
+    Returns a complex-single gpuArray of MATLAB size [(FFT_H/2+1), FFT_W, F] (:90-103)."""
+    if len(args) != 3:
+        raise FFTConvError(ERRID_FFTDATA, MSG_INVALID)
+    data, kh, kw = args
+    d = _as_single_3d(data, ERRID_FFTDATA, MSG_INVALID)
+    return _fft_data(d, int(kh), int(kw), 0)
+
+
+def cudaFFTDataClamp(data, kernelH, kernelW, kernelY, kernelX, device: int = 0) -> GpuArray:
+    """cudaFFTData with the clamp/wrap pad of the SDK padData (src/convolutionFFTkernel.cu:46-76)."""
+    d = _as_single_3d(data, ERRID_FFTDATA, MSG_INVALID)
+    return _fft_data(d, int(kernelH), int(kernelW), device, clamp=(int(kernelY), int(kernelX)))
+
+
+def _fft_data(d_fwh: np.ndarray, kh: int, kw: int, device: int, clamp=None) -> GpuArray:
+    torch = _torch()
+    L = lib()
+    F, W, H = d_fwh.shape
+    FH, FW = computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)
+    CH = FH // 2 + 1
+    with torch.cuda.device(device):
+        spec = torch.empty((F, FW, CH), dtype=torch.complex64, device=f"cuda:{device}")
+        st = torch.cuda.current_stream().cuda_stream
+        if clamp is None:
+            rc = L.fftconv_fft_data(d_fwh.ctypes.data, 0, H, W, F, kh, kw, spec.data_ptr(), device, st)
+        else:
+            rc = L.fftconv_fft_data_clamp(d_fwh.ctypes.data, 0, H, W, F, kh, kw, clamp[0], clamp[1],
+                                          spec.data_ptr(), device, st)
+    _check(rc, ERRID_FFTDATA)
+    return GpuArray(spec, (CH, FW, F), True)
+
+
+def fft_data_device(data_t, H: int, W: int, F: int, kh: int, kw: int, spec_t=None, stream=None):
+    """Extension: data already on the device (torch float32 tensor, memory [F][W][H]); stream-ordered."""
+    torch = _torch()
+    FH, FW = computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)
+    CH = FH // 2 + 1
+    dev = int(data_t.device.index or 0)
+    if spec_t is None:
+        spec_t = torch.empty((F, FW, CH), dtype=torch.complex64, device=data_t.device)
+    st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    rc = lib().fftconv_fft_data(data_t.data_ptr(), 1, H, W, F, kh, kw, spec_t.data_ptr(), dev, st)
+    _check(rc, ERRID_FFTDATA)
+    return spec_t
+
+
+# ----------------------------------------------------------------------- kernel marshalling
+class _Cell:
+    """Marshals a kernel cell (list) into the pointer/size arrays of the C ABI."""
+
+    def __init__(self, cell, F_expected: Optional[int], allow_gpu: bool = True):
+        if not isinstance(cell, (list, tuple)):
+            raise FFTConvError(ERRID_CONV, MSG_NOT_CELL)
+        K = len(cell)
+        self.K = K
+        self.keep = []
+        self.ptrs = (ctypes.c_void_p * max(K, 1))()
+        self.kh = (ctypes.c_int * max(K, 1))()
+        self.kw = (ctypes.c_int * max(K, 1))()
+        self.kf = (ctypes.c_int * max(K, 1))()
+        self.on_dev = (ctypes.c_ubyte * max(K, 1))()
+        host = []
+        for k, ker in enumerate(cell):
+            if isinstance(ker, GpuArray):
+                if not allow_gpu or ker.is_complex or len(ker.shape) != 3 or str(ker.tensor.dtype) != "torch.float32":
+                    raise FFTConvError(ERRID_CONV, MSG_KERNEL_TYPE)
+                self.keep.append(ker.tensor)
+                self.ptrs[k] = ker.data_ptr()
+                self.kh[k], self.kw[k], self.kf[k] = ker.shape
+                self.on_dev[k] = 1
+            else:
+                if not isinstance(ker, np.ndarray) or ker.dtype != np.float32 or ker.ndim != 3:
+                    raise FFTConvError(ERRID_CONV, MSG_KERNEL_TYPE)      # src/cudaConvFFTData.cu:197-198
+                self.kh[k], self.kw[k], self.kf[k] = ker.shape
+                host.append((k, ker))
+        # host kernels are packed back to back so the library uploads them with one copy
+        if host:
+            total = sum(int(ker.size) for _, ker in host)
+            pack = np.empty(total, dtype=np.float32)
+            off = 0
+            for k, ker in host:
+                n = int(ker.size)
+                pack[off:off + n] = ker.transpose(2, 1, 0).ravel()
+                self.ptrs[k] = pack.ctypes.data + 4 * off
+                off += n
+            self.keep.append(pack)
+
+
+def _threads_arg(threads):
+    if threads is None:
+        return None, 0
+    t = np.ascontiguousarray(np.asarray(threads, dtype=np.float64).ravel())
+    return t, int(t.size)
+
+
+def _alloc_outs(K: int, FH: int, FW: int):
+    outs = np.empty((K, FW, FH), dtype=np.float32)
+    ptrs = (ctypes.c_void_p * max(K, 1))()
+    for k in range(K):
+        ptrs[k] = outs.ctypes.data + 4 * k * FW * FH
+    return outs, ptrs
+
+
+def _wrap_outs(outs: np.ndarray) -> List[np.ndarray]:
+    # [FW][FH] memory == MATLAB (FH, FW) column-major
+    return [outs[k].T for k in range(outs.shape[0])]
+
+
+# ------------------------------------------------------------------------ cudaConvFFTData
+def cudaConvFFTData(*args, options: Optional[Options] = None) -> List[np.ndarray]:
+    """cvcell = cudaConvFFTData(fftData, kernelCell[, threads])  — src/cudaConvFFTData.cu:24-306.
+
+    fftData must be a gpuArray (:68); kernelCell a cell of single 3-D arrays kh x kw x F, host or
+    gpuArray, sizes may differ per cell (:194-231); optional 4-vector of thread-block sizes (:71-81,
+    validated and ignored).  Returns a 1 x K list of host single (FFT_H, FFT_W) arrays (:111,275-279)."""
+    return _conv_fft_data(args, options, streams=False)
+
+
+def cudaConvFFTDataStreams(*args, options: Optional[Options] = None) -> List[np.ndarray]:
+    """Same contract as cudaConvFFTData, host kernels only — src/cudaConvFFTDataStreams.cu:121-522."""
+    return _conv_fft_data(args, options, streams=True)
+
+
+def _conv_fft_data(args, options, streams: bool):
+    if len(args) < 2 or len(args) > 3 or not isinstance(args[0], GpuArray):
+        raise FFTConvError(ERRID_CONV if not streams else ERRID_FFTDATA, MSG_NOT_GPU)
+    spec, cell = args[0], args[1]
+    threads, nthreads = _threads_arg(args[2] if len(args) == 3 else None)
+    if len(args) == 3 and nthreads != 4:
+        _check(lib().fftconv_conv_fft_data(spec.data_ptr(), 2, 16, 1, 0, None, None, None, None, None, None, 0,
+                                           threads.ctypes.data, nthreads, None, 0, None), ERRID_CONV)
+    CH, FW, F = spec.shape                         # :92-98
+    FH = (CH - 1) * 2
+    c = _Cell(cell, F, allow_gpu=not streams)
+    outs, optrs = _alloc_outs(c.K, FH, FW)
+    L = lib()
+    torch = _torch()
+    dev = spec.device_index
+    tp = threads.ctypes.data if threads is not None else None
+    op = ctypes.byref(options) if options is not None else None
+    with torch.cuda.device(dev):
+        if streams:
+            rc = L.fftconv_conv_fft_data_streams(spec.data_ptr(), CH, FW, F, c.K, c.ptrs, c.kh, c.kw, c.kf,
+                                                 optrs, tp, nthreads, op, dev)
+        else:
+            st = torch.cuda.current_stream().cuda_stream
+            rc = L.fftconv_conv_fft_data(spec.data_ptr(), CH, FW, F, c.K, c.ptrs, c.kh, c.kw, c.kf, c.on_dev,
+                                         optrs, 0, tp, nthreads, op, dev, st)
+    _check(rc, ERRID_CONV)
+    return _wrap_outs(outs)
+
+
+# ---------------------------------------------------------------------- cudaConvolutionFFT
+def cudaConvolutionFFT(*args, options: Optional[Options] = None) -> List[np.ndarray]:
+    """cvcell = cudaConvolutionFFT(data, maxKH, maxKW, kernelCell[, threads[, gpuId]])
+    — src/cudaConvolutionFFT.cu:27-311 (gpuId is 0-based, :84-89)."""
+    if len(args) < 4 or len(args) > 6:
+        raise FFTConvError(ERRID_CONV, MSG_WRONG_NARGS)          # :45-46
+    data, max_kh, max_kw, cell = args[:4]
+    d = _as_single_3d(data, "", MSG_INVALID_DATA)                # :50-54 (mexErrMsgTxt: no id)
+    if not isinstance(cell, (list, tuple)):
+        raise FFTConvError(ERRID_CONV, MSG_NOT_CELL)             # :64-65
+    threads, nthreads = _threads_arg(args[4] if len(args) > 4 else None)
+    gpu = int(args[5]) if len(args) > 5 else 0
+    F, W, H = d.shape
+    FH, FW = computeFFTsize16(H + int(max_kh) - 1), computeFFTsize16(W + int(max_kw) - 1)
+    L = lib()
+    tp = threads.ctypes.data if threads is not None else None
+    if threads is not None and nthreads != 4:
+        _check(L.fftconv_convolution_fft(d.ctypes.data, 0, H, W, F, int(max_kh), int(max_kw), 0, None, None, None,
+                                         None, None, None, 0, tp, nthreads, None, gpu, None), ERRID_CONV)
+    c = _Cell(cell, F)
+    outs, optrs = _alloc_outs(c.K, FH, FW)
+    torch = _torch()
+    op = ctypes.byref(options) if options is not None else None
+    with torch.cuda.device(gpu):
+        st = torch.cuda.current_stream().cuda_stream
+        rc = L.fftconv_convolution_fft(d.ctypes.data, 0, H, W, F, int(max_kh), int(max_kw), c.K, c.ptrs, c.kh, c.kw,
+                                       c.kf, c.on_dev, optrs, 0, tp, nthreads, op, gpu, st)
+    _check(rc, ERRID_CONV)
+    return _wrap_outs(outs)
+
+
+# ------------------------------------------------------------------------------ extensions
+def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Options] = None, stream=None):
+    """Device-resident bank: spec_t complex64 [F][FW][CH], bank_t float32 [K][F][kw][kh] (torch, cuda).
+    Writes K planes [FW][FH] (or the crop) into out_t; stream-ordered, no host sync."""
+    torch = _torch()
+    F, FW, CH = spec_t.shape
+    FH = (CH - 1) * 2
+    K = int(bank_t.shape[0])
+    dev = int(spec_t.device.index or 0)
+    if out_t is None:
+        ch = options.crop_h if options is not None and options.crop_h > 0 else FH
+        cw = options.crop_w if options is not None and options.crop_w > 0 else FW
+        ld = options.out_ld if options is not None and options.out_ld > 0 else ch
+        out_t = torch.empty((K, cw, ld), dtype=torch.float32, device=spec_t.device)
+    st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    op = ctypes.byref(options) if options is not None else None
+    rc = lib().fftconv_conv_bank(spec_t.data_ptr(), CH, FW, F, K, bank_t.data_ptr(), kh, kw, out_t.data_ptr(), op, dev, st)
+    _check(rc, ERRID_CONV)
+    return out_t
+
+
+def modulateAndNormalize(a: GpuArray, b: GpuArray) -> None:
+    """In place a = a .* b / numel(a)  — modulateAndNormalize, src/convolutionFFTkernel.cu:84-100."""
+    torch = _torch()
+    n = int(a.tensor.numel())
+    dev = a.device_index
+    rc = lib().fftconv_modulate_and_normalize(a.data_ptr(), b.data_ptr(), n, dev, torch.cuda.current_stream(dev).cuda_stream)
+    _check(rc, ERRID_CONV)

@@ -1,0 +1,133 @@
+/* fftconv.h — C ABI of the B200-native FFT-convolution engine (libfftconv.so).
+ *
+ * Drop-in boundary for the hot path of chrischoy/CUDA-FFT-Convolution.  Every entry point
+ * below replaces one MEX entry point of the reference (file:line cited per function); the
+ * MEX shims in cuda-fft-convolution_b200/mex/ and the stand-alone C++ harness only marshal
+ * arguments and call these.  Plain pointers and sizes only — no torch / MATLAB types.
+ *
+ * Memory layouts are the reference's (MATLAB column-major, h contiguous,
+ * src/cudaConvFFTData.cuh:26-27):
+ *     data      H x W x F   fp32  = C array [F][W][H]
+ *     kernel    kh x kw x F fp32  = C array [F][kw][kh]
+ *     spectrum  CH x FW x F complex fp32 (interleaved) = C array [F][FW][CH], CH = FH/2+1
+ *               (exactly what cufftPlanMany(n={FW,FH}, R2C, batch=F) writes,
+ *                src/cudaFFTData.cu:128-146)
+ *     output    FH x FW fp32 per kernel = C array [FW][FH]; the full linear convolution
+ *               sum_f conv2(D_f, k_f) sits top-left, the rest of the plane is ~0
+ *               (src/cudaConvFFTData.cu:111,186-188,275-279).  No flip, no crop.
+ *     FH = fftconv_fft_size16(H + KH - 1), FW = fftconv_fft_size16(W + KW - 1).
+ *
+ * Return value: 0 on success, a negative FFTCONV_ERR_* otherwise; the message is available
+ * from fftconv_last_error().  The library never calls exit() (the reference does,
+ * src/cudaConvFFTData.h:6-29) and never falls back to a CPU path.
+ *
+ * Synchronisation: when any output (or the stream argument) lives on the host side, i.e.
+ * out_on_device == 0, the call returns after the results are in the host buffers (MEX
+ * semantics).  With device outputs the call is stream-ordered on `stream` (a cudaStream_t
+ * passed as void*, NULL = legacy default stream) and returns without synchronising.
+ */
+#ifndef FFTCONV_H_
+#define FFTCONV_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFTCONV_OK                 0
+#define FFTCONV_ERR_INVALID_INPUT  (-1)  /* "Invalid input to MEX file." src/cudaFFTData.cu:28-29,49-54 */
+#define FFTCONV_ERR_NOT_CELL       (-2)  /* "Kernel must be a cell array" src/cudaConvFFTData.cu:106-107 (raised by the shims) */
+#define FFTCONV_ERR_THREAD_SIZE    (-3)  /* "CUDA Thread Size must be 4 integers ..." src/cudaConvFFTData.cu:71-72 */
+#define FFTCONV_ERR_KERNEL_TYPE    (-4)  /* "Kernels must be of type float and have features larger than 1" :197-198 (shims) */
+#define FFTCONV_ERR_KERNEL_SHAPE   (-5)  /* "Kernel and Data must have the same number of features and kernel size should be smaller than data size" :229-230 */
+#define FFTCONV_ERR_NOT_GPU_ARRAY  (-6)  /* "The data must be FFT-ed real array in GPU" :68-69 */
+#define FFTCONV_ERR_UNSUPPORTED    (-9)  /* plane larger than this build supports */
+#define FFTCONV_ERR_CUDA           (-10) /* a CUDA runtime call failed (reference: printf + exit) */
+
+typedef struct fftconv_float2 { float x, y; } fftconv_float2;
+
+/* Extension block (all zero = exact reference behaviour). */
+typedef struct fftconv_options {
+    int correlate;   /* 1: multiply by conj(kernel spectrum) = built-in flip
+                        (complexConjMulAndScale, src/cudaConvFFTData.cuh:42-45,63)            */
+    int crop_h;      /* >0: store only the first crop_h rows ...                              */
+    int crop_w;      /* ... and crop_w columns of each plane (demoCudaConvolutionFFT.m:149)   */
+    int out_ld;      /* leading dimension (floats) of a stored column; 0 = crop_h or FH       */
+    int force_generic; /* 1: bypass the 16-point-tiled fast path (testing)                    */
+    int reserved[3];
+} fftconv_options;
+
+/* computeFFTsize16 — src/cudaConvFFTData.h:96-102.  Part of the API contract. */
+int fftconv_fft_size16(int n);
+/* computeFFTsize (power-of-two rule; unused by the reference) — src/cudaConvFFTData.h:67-94 */
+int fftconv_fft_size_pow2(int n);
+
+/* cudaFFTData — src/cudaFFTData.cu:18-160.
+ * data: H x W x F fp32 (host if data_on_device == 0; the MEX requires host, :49-54).
+ * d_spec: caller-allocated DEVICE buffer of CH*FW*F complex (the gpuArray of :90-103).  */
+int fftconv_fft_data(const float* data, int data_on_device, int H, int W, int F,
+                     int KH, int KW, fftconv_float2* d_spec, int device, void* stream);
+
+/* Same, with the clamp-to-edge / wrap padding of the SDK padData
+ * (src/convolutionFFTkernel.cu:46-76): index i < n -> i; n <= i < n+kernelOfs -> n-1; else 0. */
+int fftconv_fft_data_clamp(const float* data, int data_on_device, int H, int W, int F,
+                           int KH, int KW, int kernel_y, int kernel_x,
+                           fftconv_float2* d_spec, int device, void* stream);
+
+/* cudaConvFFTData — src/cudaConvFFTData.cu:24-306 (hot loop :191-282).
+ * d_spec: device spectrum [F][FW][CH].  kernels[k]: kh[k] x kw[k] x F fp32, on the device
+ * iff kernel_on_device[k] (NULL = all host).  kf: per-kernel feature count for the F check
+ * of :229 (NULL = F).  outs[k]: FH*FW floats each, all host or all device.
+ * threads: optional 4-vector accepted for call compatibility (:71-81); only its length is
+ * validated, the engine picks its own tiling.  opt may be NULL. */
+int fftconv_conv_fft_data(const fftconv_float2* d_spec, int CH, int FW, int F,
+                          int K, const float* const* kernels, const int* kh, const int* kw,
+                          const int* kf, const unsigned char* kernel_on_device,
+                          float* const* outs, int out_on_device,
+                          const double* threads, int nthreads,
+                          const fftconv_options* opt, int device, void* stream);
+
+/* cudaConvFFTDataStreams — src/cudaConvFFTDataStreams.cu:121-522.  Same contract as
+ * cudaConvFFTData, host kernels only (:352-374).  The reference's 2-stream round-robin
+ * (:292-328,:338-469) is rebuilt as a chunked copy/compute pipeline over the kernel bank. */
+int fftconv_conv_fft_data_streams(const fftconv_float2* d_spec, int CH, int FW, int F,
+                                  int K, const float* const* kernels, const int* kh, const int* kw,
+                                  const int* kf, float* const* outs,
+                                  const double* threads, int nthreads,
+                                  const fftconv_options* opt, int device);
+
+/* cudaConvolutionFFT — src/cudaConvolutionFFT.cu:27-311: both calls fused, data on the host
+ * (:51-54), optional thread vector (:71-82) and 0-based GPU id (:84-89). */
+int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W, int F,
+                            int maxKH, int maxKW,
+                            int K, const float* const* kernels, const int* kh, const int* kw,
+                            const int* kf, const unsigned char* kernel_on_device,
+                            float* const* outs, int out_on_device,
+                            const double* threads, int nthreads,
+                            const fftconv_options* opt, int device, void* stream);
+
+/* Extension: device-resident packed bank, K kernels of identical kh x kw x F stored back to
+ * back; K output planes stored back to back in d_out (plane stride = FW*FH floats, or
+ * crop_w*out_ld with opt->crop_*).  Stream-ordered, no host synchronisation. */
+int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F,
+                      int K, const float* d_bank, int kh, int kw,
+                      float* d_out, const fftconv_options* opt, int device, void* stream);
+
+/* modulateAndNormalize — src/convolutionFFTkernel.cu:84-100: in place a = a*b/dataN. */
+int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
+                                   long long n, int device, void* stream);
+
+/* Number of kernel launches issued by this library since load (bench accounting). */
+long long fftconv_launch_count(void);
+/* Bytes of device scratch currently held by the cached workspace on `device`. */
+long long fftconv_workspace_bytes(int device);
+/* Drop cached plans / scratch (all devices). */
+void fftconv_release(void);
+/* Last error message of the calling thread ("" if none). */
+const char* fftconv_last_error(void);
+/* "fftconv-b200 <version> sm_100a" */
+const char* fftconv_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFTCONV_H_ */

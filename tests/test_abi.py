@@ -1,0 +1,88 @@
+"""CPU tests of the boundary: libfftconv.so loads, exports every symbol include/fftconv.h
+declares, and the argument checks that do not need a device behave like the reference."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "fftconv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fftconv_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(fc):
+    L = fc.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/fftconv.h but not exported"
+    assert sorted(fc.EXPORTED_SYMBOLS) == declared
+    assert b"sm_100a" in L.fftconv_version()
+
+
+def test_fft_size16_through_abi(fc, oracle):
+    for n in list(range(1, 600)) + [4095, 4096, 4607, 4608, 4609]:
+        assert fc.computeFFTsize16(n) == oracle.compute_fft_size16(n)
+    for n in (1, 16, 17, 73, 100, 512, 513, 1000):
+        assert fc.computeFFTsize(n) == oracle.compute_fft_size_pow2(n)
+
+
+def test_argument_errors_without_device(fc):
+    L = fc.lib()
+    # null spectrum -> "The data must be FFT-ed real array in GPU" (src/cudaConvFFTData.cu:68-69)
+    rc = L.fftconv_conv_fft_data(None, 9, 16, 1, 0, None, None, None, None, None, None, 0, None, 0, None, 0, None)
+    assert rc == -6 and "FFT-ed real array in GPU" in fc.last_error()
+    # thread vector with != 4 entries (src/cudaConvFFTData.cu:71-72)
+    t = (ctypes.c_double * 3)(8, 8, 8)
+    dummy = ctypes.c_void_p(16)
+    rc = L.fftconv_conv_fft_data(dummy, 9, 16, 1, 0, None, None, None, None, None, None, 0, t, 3, None, 0, None)
+    assert rc == -3 and "CUDA Thread Size must be 4 integers" in fc.last_error()
+    # invalid data
+    rc = L.fftconv_fft_data(None, 0, 4, 4, 1, 3, 3, None, 0, None)
+    assert rc == -1 and fc.last_error() == "Invalid input to MEX file."
+    # kernel with the wrong feature count / larger than the plane (src/cudaConvFFTData.cu:229-230)
+    kp = (ctypes.c_void_p * 1)(64)
+    op = (ctypes.c_void_p * 1)(64)
+    one = (ctypes.c_int * 1)
+    rc = L.fftconv_conv_fft_data(dummy, 9, 16, 2, 1, kp, one(3), one(3), one(5), None, op, 0, None, 0, None, 0, None)
+    assert rc == -5 and "same number of features" in fc.last_error()
+    rc = L.fftconv_conv_fft_data(dummy, 9, 16, 2, 1, kp, one(17), one(3), one(2), None, op, 0, None, 0, None, 0, None)
+    assert rc == -5
+
+
+def test_python_mirror_argument_errors(fc):
+    with pytest.raises(fc.FFTConvError) as e:
+        fc.cudaFFTData(np.zeros((4, 4), np.float32), 3, 3)           # not 3-D (src/cudaFFTData.cu:51)
+    assert e.value.identifier == "parallel:gpu:mexGPUExample:InvalidInput"
+    with pytest.raises(fc.FFTConvError):
+        fc.cudaFFTData(np.zeros((4, 4, 2), np.float64), 3, 3)        # not single
+    with pytest.raises(fc.FFTConvError):
+        fc.cudaFFTData(np.zeros((4, 4, 2), np.float32), 3)           # nrhs != 3
+    with pytest.raises(fc.FFTConvError) as e:
+        fc.cudaConvolutionFFT(np.zeros((4, 4, 2), np.float32), 3, 3)  # too few inputs
+    assert "Wrong number of inputs" in str(e.value)
+    with pytest.raises(fc.FFTConvError) as e:
+        fc.cudaConvolutionFFT(np.zeros((4, 4, 2), np.float32), 3, 3, np.zeros((3, 3, 2), np.float32))
+    assert "Kernel must be a cell array" in str(e.value)
+    with pytest.raises(fc.FFTConvError) as e:
+        fc.cudaConvFFTData(np.zeros((4, 4, 2), np.float32), [])       # spectrum must be a gpuArray
+    assert "FFT-ed real array in GPU" in str(e.value)
+    with pytest.raises(fc.FFTConvError) as e:
+        fc.cudaConvolutionFFT(np.zeros((4, 4, 2), np.float32), 3, 3, [], [8, 8, 8])
+    assert "CUDA Thread Size must be 4 integers" in str(e.value)
+
+
+def test_no_product_import_of_oracle():
+    """The product path must not route through the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "cuda-fft-convolution_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, fn
