@@ -153,7 +153,9 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(conv_w_pass_generic<false>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(conv_w_pass_generic<true>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(inv_h_pass)) return FFTCONV_ERR_CUDA;
-        if (tile16_opt_in()) return fail(FFTCONV_ERR_CUDA, "cudaFuncSetAttribute failed for the tile16 kernels");
+        if (opt_in_smem(tile16_conv<false>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(tile16_conv<true>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(tile16_c2r)) return FFTCONV_ERR_CUDA;
         c.inited = true;
     }
     *out = &c;
@@ -241,6 +243,106 @@ static int run_fft_data(Ctx& c, const float* d_data, int H, int W, int F, int FH
     fwd_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>((const cpx*)c.T.p, ncols, FW, CH, pW, twW,
                                                                      d_spec, TU, ldW);
     LAUNCH_CHECK();
+    return 0;
+}
+
+
+// ------------------------------------------------------------------ tile16 fast path (host)
+struct Tile16Cfg {
+    int mh, mw, NT, nya, nxa, XC, XCP, KB, nstage;
+    size_t dp_bytes, a_bytes, smem;
+};
+
+static bool tile16_config(int FH, int FW, int maxkh, int maxkw, Tile16Cfg& g) {
+    g.mh = FH / 16; g.mw = FW / 16; g.NT = g.mh / 2 + 1;
+    g.nya = (maxkh + 15) / 16; g.nxa = (maxkw + 15) / 16;
+    g.XC = 16 * g.nxa; g.XCP = g.XC + 2;
+    if (FW > 544 || g.nxa > 4 || g.nya > 16) return false;
+    g.KB = T16_MAX_THREADS / FW;                       // threads = KB*FW
+    if (g.KB < 1) return false;
+    if (g.KB > 8) g.KB = 8;
+    g.dp_bytes = (size_t)16 * g.mw * T16_PAD * sizeof(cpx);
+    g.a_bytes = (size_t)g.KB * 16 * g.XCP * sizeof(cpx);
+    const size_t y_bytes = 2 * (size_t)g.KB * 256 * (g.mw | 1) * sizeof(cpx);
+    for (g.nstage = 3; g.nstage >= 2; --g.nstage) {
+        const size_t pipe = (size_t)g.nstage * (g.dp_bytes + g.a_bytes);
+        g.smem = ((std::max(pipe, y_bytes) + 15) & ~(size_t)15) + 64;
+        if (g.smem <= kMaxSmem) return true;
+    }
+    return false;
+}
+
+static bool tile16_supported(int FH, int FW, int maxkh, int maxkw) {
+    Tile16Cfg g;
+    return tile16_config(FH, FW, maxkh, maxkw, g);
+}
+
+static size_t tile16_scratch_per_kernel(int FH, int FW, int F, int maxkh, int maxkw) {
+    Tile16Cfg g;
+    tile16_config(FH, FW, maxkh, maxkw, g);
+    return sizeof(cpx) * ((size_t)g.NT * F * 16 * g.XCP + (size_t)FW * g.NT * 16);
+}
+
+static int tile16_prepare(Ctx& c, const cpx* d_spec, int FH, int FW, int F, int maxkh, int maxkw, int KC,
+                          cudaStream_t st) {
+    Tile16Cfg g;
+    tile16_config(FH, FW, maxkh, maxkw, g);
+    const int NG = (KC + g.KB - 1) / g.KB;
+    if (int e = dev_reserve(c.Ag, (size_t)g.NT * NG * F * g.a_bytes)) return e;
+    if (int e = dev_reserve(c.Wg, sizeof(cpx) * (size_t)KC * FW * g.NT * 16)) return e;
+    const size_t dp_total = (size_t)g.NT * F * g.dp_bytes;
+    if (int e = dev_reserve(c.priv, dp_total)) return e;
+    const long long n = (long long)(dp_total / sizeof(cpx));
+    const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c.sm_count * 16);
+    tile16_relayout<<<grid, 256, 0, st>>>(d_spec, (cpx*)c.priv.p, F, FH, FW, FH / 2 + 1, g.mh, g.mw, g.NT);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int tile16_chunk(Ctx& c, int FH, int FW, int F, int maxkh, int maxkw, const SrcDesc* d_descs, int nk,
+                        float* const* d_outptrs, const fftconv_options& opt, cudaStream_t st) {
+    Tile16Cfg g;
+    tile16_config(FH, FW, maxkh, maxkw, g);
+    const cpx *twH, *twW, *twMw, *twMh;
+    if (int e = get_twiddles(c, FH, st, &twH)) return e;
+    if (int e = get_twiddles(c, FW, st, &twW)) return e;
+    if (int e = get_twiddles(c, g.mw, st, &twMw)) return e;
+    if (int e = get_twiddles(c, g.mh, st, &twMh)) return e;
+    const int NG = (nk + g.KB - 1) / g.KB;
+    // 1. template h transforms into the tile-major private layout
+    {
+        const long long total = (long long)nk * F * g.NT * g.XC;
+        tile16_kern_hpass<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d_descs, nk, F, FH, g.mh, g.NT, g.nya, g.XC,
+                                                                           g.KB, NG, twH, (cpx*)c.Ag.p);
+        LAUNCH_CHECK();
+    }
+    // 2. fused forward-w / multiply-accumulate / inverse-w / 16-point inverse-h
+    {
+        Tile16Params P;
+        P.Dp = (const cpx*)c.priv.p; P.Ag = (const cpx*)c.Ag.p; P.Wg = (cpx*)c.Wg.p;
+        P.twW = twW; P.twH = twH; P.twM = twMw; P.planM = make_line_plan(g.mw);
+        P.F = F; P.FH = FH; P.FW = FW; P.mh = g.mh; P.mw = g.mw; P.NT = g.NT; P.NG = NG; P.KB = g.KB;
+        P.nk = nk; P.nxa = g.nxa; P.nstage = g.nstage;
+        const int threads = ((g.KB * FW + 31) / 32) * 32;
+        dim3 grid(NG, g.NT);
+        if (opt.correlate) tile16_conv<true><<<grid, threads, g.smem, st>>>(P);
+        else tile16_conv<false><<<grid, threads, g.smem, st>>>(P);
+        LAUNCH_CHECK();
+    }
+    // 3. mh-point inverse along h, scale, crop, store
+    {
+        const int mhp = g.mh | 1;
+        int NP = (int)((64 * 1024) / (2 * 16 * (size_t)mhp * sizeof(cpx)));
+        NP = NP < 1 ? 1 : (NP > 8 ? 8 : NP);
+        const long long nlines = (long long)nk * (FW / 2);
+        const int crop_h = opt.crop_h > 0 ? opt.crop_h : FH;
+        const int crop_w = opt.crop_w > 0 ? opt.crop_w : FW;
+        const int out_ld = opt.out_ld > 0 ? opt.out_ld : crop_h;
+        tile16_c2r<<<(unsigned)((nlines + NP - 1) / NP), 256, 2 * (size_t)NP * 16 * mhp * sizeof(cpx), st>>>(
+            (const cpx*)c.Wg.p, nk, FH, FW, g.mh, g.NT, make_line_plan(g.mh), twMh, 1.0f / ((float)FW * (float)FH),
+            d_outptrs, crop_h, crop_w, out_ld, NP, mhp);
+        LAUNCH_CHECK();
+    }
     return 0;
 }
 
@@ -342,11 +444,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     if (!a.out_on_device) per_kernel += plane * sizeof(float);
     const size_t budget = (size_t)96 << 20;    // keep a chunk's intermediates L2-resident (126 MB L2)
     int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
-    if (tile16) KC = tile16_round_chunk(KC, K);
-
     if (tile16) {
-        if (int e = tile16_reserve(c.Ag, c.Wg, FH, FW, F, maxkh, maxkw, KC)) return e;
-        if (int e = tile16_prepare_spectrum(c.priv, a.d_spec, FH, FW, F, st)) return e;
+        if (int e = tile16_prepare(c, a.d_spec, FH, FW, F, maxkh, maxkw, KC, st)) return e;
     } else {
         if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)KC * F * maxkw * CH)) return e;
         if (int e = dev_reserve(c.Z, sizeof(cpx) * (size_t)KC * FW * CH)) return e;
@@ -416,8 +515,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (!a.out_on_device && chunk >= 2) CU(cudaStreamWaitEvent(st, c.ev[chunk & 1], 0));   // staging half free?
         int e;
         if (tile16)
-            e = tile16_chunk(c.Ag, c.Wg, c.priv, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0,
-                             a.opt, c.sm_count, st);
+            e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
             e = conv_generic_chunk(c, a, FH, d_desc + k0, d_kcols + k0, nk, maxkw, d_outp + k0, st);
         if (e) return e;
