@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the FFT-convolution hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1]
+
+A "step" is one pass of the hot path over one batch of synthetic input:
+    pad -> R2C FFT of the data -> [per template: pruned FFT, multiply, sum over channels,
+    inverse FFT, scale] -> one fp32 plane per template.
+Workload at N = 1 (BASELINE.json configs[1], the HOG-DPM case): one 31-channel 256x256 feature
+map x 1,000 templates of 16x16x31 -> 1,000 planes of 272x272.  With N > 1 every rank holds its
+own shard of 1,000 templates (weak scaling: the bank grows with N), rank 0 transforms the data
+and the spectrum is broadcast with NCCL inside the timed step.
+
+`value`   : conv outputs/s (pixels x kernels, whole job) with inputs already resident in HBM.
+`e2e`     : same metric through the C-ABI call with HOST (pinned) buffers, H2D and D2H inside
+            the timed region.
+`roofline`: dominant kernel (tile16_conv) timed with CUDA events on its launch stream.
+`cpu_baseline` / `--impl reference`: the reference's CPU path (demoCudaConvolutionFFT.m:76-102,
+            fft2/ifft2 and conv2) restated in oracle/ and timed on this host's cores.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "cuda-fft-convolution_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WORKLOADS = {
+    # name: (H, W, F, kh, kw, K per GPU, description)
+    "c2": (256, 256, 31, 16, 16, 1000, "HOG-DPM: 31-channel 256x256 feature map x 1000 templates 16x16x31 (BASELINE configs[1])"),
+    "c1": (64, 8, 5, 10, 4, 10, "demoCudaConvolutionFFT.m: 64x8x5 x 10 kernels 10x4x5 (BASELINE configs[0])"),
+}
+METRIC = "conv outputs/sec (pixels x kernels)"
+UNIT = "outputs/s"
+
+
+def fft16(n):
+    return (n // 16) * 16 + (16 if n % 16 else 0)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [x.strip() for x in r.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax = max(smax, float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- CPU reference
+def cpu_reference(workload: str, steps: int, warmup: int, sample_kernels: int = 0):
+    """The reference's CPU path restated (oracle/): fft2 .* fft2 -> ifft2 -> sum over channels
+    (demoCudaConvolutionFFT.m:78-102, multi-threaded pocketfft, fp32) and conv2 summed over
+    channels (:91-96, C + OpenMP).  Each step is a bounded sample of the workload."""
+    import oracle
+    H, W, F, kh, kw, K, desc = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    S = sample_kernels or (min(K, 32) if workload == "c2" else K)
+    rng = np.random.default_rng(2)
+    data = (rng.random((H, W, F), dtype=np.float32) * 0.2).astype(np.float32)
+    kernels = [(rng.standard_normal((kh, kw, F)) * 0.05).astype(np.float32) for _ in range(S)]
+    FH, FW = fft16(H + kh - 1), fft16(W + kw - 1)
+
+    def step_fft():
+        oracle.fft_conv_cpu(data, kh, kw, kernels, workers=cores)
+
+    def step_direct():
+        for k in kernels[: max(1, S // 4)]:
+            oracle.direct_conv64_c(data, k, FH, FW, threads=cores, f32=True)
+
+    for _ in range(max(1, min(warmup, 2))):
+        step_fft()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_fft()
+    t_fft = (time.perf_counter() - t0) / steps
+    step_direct()
+    t0 = time.perf_counter()
+    step_direct()
+    t_dir = (time.perf_counter() - t0)
+    v_fft = S * FH * FW / t_fft
+    v_dir = max(1, S // 4) * FH * FW / t_dir
+    best = max(v_fft, v_dir)
+    return {
+        "value": best, "unit": UNIT, "cores": cores, "kind": "port",
+        "sample": f"{S} of {K} templates per step (fft2/ifft2 path: {v_fft:.3e} outputs/s; conv2 direct path on "
+                  f"{max(1, S // 4)} templates: {v_dir:.3e} outputs/s); scipy.fft pocketfft workers={cores}, gcc -O3 OpenMP",
+        "ms_per_step": t_fft * 1e3 if v_fft >= v_dir else t_dir * 1e3,
+        "sample_kernels": S,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference(args.workload, max(1, args.steps), args.warmup)
+    H, W, F, kh, kw, K, desc = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": desc, "fft_plane": [fft16(H + kh - 1), fft16(W + kw - 1)],
+                   "note": "reference CPU path (MATLAB fft2/conv2 of demoCudaConvolutionFFT.m) restated in oracle/, "
+                           "timed on the host cores on a bounded sample of the same workload"},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import fftconv_b200 as fc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    H, W, F, kh, kw, K, desc = WORKLOADS[args.workload]
+    FH, FW = fft16(H + kh - 1), fft16(W + kw - 1)
+    CH = FH // 2 + 1
+    L = fc.lib()
+
+    # synthetic inputs (seed 2, data U[0,0.2), templates N(0,0.05)); shard = own seed
+    g = torch.Generator(device=dev).manual_seed(2)
+    data = (torch.rand((F, W, H), device=dev, generator=g) * 0.2).contiguous()
+    gk = torch.Generator(device=dev).manual_seed(1000 + rank)
+    bank = (torch.randn((K, F, kw, kh), device=dev, generator=gk) * 0.05).contiguous()
+    spec = torch.empty((F, FW, CH), dtype=torch.complex64, device=dev)
+    out = torch.empty((K, FW, FH), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step():
+        """data FFT (rank 0) -> [NCCL broadcast of the spectrum] -> bank convolution on every rank"""
+        if rank == 0:
+            fc.fft_data_device(data, H, W, F, kh, kw, spec_t=spec)
+        if dist is not None:
+            dist.broadcast(torch.view_as_real(spec), src=0)
+        fc.conv_bank(spec, bank, kh, kw, out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, each bracketed by CUDA events; L2 flushed (untimed) between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = fc.launch_count()
+    with ClockSampler(local) as clk:
+        barrier()
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            flush.zero_()
+            if dist is not None:
+                dist.barrier()
+            ev[i][0].record(stream)
+            step()
+            ev[i][1].record(stream)
+        barrier()
+        t_wall = time.perf_counter() - t_wall0
+    launches = fc.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    outputs_per_step = world * K * FH * FW
+    value = outputs_per_step / (ms_per_step * 1e-3)
+    clocks = clk.summary()
+
+    # ---- parity spot check of what was just timed (float64 FFT convolution on the device; the
+    # oracle proper is exercised by tests/ and smoke())
+    d64 = data.double()
+    ref = torch.fft.irfft2(torch.fft.rfft2(d64, s=(FW, FH)).unsqueeze(0) *
+                           torch.fft.rfft2(bank[:3].double(), s=(FW, FH)), s=(FW, FH)).sum(1)
+    rel_l2 = float((out[:3].double() - ref).norm() / ref.norm())
+    if not rel_l2 < 1e-5:
+        raise SystemExit(f"parity check failed inside bench: rel-L2 {rel_l2}")
+
+    # ---- roofline leg: per-kernel device time with CUDA events on the launch stream
+    fc.profile(True)
+    for _ in range(3):
+        flush.zero_()
+        step()
+    torch.cuda.synchronize()
+    prof = fc.profile_read()
+    fc.profile(False)
+    peak, peak_src = peaks()
+    dom = max(prof.items(), key=lambda kv: kv[1][0])
+    dom_name, (dom_ms, dom_n) = dom
+    launches_per_step = dom_n / 3
+    kernels_per_launch = K / launches_per_step
+    # algorithmic (compulsory) bytes per (image, template) pair, SURVEY 8(d): read the template once,
+    # write its plane once (+ the data spectrum amortised over the launch)
+    bytes_per_unit = 4 * kh * kw * F + 4 * FH * FW
+    alg_bytes_launch = bytes_per_unit * kernels_per_launch + 8 * CH * FW * F
+    dur_s = dom_ms / dom_n * 1e-3
+    achieved = alg_bytes_launch / dur_s / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom_name)
+    except Exception:
+        pass
+    nominal_flops = (F + K * F + K) * 2.5 * FH * FW * np.log2(FH * FW) + 8.0 * K * F * CH * FW
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "avg_launch_ms": dom_ms / dom_n, "launches_per_step": launches_per_step,
+        "algorithmic_bytes_per_launch": alg_bytes_launch,
+        "kernel_share_of_step": {k: v[0] / sum(x[0] for x in prof.values()) for k, v in prof.items()},
+        "fp32_note": "fused pipeline is fp32-FMA bound, not HBM bound (SURVEY 8d): nominal "
+                     f"{nominal_flops / 1e9:.1f} GFLOP/step (cuFFT convention) -> "
+                     f"{nominal_flops / (ms_per_step * 1e-3) / 1e12 * world:.2f} TFLOP/s nominal-equivalent "
+                     "vs 74.4 TFLOP/s fp32 peak",
+    }
+
+    # ---- e2e: the reference-facing C-ABI call with HOST (pinned) buffers, copies inside the timed region
+    h_data = torch.empty((F, W, H), dtype=torch.float32, pin_memory=True).copy_(data.cpu())
+    h_bank = torch.empty((K, F, kw, kh), dtype=torch.float32, pin_memory=True).copy_(bank.cpu())
+    h_out = torch.empty((K, FW, FH), dtype=torch.float32, pin_memory=True)
+    kp = (ctypes.c_void_p * K)(*[h_bank.data_ptr() + 4 * k * F * kw * kh for k in range(K)])
+    op = (ctypes.c_void_p * K)(*[h_out.data_ptr() + 4 * k * FW * FH for k in range(K)])
+    khs = (ctypes.c_int * K)(*([kh] * K))
+    kws = (ctypes.c_int * K)(*([kw] * K))
+    st = stream.cuda_stream
+
+    def e2e_step():
+        if world == 1:
+            rc = L.fftconv_convolution_fft(h_data.data_ptr(), 0, H, W, F, kh, kw, K, kp, khs, kws, None, None,
+                                           op, 0, None, 0, None, local, st)
+        else:
+            rc = 0
+            if rank == 0:
+                rc = L.fftconv_fft_data(h_data.data_ptr(), 0, H, W, F, kh, kw, spec.data_ptr(), local, st)
+            dist.broadcast(torch.view_as_real(spec), src=0)
+            rc = rc or L.fftconv_conv_fft_data(spec.data_ptr(), CH, FW, F, K, kp, khs, kws, None, None, op, 0,
+                                               None, 0, None, local, st)
+        if rc != 0:
+            raise SystemExit("e2e call failed: " + fc.last_error())
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(2, min(args.steps, 10))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_t.item()) / e2e_steps
+    e2e_rel = float((h_out[:3].double() - ref.cpu()).norm() / ref.cpu().norm())
+    if not e2e_rel < 1e-5:
+        raise SystemExit(f"e2e parity check failed: rel-L2 {e2e_rel}")
+    e2e = {"value": outputs_per_step / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": int(4 * H * W * F + world * 4 * K * F * kh * kw),
+           "d2h_bytes_per_step": int(world * 4 * K * FH * FW),
+           "api": "fftconv_convolution_fft (cudaConvolutionFFT) host->host" if world == 1 else
+                  "fftconv_fft_data + NCCL broadcast + fftconv_conv_fft_data, host->host",
+           "bound": "PCIe D2H of the output planes"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cb = cpu_reference(args.workload, 2, 1)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "templates_per_gpu": K, "fft_plane": [FH, FW], "outputs_per_step": outputs_per_step,
+                       "l2": "flushed between steps by an untimed 256 MiB memset; each step also writes "
+                             f"{4 * K * FH * FW / 1e6:.0f} MB of outputs (> 126 MB L2)",
+                       "parallelism": f"template bank sharded over {world} GPU(s), data spectrum "
+                                      + ("broadcast by NCCL inside the step" if world > 1 else "local"),
+                       "timing": "CUDA events per step on the launch stream, max over ranks",
+                       "rel_l2_vs_fp64": rel_l2},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--workload", args.workload] + (["--no-cpu"] if args.no_cpu else [])
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

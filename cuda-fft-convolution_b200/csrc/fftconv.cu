@@ -46,6 +46,25 @@ static int fail(int code, const char* fmt, ...) {
         CU(cudaGetLastError());                                                            \
     } while (0)
 
+// Optional per-kernel timing (bench.py roofline leg): every launch of a profiled kind is
+// bracketed by CUDA events on the stream it is launched on.
+enum ProfKind { PK_RELAYOUT = 0, PK_KERN_H, PK_CONV, PK_C2R, PK_DATA_H, PK_DATA_W, PK_GEN_H, PK_GEN_W, PK_GEN_C2R, PK_COUNT };
+static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass", "tile16_conv", "tile16_c2r",
+                                           "fwd_h_pass(data)", "fwd_w_pass(data)", "fwd_h_pass(kernels)",
+                                           "conv_w_pass_generic", "inv_h_pass"};
+static bool g_prof_on = false;
+struct ProfRec { int kind; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+    int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
+        if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (a) { cudaEventRecord(b, st); g_prof.push_back({kind, a, b}); }
+    }
+};
+
 static const char* kMsgThread =
     "CUDA Thread Size must be 4 integers : THREAD_PER_BLOCK_H, THREAD_PER_BLOCK_W, "
     "THREAD_PER_BLOCK_D, THREAD_PER_BLOCK_2D\nYou must choose size such that total thread will "
@@ -229,6 +248,8 @@ static int run_fft_data(Ctx& c, const float* d_data, int H, int W, int F, int FH
     const long long nlines = (long long)F * ((ncols + 1) / 2);
     const unsigned grid = (unsigned)((nlines + NL - 1) / NL);
     const size_t smemH = 2 * (size_t)NL * ldH * sizeof(cpx);
+    {
+    ProfScope ps(PK_DATA_H, st);
     if (pad_mode == PAD_CLAMP)
         fwd_h_pass<PAD_CLAMP><<<grid, 256, smemH, st>>>((const SrcDesc*)c.desc.p, 1, F, W, FH, CH, pH, twH,
                                                          (cpx*)c.T.p, NL, ldH, kernel_y, kernel_x, FW);
@@ -236,10 +257,12 @@ static int run_fft_data(Ctx& c, const float* d_data, int H, int W, int F, int FH
         fwd_h_pass<PAD_ZERO><<<grid, 256, smemH, st>>>((const SrcDesc*)c.desc.p, 1, F, W, FH, CH, pH, twH,
                                                         (cpx*)c.T.p, NL, ldH, 0, 0, W);
     LAUNCH_CHECK();
+    }
 
     int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
     TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
     dim3 g2((CH + TU - 1) / TU, F);
+    ProfScope ps(PK_DATA_W, st);
     fwd_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>((const cpx*)c.T.p, ncols, FW, CH, pW, twW,
                                                                      d_spec, TU, ldW);
     LAUNCH_CHECK();
@@ -249,27 +272,44 @@ static int run_fft_data(Ctx& c, const float* d_data, int H, int W, int F, int FH
 
 // ------------------------------------------------------------------ tile16 fast path (host)
 struct Tile16Cfg {
-    int mh, mw, NT, nya, nxa, XC, XCP, KB, nstage;
+    int mh, mw, NT, nya, nxa, XC, XCP, KB, nstage, nmain, nextra;
     size_t dp_bytes, a_bytes, smem;
 };
 
 static bool tile16_config(int FH, int FW, int maxkh, int maxkw, Tile16Cfg& g) {
+    g = Tile16Cfg{};
     g.mh = FH / 16; g.mw = FW / 16; g.NT = g.mh / 2 + 1;
     g.nya = (maxkh + 15) / 16; g.nxa = (maxkw + 15) / 16;
     g.XC = 16 * g.nxa; g.XCP = g.XC + 2;
     if (FW > 544 || g.nxa > 4 || g.nya > 16) return false;
-    g.KB = T16_MAX_THREADS / FW;                       // threads = KB*FW
-    if (g.KB < 1) return false;
-    if (g.KB > 8) g.KB = 8;
     g.dp_bytes = (size_t)16 * g.mw * T16_PAD * sizeof(cpx);
-    g.a_bytes = (size_t)g.KB * 16 * g.XCP * sizeof(cpx);
-    const size_t y_bytes = 2 * (size_t)g.KB * 256 * (g.mw | 1) * sizeof(cpx);
-    for (g.nstage = 3; g.nstage >= 2; --g.nstage) {
-        const size_t pipe = (size_t)g.nstage * (g.dp_bytes + g.a_bytes);
-        g.smem = ((std::max(pipe, y_bytes) + 15) & ~(size_t)15) + 64;
-        if (g.smem <= kMaxSmem) return true;
+    // pick the number of templates per CTA: 16 warps own `nmain` items in registers, the rest are
+    // dealt round-robin as `nextra` warp-passes per channel; maximise issue balance over the 4
+    // sub-partitions, then data-spectrum reuse (larger KB)
+    double best = -1.0;
+    for (int KB = 1; KB <= 8; ++KB) {
+        const int N = KB * 16 * g.mw;
+        int nmain, nextra, W;
+        if (N <= T16_THREADS) { nmain = N; nextra = 0; W = (N + 31) / 32; }
+        else { nmain = T16_THREADS; nextra = (N - T16_THREADS + 31) / 32; W = 16; }
+        if (nextra > 6) break;
+        const size_t a_bytes = (size_t)KB * 16 * g.XCP * sizeof(cpx);
+        const size_t y_bytes = 2 * (size_t)KB * 256 * (g.mw | 1) * sizeof(cpx);
+        int nstage = 0;
+        size_t smem = 0;
+        for (int ns = 4; ns >= 2; --ns) {
+            const size_t pipe = (size_t)ns * (g.dp_bytes + a_bytes);
+            const size_t tot = ((std::max(pipe, y_bytes) + 15) & ~(size_t)15) + 96 + (size_t)nextra * 512 * sizeof(cpx);
+            if (tot <= kMaxSmem) { nstage = ns; smem = tot; break; }
+        }
+        if (!nstage) continue;
+        const double eff = (N / 32.0) / (4.0 * ((W + 3) / 4 + nextra / 4.0)) + 1e-3 * KB;
+        if (eff > best) {
+            best = eff;
+            g.KB = KB; g.nmain = nmain; g.nextra = nextra; g.nstage = nstage; g.a_bytes = a_bytes; g.smem = smem;
+        }
     }
-    return false;
+    return best > 0.0;
 }
 
 static bool tile16_supported(int FH, int FW, int maxkh, int maxkw) {
@@ -294,6 +334,7 @@ static int tile16_prepare(Ctx& c, const cpx* d_spec, int FH, int FW, int F, int 
     if (int e = dev_reserve(c.priv, dp_total)) return e;
     const long long n = (long long)(dp_total / sizeof(cpx));
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c.sm_count * 16);
+    ProfScope ps(PK_RELAYOUT, st);
     tile16_relayout<<<grid, 256, 0, st>>>(d_spec, (cpx*)c.priv.p, F, FH, FW, FH / 2 + 1, g.mh, g.mw, g.NT);
     LAUNCH_CHECK();
     return 0;
@@ -312,6 +353,7 @@ static int tile16_chunk(Ctx& c, int FH, int FW, int F, int maxkh, int maxkw, con
     // 1. template h transforms into the tile-major private layout
     {
         const long long total = (long long)nk * F * g.NT * g.XC;
+        ProfScope ps(PK_KERN_H, st);
         tile16_kern_hpass<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d_descs, nk, F, FH, g.mh, g.NT, g.nya, g.XC,
                                                                            g.KB, NG, twH, (cpx*)c.Ag.p);
         LAUNCH_CHECK();
@@ -322,9 +364,10 @@ static int tile16_chunk(Ctx& c, int FH, int FW, int F, int maxkh, int maxkw, con
         P.Dp = (const cpx*)c.priv.p; P.Ag = (const cpx*)c.Ag.p; P.Wg = (cpx*)c.Wg.p;
         P.twW = twW; P.twH = twH; P.twM = twMw; P.planM = make_line_plan(g.mw);
         P.F = F; P.FH = FH; P.FW = FW; P.mh = g.mh; P.mw = g.mw; P.NT = g.NT; P.NG = NG; P.KB = g.KB;
-        P.nk = nk; P.nxa = g.nxa; P.nstage = g.nstage;
-        const int threads = ((g.KB * FW + 31) / 32) * 32;
+        P.nk = nk; P.nxa = g.nxa; P.nstage = g.nstage; P.nmain = g.nmain; P.nextra = g.nextra;
+        const int threads = ((g.nmain + 31) / 32) * 32;
         dim3 grid(NG, g.NT);
+        ProfScope ps(PK_CONV, st);
         if (opt.correlate) tile16_conv<true><<<grid, threads, g.smem, st>>>(P);
         else tile16_conv<false><<<grid, threads, g.smem, st>>>(P);
         LAUNCH_CHECK();
@@ -338,6 +381,7 @@ static int tile16_chunk(Ctx& c, int FH, int FW, int F, int maxkh, int maxkw, con
         const int crop_h = opt.crop_h > 0 ? opt.crop_h : FH;
         const int crop_w = opt.crop_w > 0 ? opt.crop_w : FW;
         const int out_ld = opt.out_ld > 0 ? opt.out_ld : crop_h;
+        ProfScope ps(PK_C2R, st);
         tile16_c2r<<<(unsigned)((nlines + NP - 1) / NP), 256, 2 * (size_t)NP * 16 * mhp * sizeof(cpx), st>>>(
             (const cpx*)c.Wg.p, nk, FH, FW, g.mh, g.NT, make_line_plan(g.mh), twMh, 1.0f / ((float)FW * (float)FH),
             d_outptrs, crop_h, crop_w, out_ld, NP, mhp);
@@ -377,6 +421,7 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
         const int NL = pick_lines(FH, 8);
         const long long nlines = (long long)nk * F * ((maxcols + 1) / 2);
         const unsigned grid = (unsigned)((nlines + NL - 1) / NL);
+        ProfScope ps(PK_GEN_H, st);
         fwd_h_pass<PAD_ZERO><<<grid, 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
             d_descs, nk, F, maxcols, FH, CH, pH, twH, (cpx*)c.T.p, NL, ldH, 0, 0, maxcols);
         LAUNCH_CHECK();
@@ -387,6 +432,7 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
         TU = TU < 1 ? 1 : (TU > 8 ? 8 : TU);
         dim3 grid((CH + TU - 1) / TU, nk);
         const size_t smem = 3 * (size_t)TU * ldW * sizeof(cpx);
+        ProfScope ps(PK_GEN_W, st);
         if (a.opt.correlate)
             conv_w_pass_generic<true><<<grid, 256, smem, st>>>((const cpx*)c.T.p, d_kcols, maxcols, a.d_spec, F, FW, CH,
                                                                pW, twW, (cpx*)c.Z.p, TU, ldW);
@@ -403,6 +449,7 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
         const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
         const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : FW;
         const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
+        ProfScope ps(PK_GEN_C2R, st);
         inv_h_pass<<<grid, 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
             (const cpx*)c.Z.p, nk, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_outptrs, crop_h, crop_w,
             out_ld, NL, ldH);
@@ -445,6 +492,22 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     const size_t budget = (size_t)96 << 20;    // keep a chunk's intermediates L2-resident (126 MB L2)
     int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
     if (tile16) {
+        // one CTA per SM: size the chunk so that NT * ceil(KC/KB) CTAs fill whole waves
+        Tile16Cfg g;
+        tile16_config(FH, FW, maxkh, maxkw, g);
+        const int per_wave = c.sm_count;
+        int best_kc = std::min(KC, K);
+        if (best_kc < K) {
+            for (int waves = 1; ; ++waves) {
+                const int ng = (waves * per_wave) / g.NT;
+                if (ng < 1) continue;
+                const int kc = ng * g.KB;
+                if (kc > KC) break;
+                best_kc = kc;
+            }
+            best_kc = std::max(best_kc, g.KB);
+        }
+        KC = best_kc;
         if (int e = tile16_prepare(c, a.d_spec, FH, FW, F, maxkh, maxkw, KC, st)) return e;
     } else {
         if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)KC * F * maxkw * CH)) return e;
@@ -730,6 +793,38 @@ int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_
 }
 
 long long fftconv_launch_count(void) { return g_launches.load(); }
+
+void fftconv_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_prof_on = on != 0;
+}
+
+int fftconv_profile_kinds(void) { return PK_COUNT; }
+const char* fftconv_profile_name(int kind) { return (kind >= 0 && kind < PK_COUNT) ? kProfNames[kind] : ""; }
+
+int fftconv_profile_read(int kind, double* total_ms, long long* launches, int reset) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    double ms = 0.0;
+    long long n = 0;
+    for (auto& r : g_prof) {
+        if (r.kind != kind) continue;
+        if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(FFTCONV_ERR_CUDA, "profile event sync failed");
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess) return fail(FFTCONV_ERR_CUDA, "profile event read failed");
+        ms += t; ++n;
+    }
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (reset) {
+        std::vector<ProfRec> keep;
+        for (auto& r : g_prof) {
+            if (r.kind == kind) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+            else keep.push_back(r);
+        }
+        g_prof.swap(keep);
+    }
+    return 0;
+}
 
 long long fftconv_workspace_bytes(int device) {
     std::lock_guard<std::mutex> lk(g_mu);

@@ -28,7 +28,6 @@
 namespace fftconv {
 
 #define T16_PAD 18            // padded row of 16 complex (144 B): conflict-free LDS.128 across lanes
-#define T16_MAX_THREADS 544
 
 // ------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -57,6 +56,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel_shared(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(p)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -147,10 +159,58 @@ struct Tile16Params {
     const cpx* twM;       // n = mw
     LinePlan planM;       // n = mw
     int F, FH, FW, mh, mw, NT, NG, KB, nk, nxa, nstage;
+    int nmain;            // items (row, va) owned by a thread for the whole channel loop (<= 512)
+    int nextra;           // warp-passes per channel for the remaining items, dealt round-robin to the warps
 };
 
+// Work decomposition.  An item is (row = kk*16 + ub, va): 16 accumulators (the bins va + mw*vb).
+// There are N = KB*16*mw items per CTA.  The first `nmain` (<= 512 = 16 warps, 4 per SM
+// sub-partition, 128 registers each) keep their accumulators in registers for all channels.
+// When N > 512 (e.g. FW = 272: 2*16*17 = 544) the remaining items are processed as `nextra`
+// extra warp-passes per channel, handed round-robin to the 16 warps with accumulators in shared
+// memory, so that every sub-partition issues the same number of passes.
+
+// K^[u][va + mw*vb], vb = 0..15, for one item: load the row of the template half-transform, pruned
+// m-point stage, twiddle, 16-point FFT in registers.
+template <bool TW_REGS>
+__device__ __forceinline__ void t16_item_spectrum(const cpx* __restrict__ As_row, int nxa, const cpx* __restrict__ twM,
+                                                  int va, int mw, const float* twr, const float* twi,
+                                                  const cpx* __restrict__ twW, float* re, float* im)
+{
+    const float4* ap = reinterpret_cast<const float4*>(As_row);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 q = ap[j];
+        re[2 * j] = q.x; im[2 * j] = q.y; re[2 * j + 1] = q.z; im[2 * j + 1] = q.w;
+    }
+    // pruned m-point stage: in[xb] = sum_xa w_mw^(va*xa) * A[16*xa + xb]
+    for (int xa = 1; xa < nxa; ++xa) {
+        const cpx w = twM[(va * xa) % mw];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 q = ap[8 * xa + j];
+            re[2 * j] = fmaf(w.x, q.x, fmaf(-w.y, q.y, re[2 * j]));
+            im[2 * j] = fmaf(w.x, q.y, fmaf(w.y, q.x, im[2 * j]));
+            re[2 * j + 1] = fmaf(w.x, q.z, fmaf(-w.y, q.w, re[2 * j + 1]));
+            im[2 * j + 1] = fmaf(w.x, q.w, fmaf(w.y, q.z, im[2 * j + 1]));
+        }
+    }
+#pragma unroll
+    for (int xb = 1; xb < 16; ++xb) {
+        float wr, wi;
+        if (TW_REGS) { wr = twr[xb]; wi = twi[xb]; }
+        else { const cpx w = __ldg(&twW[va * xb]); wr = w.x; wi = w.y; }       // va*xb < FW
+        const float a = re[xb], b = im[xb];
+        re[xb] = fmaf(-b, wi, a * wr);
+        im[xb] = fmaf(b, wr, a * wi);
+    }
+    Dft<16>::run(re, im);
+}
+
+#define T16_THREADS 512
+
 template <bool CONJ>
-__global__ void __launch_bounds__(T16_MAX_THREADS, 1) tile16_conv(const Tile16Params P)
+__global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params P)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int mw = P.mw, KB = P.KB, F = P.F;
@@ -160,28 +220,34 @@ __global__ void __launch_bounds__(T16_MAX_THREADS, 1) tile16_conv(const Tile16Pa
     const uint32_t stage_bytes = dp_bytes + a_bytes;            // both multiples of 16
     const int nstage = P.nstage;
     const int t = blockIdx.y, kg = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int nitems = KB * 16 * mw;                            // == KB * FW
-    const bool active = tid < nitems;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int N = KB * 16 * mw;                                 // == KB * FW
+    const int NM = P.nmain, E = P.nextra;
+    const bool active = tid < NM;
     const int item = active ? tid : 0;
     const int va = item % mw, row = item / mw;                  // row = kk*16 + ub
     const int ub = row & 15;
 
-    // barriers live behind the larger of (pipeline stages, inverse ping-pong buffers)
+    // smem: [pipeline stages | (aliased later) inverse ping-pong] [mbarriers] [extra accumulators]
     const int mwp = mw | 1;
     const size_t y_bytes = 2 * (size_t)KB * 256 * mwp * sizeof(cpx);
     const size_t pipe_bytes = (size_t)nstage * stage_bytes;
     const size_t bar_off = ((pipe_bytes > y_bytes ? pipe_bytes : y_bytes) + 15) & ~(size_t)15;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + bar_off);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + bar_off);          // [nstage] "slab landed"
+    uint32_t* done = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 32);     // [nstage] warps finished with the slab
+    uint32_t* seq = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 48);      // [E] next channel of each extra slot
+    cpx* Racc = reinterpret_cast<cpx*>(smem_raw + bar_off + 96);               // [E][16][32]
 
     const cpx* dp_src = P.Dp + (size_t)t * F * (dp_bytes / sizeof(cpx));
     const cpx* a_src = P.Ag + ((size_t)t * P.NG + kg) * F * (a_bytes / sizeof(cpx));
 
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) mbar_init(&full[s], 1);
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+        for (int e = 0; e < E; ++e) seq[e] = 0;
         fence_barrier_init();
         fence_proxy_async();
     }
+    for (int i = tid; i < E * 512; i += blockDim.x) Racc[i] = make_float2(0.f, 0.f);
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < nstage && s < F; ++s) {
@@ -196,49 +262,23 @@ __global__ void __launch_bounds__(T16_MAX_THREADS, 1) tile16_conv(const Tile16Pa
     float twr[16], twi[16];
 #pragma unroll
     for (int xb = 0; xb < 16; ++xb) {
-        const cpx w = P.twW[(va * xb) % P.FW];
+        const cpx w = P.twW[va * xb];
         twr[xb] = w.x; twi[xb] = w.y;
     }
     float accr[16], acci[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { accr[j] = 0.f; acci[j] = 0.f; }
 
-    int s = 0;
+    int s = 0, xw = 0;                                          // xw: warp owning the next extra pass
     uint32_t phase = 0;
     for (int f = 0; f < F; ++f) {
         mbar_wait(&full[s], phase);
         const unsigned char* st = smem_raw + (size_t)s * stage_bytes;
         const cpx* Dps = reinterpret_cast<const cpx*>(st);
         const cpx* As = reinterpret_cast<const cpx*>(st + dp_bytes);
-        float re[16], im[16];
         {
-            const float4* ap = reinterpret_cast<const float4*>(As + (size_t)row * XCP);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 q = ap[j];
-                re[2 * j] = q.x; im[2 * j] = q.y; re[2 * j + 1] = q.z; im[2 * j + 1] = q.w;
-            }
-            // pruned m-point stage: in[xb] = sum_xa w_mw^(va*xa) * A[16*xa + xb]
-            for (int xa = 1; xa < P.nxa; ++xa) {
-                const cpx w = P.twM[(va * xa) % mw];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 q = ap[8 * xa + j];
-                    re[2 * j] = fmaf(w.x, q.x, fmaf(-w.y, q.y, re[2 * j]));
-                    im[2 * j] = fmaf(w.x, q.y, fmaf(w.y, q.x, im[2 * j]));
-                    re[2 * j + 1] = fmaf(w.x, q.z, fmaf(-w.y, q.w, re[2 * j + 1]));
-                    im[2 * j + 1] = fmaf(w.x, q.w, fmaf(w.y, q.z, im[2 * j + 1]));
-                }
-            }
-        }
-#pragma unroll
-        for (int xb = 1; xb < 16; ++xb) {
-            const float a = re[xb], b = im[xb];
-            re[xb] = fmaf(-b, twi[xb], a * twr[xb]);
-            im[xb] = fmaf(b, twr[xb], a * twi[xb]);
-        }
-        Dft<16>::run(re, im);
-        {
+            float re[16], im[16];
+            t16_item_spectrum<true>(As + (size_t)row * XCP, P.nxa, P.twM, va, mw, twr, twi, P.twW, re, im);
             const float4* dp = reinterpret_cast<const float4*>(Dps + ((size_t)ub * mw + va) * T16_PAD);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -252,15 +292,53 @@ __global__ void __launch_bounds__(T16_MAX_THREADS, 1) tile16_conv(const Tile16Pa
                 }
             }
         }
-        __syncthreads();                                     // everyone is done with stage s
-        if (tid == 0 && f + nstage < F) {
-            unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full[s], stage_bytes);
-            bulk_g2s(dst, dp_src + (size_t)(f + nstage) * (dp_bytes / sizeof(cpx)), dp_bytes, &full[s]);
-            bulk_g2s(dst + dp_bytes, a_src + (size_t)(f + nstage) * (a_bytes / sizeof(cpx)), a_bytes, &full[s]);
+        for (int e = 0; e < E; ++e) {
+            if (warp == xw) {
+                // extra passes of one slot run in channel order (deterministic accumulation)
+                while (ld_acquire_shared(&seq[e]) != (uint32_t)f) { }
+                const int id = NM + 32 * e + lane;
+                if (id < N) {
+                    const int erow = id / mw, eva = id - erow * mw;
+                    float re[16], im[16];
+                    t16_item_spectrum<false>(As + (size_t)erow * XCP, P.nxa, P.twM, eva, mw, nullptr, nullptr, P.twW, re, im);
+                    const float4* dp = reinterpret_cast<const float4*>(Dps + ((size_t)(erow & 15) * mw + eva) * T16_PAD);
+                    cpx* ra = Racc + (size_t)e * 512 + lane;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 q = dp[j];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const float dr = h ? q.z : q.x, di = h ? q.w : q.y;
+                            const float kr = re[2 * j + h], ki = CONJ ? -im[2 * j + h] : im[2 * j + h];
+                            cpx a = ra[(2 * j + h) * 32];
+                            a.x = fmaf(kr, dr, fmaf(-ki, di, a.x));
+                            a.y = fmaf(kr, di, fmaf(ki, dr, a.y));
+                            ra[(2 * j + h) * 32] = a;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) st_release_shared(&seq[e], (uint32_t)f + 1);
+            }
+            if (++xw == nwarps) xw = 0;
+        }
+        // No block barrier in the channel loop: the LAST warp to finish with slab s refills it, so the
+        // warps drift apart and their shared-memory and FMA phases overlap.
+        __syncwarp();
+        if (lane == 0) {
+            if (atom_add_acq_rel_shared(&done[s], 1u) == (uint32_t)nwarps - 1u) {
+                done[s] = 0;
+                if (f + nstage < F) {
+                    unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
+                    mbar_expect_tx(&full[s], stage_bytes);
+                    bulk_g2s(dst, dp_src + (size_t)(f + nstage) * (dp_bytes / sizeof(cpx)), dp_bytes, &full[s]);
+                    bulk_g2s(dst + dp_bytes, a_src + (size_t)(f + nstage) * (a_bytes / sizeof(cpx)), a_bytes, &full[s]);
+                }
+            }
         }
         if (++s == nstage) { s = 0; phase ^= 1; }
     }
+    __syncthreads();                                         // all slabs consumed before the buffers are reused
 
     // ---- inverse along w: IFFT16 over vb (registers), twiddle, m-point IDFT over va (smem)
     cpx* Y0 = reinterpret_cast<cpx*>(smem_raw);
@@ -275,12 +353,29 @@ __global__ void __launch_bounds__(T16_MAX_THREADS, 1) tile16_conv(const Tile16Pa
                 make_float2(fmaf(b, twi[xb], a * twr[xb]), fmaf(b, twr[xb], -(a * twi[xb])));
         }
     }
+    for (int e = warp; e < E; e += nwarps) {
+        const int id = NM + 32 * e + lane;
+        if (id < N) {
+            const int erow = id / mw, eva = id - erow * mw;
+            const cpx* ra = Racc + (size_t)e * 512 + lane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const cpx a = ra[j * 32]; accr[j] = a.x; acci[j] = a.y; }
+            dft_regs<16, true>(accr, acci);
+#pragma unroll
+            for (int xb = 0; xb < 16; ++xb) {
+                const cpx w = __ldg(&P.twW[eva * xb]);
+                const float a = accr[xb], b = acci[xb];
+                Y0[((size_t)erow * 16 + xb) * mwp + eva] =
+                    make_float2(fmaf(b, w.y, a * w.x), fmaf(b, w.x, -(a * w.y)));
+            }
+        }
+    }
     __syncthreads();
     const cpx* Zs = fft_lines<true>(Y0, Y1, KB * 256, mwp, P.planM, P.twM);
 
     // ---- IFFT16 across the 16 rows of the tile for each column x, twiddle w_FH^(-ua*yb)
-    if (active) {
-        const int kk = tid / P.FW, x = tid - kk * P.FW;
+    for (int it = tid; it < N; it += blockDim.x) {
+        const int kk = it / P.FW, x = it - kk * P.FW;
         const int xa = x >> 4, xb = x & 15;
         const int k = kg * KB + kk;
         if (k < P.nk) {

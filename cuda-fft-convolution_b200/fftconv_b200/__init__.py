@@ -29,7 +29,7 @@ __all__ = [
     "FFTConvError", "GpuArray", "gpuArray", "gather", "computeFFTsize16", "computeFFTsize",
     "cudaFFTData", "cudaConvFFTData", "cudaConvolutionFFT", "cudaConvFFTDataStreams",
     "cudaFFTDataClamp", "modulateAndNormalize", "Options", "conv_bank", "fft_data_device",
-    "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS",
+    "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -40,6 +40,7 @@ EXPORTED_SYMBOLS = [
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
     "fftconv_conv_bank", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
+    "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
 ]
 
 # error ids / messages of the reference
@@ -101,6 +102,11 @@ def lib() -> ctypes.CDLL:
         L.fftconv_release.restype = None
         L.fftconv_last_error.restype = ctypes.c_char_p
         L.fftconv_version.restype = ctypes.c_char_p
+        L.fftconv_profile_enable.argtypes = [c_int]
+        L.fftconv_profile_enable.restype = None
+        L.fftconv_profile_name.argtypes = [c_int]
+        L.fftconv_profile_name.restype = ctypes.c_char_p
+        L.fftconv_profile_read.argtypes = [c_int, c_vp, c_vp, c_int]
         _lib = L
     return _lib
 
@@ -111,6 +117,24 @@ def last_error() -> str:
 
 def launch_count() -> int:
     return int(lib().fftconv_launch_count())
+
+
+def profile(enable: bool) -> None:
+    """Bracket every kernel launch with CUDA events (roofline leg of bench.py)."""
+    lib().fftconv_profile_enable(1 if enable else 0)
+
+
+def profile_read(reset: bool = True):
+    """-> {kernel name: (total ms, launches)} for every kernel kind that ran while profiling."""
+    L = lib()
+    out = {}
+    for kind in range(L.fftconv_profile_kinds()):
+        ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+        if L.fftconv_profile_read(kind, ctypes.byref(ms), ctypes.byref(n), 1 if reset else 0) != 0:
+            raise FFTConvError("fftconv:CudaError", last_error())
+        if n.value:
+            out[L.fftconv_profile_name(kind).decode()] = (ms.value, n.value)
+    return out
 
 
 def _check(rc: int, errid: str):

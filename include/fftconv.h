@@ -118,6 +118,13 @@ int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_
 
 /* Number of kernel launches issued by this library since load (bench accounting). */
 long long fftconv_launch_count(void);
+/* Per-kernel device timing for the roofline leg of bench.py: while enabled, every kernel launch is
+ * bracketed by CUDA events on the stream it is launched on.  fftconv_profile_read sums the elapsed
+ * time and the launch count of one kernel kind (0 <= kind < fftconv_profile_kinds()). */
+void fftconv_profile_enable(int on);
+int fftconv_profile_kinds(void);
+const char* fftconv_profile_name(int kind);
+int fftconv_profile_read(int kind, double* total_ms, long long* launches, int reset);
 /* Bytes of device scratch currently held by the cached workspace on `device`. */
 long long fftconv_workspace_bytes(int device);
 /* Drop cached plans / scratch (all devices). */
