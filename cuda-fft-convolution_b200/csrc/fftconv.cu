@@ -299,7 +299,7 @@ static bool tile16_config(int FH, int FW, int maxkh, int maxkw, Tile16Cfg& g) {
         size_t smem = 0;
         for (int ns = 4; ns >= 2; --ns) {
             const size_t pipe = (size_t)ns * (g.dp_bytes + a_bytes);
-            const size_t tot = ((std::max(pipe, y_bytes) + 15) & ~(size_t)15) + 96 + (size_t)nextra * 512 * sizeof(cpx);
+            const size_t tot = ((std::max(pipe, y_bytes) + 15) & ~(size_t)15) + 160 + (size_t)nextra * 2048 * sizeof(cpx);
             if (tot <= kMaxSmem) { nstage = ns; smem = tot; break; }
         }
         if (!nstage) continue;

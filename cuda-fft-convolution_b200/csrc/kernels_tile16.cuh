@@ -235,19 +235,19 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
     const size_t bar_off = ((pipe_bytes > y_bytes ? pipe_bytes : y_bytes) + 15) & ~(size_t)15;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + bar_off);          // [nstage] "slab landed"
     uint32_t* done = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 32);     // [nstage] warps finished with the slab
-    uint32_t* seq = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 48);      // [E] next channel of each extra slot
-    cpx* Racc = reinterpret_cast<cpx*>(smem_raw + bar_off + 96);               // [E][16][32]
+    uint32_t* seq = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 48);      // [E][4] passes done per accumulator copy
+    cpx* Racc = reinterpret_cast<cpx*>(smem_raw + bar_off + 160);              // [E][4][16][32]
 
     const cpx* dp_src = P.Dp + (size_t)t * F * (dp_bytes / sizeof(cpx));
     const cpx* a_src = P.Ag + ((size_t)t * P.NG + kg) * F * (a_bytes / sizeof(cpx));
 
     if (tid == 0) {
         for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
-        for (int e = 0; e < E; ++e) seq[e] = 0;
+        for (int e = 0; e < 4 * E; ++e) seq[e] = 0;
         fence_barrier_init();
         fence_proxy_async();
     }
-    for (int i = tid; i < E * 512; i += blockDim.x) Racc[i] = make_float2(0.f, 0.f);
+    for (int i = tid; i < E * 2048; i += blockDim.x) Racc[i] = make_float2(0.f, 0.f);
     __syncthreads();
     if (tid == 0) {
         for (int s = 0; s < nstage && s < F; ++s) {
@@ -260,8 +260,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
 
     // per-thread w twiddles  w_FW^(va*xb), xb = 0..15
     float twr[16], twi[16];
+    twr[0] = 1.f; twi[0] = 0.f;
 #pragma unroll
-    for (int xb = 0; xb < 16; ++xb) {
+    for (int xb = 1; xb < 16; ++xb) {
         const cpx w = P.twW[va * xb];
         twr[xb] = w.x; twi[xb] = w.y;
     }
@@ -279,6 +280,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
         {
             float re[16], im[16];
             t16_item_spectrum<true>(As + (size_t)row * XCP, P.nxa, P.twM, va, mw, twr, twi, P.twW, re, im);
+#ifdef T16_FENCE_DP
+            asm volatile("" ::: "memory");
+#endif
             const float4* dp = reinterpret_cast<const float4*>(Dps + ((size_t)ub * mw + va) * T16_PAD);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -294,15 +298,18 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
         }
         for (int e = 0; e < E; ++e) {
             if (warp == xw) {
-                // extra passes of one slot run in channel order (deterministic accumulation)
-                while (ld_acquire_shared(&seq[e]) != (uint32_t)f) { }
+                // Each slot has 4 accumulator copies used in turn (channel f -> copy f & 3), so that
+                // consecutive passes of a slot, which run on different warps, do not serialise; the
+                // passes of one copy still run in channel order (deterministic accumulation).
+                const int cpy = f & 3;
+                while (ld_acquire_shared(&seq[4 * e + cpy]) != (uint32_t)(f >> 2)) __nanosleep(64);
                 const int id = NM + 32 * e + lane;
                 if (id < N) {
                     const int erow = id / mw, eva = id - erow * mw;
                     float re[16], im[16];
                     t16_item_spectrum<false>(As + (size_t)erow * XCP, P.nxa, P.twM, eva, mw, nullptr, nullptr, P.twW, re, im);
                     const float4* dp = reinterpret_cast<const float4*>(Dps + ((size_t)(erow & 15) * mw + eva) * T16_PAD);
-                    cpx* ra = Racc + (size_t)e * 512 + lane;
+                    cpx* ra = Racc + ((size_t)e * 4 + cpy) * 512 + lane;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const float4 q = dp[j];
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
                     }
                 }
                 __syncwarp();
-                if (lane == 0) st_release_shared(&seq[e], (uint32_t)f + 1);
+                if (lane == 0) st_release_shared(&seq[4 * e + cpy], (uint32_t)(f >> 2) + 1);
             }
             if (++xw == nwarps) xw = 0;
         }
@@ -345,8 +352,9 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
     cpx* Y1 = Y0 + (size_t)KB * 256 * mwp;
     dft_regs<16, true>(accr, acci);
     if (active) {
+        Y0[((size_t)row * 16) * mwp + va] = make_float2(accr[0], acci[0]);
 #pragma unroll
-        for (int xb = 0; xb < 16; ++xb) {
+        for (int xb = 1; xb < 16; ++xb) {
             // multiply by conj(w_FW^(va*xb))
             const float a = accr[xb], b = acci[xb];
             Y0[((size_t)row * 16 + xb) * mwp + va] =
@@ -357,9 +365,12 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
         const int id = NM + 32 * e + lane;
         if (id < N) {
             const int erow = id / mw, eva = id - erow * mw;
-            const cpx* ra = Racc + (size_t)e * 512 + lane;
+            const cpx* ra = Racc + (size_t)e * 2048 + lane;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { const cpx a = ra[j * 32]; accr[j] = a.x; acci[j] = a.y; }
+            for (int j = 0; j < 16; ++j) {
+                const cpx a0 = ra[j * 32], a1 = ra[512 + j * 32], a2 = ra[1024 + j * 32], a3 = ra[1536 + j * 32];
+                accr[j] = (a0.x + a1.x) + (a2.x + a3.x); acci[j] = (a0.y + a1.y) + (a2.y + a3.y);
+            }
             dft_regs<16, true>(accr, acci);
 #pragma unroll
             for (int xb = 0; xb < 16; ++xb) {
