@@ -1,0 +1,134 @@
+// fftconv_bench — stand-alone C++ driver of the C ABI (include/fftconv.h); no MATLAB, no Python.
+//
+//   fftconv_bench [--config c1|c2|c3|c3s] [--H h --W w --F f --kh a --kw b --K k] [--iters n]
+//                 [--host] [--check n] [--device d]
+//
+// Builds the named synthetic workload, runs cudaConvolutionFFT-equivalent calls through
+// libfftconv.so and prints conv outputs/s.  --host passes host buffers (MEX-style call, copies
+// included); default keeps bank and planes resident on the device.  --check n verifies n sampled
+// output pixels per template against a float64 direct convolution computed here on the CPU
+// (verification of the driver's own run, not a compute path).
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/fftconv.h"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
+#define FC(x) do { int r_ = (x); if (r_ != 0) { fprintf(stderr, "fftconv error %d: %s\n", r_, fftconv_last_error()); return 3; } } while (0)
+
+struct Cfg { int H, W, F, kh, kw, K; const char* name; };
+
+int main(int argc, char** argv) {
+    Cfg c{256, 256, 31, 16, 16, 1000, "c2"};
+    int iters = 10, check = 0, device = 0;
+    bool host = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() { return i + 1 < argc ? atoi(argv[++i]) : 0; };
+        if (a == "--config" && i + 1 < argc) {
+            std::string n = argv[++i];
+            if (n == "c1") c = Cfg{64, 8, 5, 10, 4, 10, "c1"};
+            else if (n == "c2") c = Cfg{256, 256, 31, 16, 16, 1000, "c2"};
+            else if (n == "c3") c = Cfg{4096, 4096, 1, 512, 512, 64, "c3"};
+            else if (n == "c3s") c = Cfg{1024, 1024, 1, 128, 128, 16, "c3s"};
+            else { fprintf(stderr, "unknown config %s\n", n.c_str()); return 1; }
+        } else if (a == "--H") c.H = next(); else if (a == "--W") c.W = next(); else if (a == "--F") c.F = next();
+        else if (a == "--kh") c.kh = next(); else if (a == "--kw") c.kw = next(); else if (a == "--K") c.K = next();
+        else if (a == "--iters") iters = next(); else if (a == "--check") check = next();
+        else if (a == "--device") device = next(); else if (a == "--host") host = true;
+        else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 1; }
+    }
+    const int FH = fftconv_fft_size16(c.H + c.kh - 1), FW = fftconv_fft_size16(c.W + c.kw - 1), CH = FH / 2 + 1;
+    const size_t nd = (size_t)c.H * c.W * c.F, nk1 = (size_t)c.kh * c.kw * c.F, plane = (size_t)FH * FW;
+    printf("%s  %s: data %dx%dx%d, %d templates %dx%dx%d, plane %dx%d\n", fftconv_version(), c.name, c.H, c.W, c.F,
+           c.K, c.kh, c.kw, c.F, FH, FW);
+
+    std::mt19937 rng(2);
+    std::uniform_real_distribution<float> U(0.f, 0.2f);
+    std::normal_distribution<float> Nn(0.f, 0.05f);
+    std::vector<float> h_data(nd), h_bank(nk1 * c.K);
+    for (auto& v : h_data) v = U(rng);
+    for (auto& v : h_bank) v = Nn(rng);
+
+    CK(cudaSetDevice(device));
+    float *d_data, *d_bank, *d_out;
+    fftconv_float2* d_spec;
+    CK(cudaMalloc(&d_data, nd * 4)); CK(cudaMalloc(&d_bank, nk1 * c.K * 4));
+    CK(cudaMalloc(&d_out, plane * c.K * 4)); CK(cudaMalloc(&d_spec, sizeof(fftconv_float2) * (size_t)CH * FW * c.F));
+    CK(cudaMemcpy(d_data, h_data.data(), nd * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_bank, h_bank.data(), nk1 * c.K * 4, cudaMemcpyHostToDevice));
+
+    float* h_out = nullptr;
+    std::vector<const float*> kp(c.K);
+    std::vector<float*> op(c.K);
+    std::vector<int> khs(c.K, c.kh), kws(c.K, c.kw);
+    if (host) {
+        CK(cudaMallocHost(&h_out, plane * c.K * 4));
+        for (int k = 0; k < c.K; ++k) { kp[k] = h_bank.data() + nk1 * k; op[k] = h_out + plane * k; }
+    }
+    cudaStream_t st;
+    CK(cudaStreamCreate(&st));
+    auto step = [&]() -> int {
+        if (host)
+            return fftconv_convolution_fft(h_data.data(), 0, c.H, c.W, c.F, c.kh, c.kw, c.K, kp.data(), khs.data(),
+                                           kws.data(), nullptr, nullptr, op.data(), 0, nullptr, 0, nullptr, device, st);
+        int r = fftconv_fft_data(d_data, 1, c.H, c.W, c.F, c.kh, c.kw, d_spec, device, st);
+        if (r) return r;
+        return fftconv_conv_bank(d_spec, CH, FW, c.F, c.K, d_bank, c.kh, c.kw, d_out, nullptr, device, st);
+    };
+    for (int i = 0; i < 3; ++i) FC(step());
+    CK(cudaStreamSynchronize(st));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    auto t0 = std::chrono::steady_clock::now();
+    CK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i) FC(step());
+    CK(cudaEventRecord(e1, st));
+    CK(cudaStreamSynchronize(st));
+    const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / iters;
+    float ev_ms = 0.f;
+    CK(cudaEventElapsedTime(&ev_ms, e0, e1));
+    const double ms = host ? wall_ms : ev_ms / iters;
+    printf("%s path: %.3f ms per call, %.3e conv outputs/s, %lld kernel launches so far\n", host ? "host->host" : "device-resident",
+           ms, (double)c.K * plane / (ms * 1e-3), fftconv_launch_count());
+
+    if (check > 0) {
+        std::vector<float> out(plane * c.K);
+        if (host) memcpy(out.data(), h_out, plane * c.K * 4);
+        else CK(cudaMemcpy(out.data(), d_out, plane * c.K * 4, cudaMemcpyDeviceToHost));
+        std::mt19937 pick(7);
+        double num = 0, den = 0;
+        const int OH = c.H + c.kh - 1, OW = c.W + c.kw - 1;
+        for (int k = 0; k < c.K; k += std::max(1, c.K / 8))
+            for (int s = 0; s < check; ++s) {
+                const int oy = pick() % OH, ox = pick() % OW;
+                double acc = 0;
+                for (int f = 0; f < c.F; ++f)
+                    for (int kx = 0; kx < c.kw; ++kx) {
+                        const int dx = ox - kx;
+                        if (dx < 0 || dx >= c.W) continue;
+                        for (int ky = 0; ky < c.kh; ++ky) {
+                            const int dy = oy - ky;
+                            if (dy < 0 || dy >= c.H) continue;
+                            acc += (double)h_data[((size_t)f * c.W + dx) * c.H + dy] *
+                                   (double)h_bank[nk1 * k + ((size_t)f * c.kw + kx) * c.kh + ky];
+                        }
+                    }
+                const double got = out[plane * k + (size_t)ox * FH + oy];
+                num += (got - acc) * (got - acc); den += acc * acc;
+            }
+        const double rel = std::sqrt(num / std::max(den, 1e-300));
+        printf("check: relative L2 on sampled pixels vs float64 direct convolution = %.3e (%s)\n", rel, rel < 1e-5 ? "ok" : "FAIL");
+        if (!(rel < 1e-5)) return 4;
+    }
+    fftconv_release();
+    return 0;
+}

@@ -1,0 +1,24 @@
+// MEX shim: cvcell = cudaConvFFTData(fftData, kernelCell[, threads])   replaces src/cudaConvFFTData.cu:24-306
+#include "mex_common.h"
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    if (mxInitGPU() != MX_GPU_SUCCESS) mexErrMsgTxt("mxInitGPU fail");
+    if (nrhs < 2 || nrhs > 3 || !mxIsGPUArray(prhs[0]))
+        mexErrMsgIdAndTxt(kErrConv, "The data must be FFT-ed real array in GPU");  // :68-69
+    int nthreads = 0;
+    const double* threads = thread_arg(nrhs, prhs, 2, nthreads);
+    const mxGPUArray* spec = mxGPUCreateFromMxArray(prhs[0]);
+    const mwSize* sd = mxGPUGetDimensions(spec);                                    // :92-98
+    const int CH = (int)sd[0], FW = (int)sd[1], F = (int)sd[2], FH = (CH - 1) * 2;
+    KernelCell c;
+    c.handles.push_back(spec);
+    marshal_cell(prhs[1], true, c);
+    std::vector<float*> outs;
+    plhs[0] = alloc_out_cell((int)c.ptr.size(), FH, FW, outs);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int rc = fftconv_conv_fft_data((const fftconv_float2*)mxGPUGetDataReadOnly(spec), CH, FW, F,
+                                         (int)c.ptr.size(), c.ptr.data(), c.kh.data(), c.kw.data(), c.kf.data(),
+                                         c.on_dev.data(), outs.data(), 0, threads, nthreads, nullptr, dev, nullptr);
+    raise_if(rc, kErrConv, &c);
+    c.release();
+}
