@@ -71,7 +71,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"],
+                                          "-i", str(self.index), "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -178,6 +178,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import fftconv_b200 as fc
+    from fftconv_b200.sharding import broadcast_spectrum
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,8 +210,7 @@ def run_ours(args):
         """data FFT (rank 0) -> [NCCL broadcast of the spectrum] -> bank convolution on every rank"""
         if rank == 0:
             fc.fft_data_device(data, H, W, F, kh, kw, spec_t=spec)
-        if dist is not None:
-            dist.broadcast(torch.view_as_real(spec), src=0)
+        broadcast_spectrum(spec, 0)
         fc.conv_bank(spec, bank, kh, kw, out)
 
     def barrier():
@@ -313,7 +313,7 @@ def run_ours(args):
             rc = 0
             if rank == 0:
                 rc = L.fftconv_fft_data(h_data.data_ptr(), 0, H, W, F, kh, kw, spec.data_ptr(), local, st)
-            dist.broadcast(torch.view_as_real(spec), src=0)
+            broadcast_spectrum(spec, 0)
             rc = rc or L.fftconv_conv_fft_data(spec.data_ptr(), CH, FW, F, K, kp, khs, kws, None, None, op, 0,
                                                None, 0, None, local, st)
         if rc != 0:
@@ -370,7 +370,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
