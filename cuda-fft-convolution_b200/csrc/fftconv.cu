@@ -15,6 +15,7 @@
 #include "../../include/fftconv.h"
 #include "kernels_generic.cuh"
 #include "kernels_tile16.cuh"
+#include "kernels_osgemm.cuh"
 
 namespace fftconv {
 
@@ -48,10 +49,13 @@ static int fail(int code, const char* fmt, ...) {
 
 // Optional per-kernel timing (bench.py roofline leg): every launch of a profiled kind is
 // bracketed by CUDA events on the stream it is launched on.
-enum ProfKind { PK_RELAYOUT = 0, PK_KERN_H, PK_CONV, PK_C2R, PK_DATA_H, PK_DATA_W, PK_GEN_H, PK_GEN_W, PK_GEN_C2R, PK_COUNT };
+enum ProfKind { PK_RELAYOUT = 0, PK_KERN_H, PK_CONV, PK_C2R, PK_DATA_H, PK_DATA_W, PK_GEN_H, PK_GEN_W, PK_GEN_C2R,
+                PK_OS_PLANE, PK_OS_DATA_H, PK_OS_DATA_W, PK_OS_KERN_H, PK_OS_KERN_W, PK_OS_GEMM, PK_OS_INV, PK_COUNT };
 static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass", "tile16_conv", "tile16_c2r",
                                            "fwd_h_pass(data)", "fwd_w_pass(data)", "fwd_h_pass(kernels)",
-                                           "conv_w_pass_generic", "inv_h_pass"};
+                                           "conv_w_pass_generic", "inv_h_pass",
+                                           "os_spectrum_to_plane", "os_hpass(data tiles)", "os_wpass(data tiles)",
+                                           "os_hpass(templates)", "os_wpass(templates)", "os_gemm", "os_inverse"};
 static bool g_prof_on = false;
 struct ProfRec { int kind; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
@@ -105,6 +109,7 @@ struct Ctx {
     bool inited = false;
     std::map<int, cpx*> tw;          // n -> device twiddle table e^{-2 pi i j / n}
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
+    DevBuf osHk, osHd, osA, osB, osP, osPlane, osZ;     // overlap-save / tcgen05 path scratch
     void* pinned = nullptr;          // host staging (descriptors, packed kernels)
     size_t pinned_cap = 0;
     cudaEvent_t pinned_free = nullptr;   // recorded after the last async copy out of `pinned`
@@ -175,6 +180,12 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(tile16_conv<false>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(tile16_conv<true>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(tile16_c2r)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_wpass<0, 1>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_wpass<0, 2>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_wpass<1, 4>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
         c.inited = true;
     }
     *out = &c;
@@ -390,6 +401,188 @@ static int tile16_chunk(Ctx& c, int FH, int FW, int F, int maxkh, int maxkw, con
     return 0;
 }
 
+
+// ------------------------------------------------------ overlap-save + tcgen05 GEMM path (host)
+struct OsCfg {
+    int F, FH, FW, maxkh, maxkw;
+    int NFK, XCK;                 // template transform: 16*NFK leading samples per side
+    int Sh, Sw, nth, ntw, NT;     // valid outputs per tile side, tile grid
+    int NKS, KC;                  // K stages per item, 16-byte k units per stage (even)
+    int NNB, NTn, NMMA, RS;       // tile blocks, tiles per block, MMA N, P row stride (floats)
+    int nsta;                     // A ring depth
+    size_t gemm_smem, inv_smem;
+    size_t a_stage, b_buf, p_blk; // bytes
+};
+
+static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g) {
+    g = OsCfg{};
+    if (maxkh > 32 || maxkw > 32 || maxkh < 1 || maxkw < 1) return false;
+    g.F = F; g.FH = FH; g.FW = FW; g.maxkh = maxkh; g.maxkw = maxkw;
+    g.NFK = std::max(maxkh, maxkw) <= 16 ? 1 : 2;
+    g.XCK = 16 * g.NFK;
+    g.Sh = 65 - maxkh; g.Sw = 65 - maxkw;
+    g.nth = (FH + g.Sh - 1) / g.Sh; g.ntw = (FW + g.Sw - 1) / g.Sw;
+    g.NT = g.nth * g.ntw;
+    g.NKS = (2 * F + 31) / 32;
+    const int units = (2 * F + 3) / 4;
+    g.KC = ((units + g.NKS - 1) / g.NKS + 1) & ~1;
+    g.NNB = (g.NT + 39) / 40;
+    g.NTn = (g.NT + g.NNB - 1) / g.NNB;
+    g.NMMA = (2 * g.NTn + 15) & ~15;
+    g.RS = (2 * g.NTn + 7) & ~7;
+    g.a_stage = (size_t)2 * g.KC * OS_TM * 16;
+    g.b_buf = (size_t)g.NKS * 2 * g.KC * g.NMMA * 16;
+    g.p_blk = (size_t)OS_TM * g.RS * 4;
+    if (g.b_buf >= (1u << 20) || g.a_stage >= (1u << 20)) return false;       // mbarrier tx-count range
+    g.nsta = 0;
+    for (int ns = 4; ns >= 2; --ns) {
+        const size_t tot = (size_t)ns * g.a_stage + 2 * g.b_buf + g.p_blk + 256;
+        if (tot <= kMaxSmem) { g.nsta = ns; g.gemm_smem = tot; break; }
+    }
+    if (!g.nsta) return false;
+    g.inv_smem = (size_t)OS_IG * 32 * OS_IROW * sizeof(cpx) + (size_t)OS_IG * g.Sw * (g.Sh | 1) * sizeof(float);
+    if (g.inv_smem > kMaxSmem) return false;
+    return true;
+}
+
+static int os_env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// Source plane -> B operand images (once per call).  If d_spec is given the plane is first recovered from
+// the compat spectrum (inverse w, then C2R along h); otherwise the raw data [F][W][H] is tiled directly.
+static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const float* d_raw, int rawH, int rawW,
+                           int correlate, cudaStream_t st) {
+    const int F = g.F, FH = g.FH, FW = g.FW, CH = FH / 2 + 1;
+    SrcDesc src;
+    if (d_raw) {
+        src.ptr = d_raw; src.rows = rawH; src.cols = rawW;
+    } else {
+        const cpx *twH, *twW;
+        if (int e = get_twiddles(c, FH, st, &twH)) return e;
+        if (int e = get_twiddles(c, FW, st, &twW)) return e;
+        const LinePlan pH = make_line_plan(FH), pW = make_line_plan(FW);
+        const int ldH = odd_ld(FH), ldW = odd_ld(FW);
+        if (int e = dev_reserve(c.osZ, sizeof(cpx) * (size_t)F * FW * CH)) return e;
+        if (int e = dev_reserve(c.osPlane, sizeof(float) * (size_t)F * FW * FH + sizeof(float*) * (size_t)F)) return e;
+        float* plane = (float*)c.osPlane.p;
+        float** d_planes = reinterpret_cast<float**>(plane + (size_t)F * FW * FH);
+        if (int e = pinned_reserve(c, sizeof(float*) * (size_t)F)) return e;
+        CU(cudaEventSynchronize(c.pinned_free));
+        float** h_planes = reinterpret_cast<float**>(c.pinned);
+        for (int f = 0; f < F; ++f) h_planes[f] = plane + (size_t)f * FW * FH;
+        CU(cudaMemcpyAsync(d_planes, h_planes, sizeof(float*) * (size_t)F, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c.pinned_free, st));
+        ProfScope ps(PK_OS_PLANE, st);
+        int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
+        TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
+        dim3 g2((CH + TU - 1) / TU, F);
+        inv_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>(d_spec, FW, CH, pW, twW, (cpx*)c.osZ.p, TU, ldW);
+        LAUNCH_CHECK();
+        const int NL = pick_lines(FH, 8);
+        const long long nlines = (long long)F * (FW / 2);
+        inv_h_pass<<<(unsigned)((nlines + NL - 1) / NL), 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
+            (const cpx*)c.osZ.p, F, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_planes, FH, FW, FH, NL, ldH);
+        LAUNCH_CHECK();
+        src.ptr = plane; src.rows = FH; src.cols = FW;
+    }
+    if (int e = dev_reserve(c.osHd, sizeof(cpx) * (size_t)g.NT * F * OS_CH * 64)) return e;
+    if (int e = dev_reserve(c.osB, (size_t)g.NNB * OS_NBIN * g.b_buf)) return e;
+    {
+        OsHArgs a{};
+        a.descs = nullptr; a.src = src; a.nitems = g.NT; a.F = F; a.XC = 64; a.H = (cpx*)c.osHd.p;
+        a.FH = FH; a.FW = FW; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
+        const long long nlines = (long long)g.NT * F * 32;
+        ProfScope ps(PK_OS_DATA_H, st);
+        os_hpass<1, 4><<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(a);
+        LAUNCH_CHECK();
+    }
+    {
+        OsWArgs a{};
+        a.H = (const cpx*)c.osHd.p; a.F = F; a.XC = 64; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC;
+        a.rows = g.NMMA; a.nblk = g.NNB; a.slots_per_blk = g.NMMA / 2; a.valid_per_blk = g.NTn; a.nvalid = g.NT;
+        a.correlate = correlate;
+        dim3 grid((g.NNB * (g.NMMA / 2) + 31) / 32, g.NKS * g.KC, (OS_CH + OS_WR - 1) / OS_WR);
+        ProfScope ps(PK_OS_DATA_W, st);
+        os_wpass<1, 4><<<grid, 256, OS_WR * 64 * 2 * 32 * sizeof(cpx), st>>>(a);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
+static int os_max_chunk(const OsCfg& g) {
+    const int ntblk = std::max(1, os_env_int("FFTCONV_OS_NTBLK", 2));
+    (void)g;
+    return ntblk * OS_TM;
+}
+
+static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates) {
+    const int ntblk = (KC_templates + OS_TM - 1) / OS_TM;
+    if (int e = dev_reserve(c.osHk, sizeof(cpx) * (size_t)ntblk * OS_TM * g.F * OS_CH * g.XCK)) return e;
+    if (int e = dev_reserve(c.osA, (size_t)ntblk * OS_NBIN * g.NKS * g.a_stage)) return e;
+    if (int e = dev_reserve(c.osP, (size_t)ntblk * g.NNB * OS_NBIN * g.p_blk)) return e;
+    return 0;
+}
+
+static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
+                    const fftconv_options& opt, cudaStream_t st) {
+    const int ntblk = (nk + OS_TM - 1) / OS_TM;
+    {
+        OsHArgs a{};
+        a.descs = d_descs; a.nitems = nk; a.F = g.F; a.XC = g.XCK; a.H = (cpx*)c.osHk.p;
+        const long long nlines = (long long)nk * g.F * (g.XCK / 2);
+        ProfScope ps(PK_OS_KERN_H, st);
+        if (g.NFK == 1) os_hpass<0, 1><<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(a);
+        else os_hpass<0, 2><<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(a);
+        LAUNCH_CHECK();
+    }
+    {
+        OsWArgs a{};
+        a.H = (const cpx*)c.osHk.p; a.F = g.F; a.XC = g.XCK; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
+        a.rows = OS_TM; a.nblk = ntblk; a.slots_per_blk = OS_TM; a.valid_per_blk = OS_TM; a.nvalid = nk;
+        a.correlate = 0;
+        dim3 grid((ntblk * OS_TM + 31) / 32, g.NKS * g.KC, (OS_CH + OS_WR - 1) / OS_WR);
+        const size_t smem = OS_WR * 64 * 2 * 32 * sizeof(cpx);
+        ProfScope ps(PK_OS_KERN_W, st);
+        if (g.NFK == 1) os_wpass<0, 1><<<grid, 256, smem, st>>>(a);
+        else os_wpass<0, 2><<<grid, 256, smem, st>>>(a);
+        LAUNCH_CHECK();
+    }
+    {
+        OsGemmArgs a{};
+        a.Aimg = (const float*)c.osA.p; a.Bimg = (const float*)c.osB.p; a.P = (float*)c.osP.p;
+        a.NTBLK = ntblk; a.NNB = g.NNB; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.RS = g.RS;
+        a.nitems = (long long)g.NNB * OS_NBIN * ntblk;
+        a.nsta = g.nsta;
+        a.lbo_swap = os_env_int("FFTCONV_OS_LBO_SWAP", 0);
+        ProfScope ps(PK_OS_GEMM, st);
+        const char* mode = getenv("FFTCONV_OS_GEMM");
+        if (mode && !strcmp(mode, "simt")) {            // validation only, never the default
+            os_gemm_simt<<<(unsigned)a.nitems, 128, 0, st>>>(a);
+        } else {
+            const unsigned grid = (unsigned)std::min<long long>(a.nitems, (long long)c.sm_count);
+            os_gemm<<<grid, 192, g.gemm_smem, st>>>(a);
+        }
+        LAUNCH_CHECK();
+    }
+    {
+        OsInvArgs a{};
+        a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS;
+        a.NT = g.NT; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
+        a.FH = g.FH; a.FW = g.FW;
+        a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
+        a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
+        a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
+        a.scale = 1.0f / (64.0f * 64.0f);
+        dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
+        ProfScope ps(PK_OS_INV, st);
+        os_inverse<<<grid, 512, g.inv_smem, st>>>(a);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------ conv core
 struct KernelRef {
     const float* ptr;
@@ -405,7 +598,24 @@ struct ConvArgs {
     bool out_on_device;
     fftconv_options opt;
     bool pipelined;                // use the side copy stream (Streams entry point)
+    const float* d_raw = nullptr;  // one-shot entry point: the raw data [F][rawW][rawH] on the device
+    int rawH = 0, rawW = 0;
 };
+
+enum ConvPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TILE16 = 2, PATH_OSGEMM = 3 };
+
+// Which pipeline serves this call.  The overlap-save / tensor-core path needs a bank large enough to fill
+// 128-row MMA blocks; small banks stay on the SIMT pipelines.
+static int choose_path(const fftconv_options& opt, int F, int FH, int FW, int maxkh, int maxkw, int K) {
+    OsCfg g;
+    const bool os_ok = !opt.correlate && os_config(F, FH, FW, maxkh, maxkw, g);
+    const bool t16_ok = tile16_supported(FH, FW, maxkh, maxkw);
+    if (opt.force_generic || opt.path == PATH_GENERIC) return PATH_GENERIC;
+    if (opt.path == PATH_OSGEMM) return os_ok ? PATH_OSGEMM : (t16_ok ? PATH_TILE16 : PATH_GENERIC);
+    if (opt.path == PATH_TILE16) return t16_ok ? PATH_TILE16 : PATH_GENERIC;
+    if (os_ok && K >= os_env_int("FFTCONV_OS_MIN_K", 64)) return PATH_OSGEMM;
+    return t16_ok ? PATH_TILE16 : PATH_GENERIC;
+}
 
 static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* d_descs, const int* d_kcols,
                               int nk, int maxcols, float* const* d_outptrs, cudaStream_t st) {
@@ -481,17 +691,26 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         maxkh = std::max(maxkh, std::min(a.kernels[k].kh, FH));
         maxkw = std::max(maxkw, std::min(a.kernels[k].kw, FW));
     }
-    const bool tile16 = !a.opt.force_generic && tile16_supported(FH, FW, maxkh, maxkw);
+    const int path = choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
+    const bool tile16 = path == PATH_TILE16;
+    const bool osg = path == PATH_OSGEMM;
+    OsCfg og;
+    if (osg) os_config(F, FH, FW, maxkh, maxkw, og);
 
     // ---- chunking: bound the scratch held per chunk
     const size_t plane = plane_floats(a, FH);
     size_t per_kernel = 0;
     if (tile16) per_kernel = tile16_scratch_per_kernel(FH, FW, F, maxkh, maxkw);
+    else if (osg) per_kernel = 0;
     else per_kernel = sizeof(cpx) * ((size_t)F * maxkw * CH + (size_t)FW * CH);
     if (!a.out_on_device) per_kernel += plane * sizeof(float);
     const size_t budget = (size_t)96 << 20;    // keep a chunk's intermediates L2-resident (126 MB L2)
     int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
-    if (tile16) {
+    if (osg) {
+        KC = std::min(K, os_max_chunk(og));
+        if (int e = os_reserve_chunk(c, og, KC)) return e;
+        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, a.opt.correlate, st)) return e;
+    } else if (tile16) {
         // one CTA per SM: size the chunk so that NT * ceil(KC/KB) CTAs fill whole waves
         Tile16Cfg g;
         tile16_config(FH, FW, maxkh, maxkw, g);
@@ -577,7 +796,9 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         const int nk = std::min(KC, K - k0);
         if (!a.out_on_device && chunk >= 2) CU(cudaStreamWaitEvent(st, c.ev[chunk & 1], 0));   // staging half free?
         int e;
-        if (tile16)
+        if (osg)
+            e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st);
+        else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
             e = conv_generic_chunk(c, a, FH, d_desc + k0, d_kcols + k0, nk, maxkw, d_outp + k0, st);
@@ -685,12 +906,15 @@ int fftconv_fft_data_clamp(const float* data, int data_on_device, int H, int W, 
     return fft_data_impl(data, data_on_device, H, W, F, KH, KW, PAD_CLAMP, kernel_y, kernel_x, d_spec, device, stream);
 }
 
+struct ConvRaw { const float* d_data; int H, W; };
+
 static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* const* kernels,
                      const int* kh, const int* kw, const int* kf, const unsigned char* kernel_on_device,
                      float* const* outs, int out_on_device, const double* threads, int nthreads,
-                     const fftconv_options* opt, int device, void* stream, bool pipelined) {
+                     const fftconv_options* opt, int device, void* stream, bool pipelined,
+                     const ConvRaw* raw = nullptr) {
     g_err.clear();
-    if (!d_spec) return fail(FFTCONV_ERR_NOT_GPU_ARRAY, "The data must be FFT-ed real array in GPU");
+    if (!d_spec && !raw) return fail(FFTCONV_ERR_NOT_GPU_ARRAY, "The data must be FFT-ed real array in GPU");
     if (CH < 2 || FW <= 0 || F <= 0 || (K > 0 && !outs)) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
     if (int e = check_threads(threads, nthreads)) return e;
     const int FH = (CH - 1) * 2;
@@ -710,6 +934,7 @@ static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
     a.kernels = refs.data(); a.outs = outs; a.out_on_device = out_on_device != 0;
     a.opt = opt ? *opt : fftconv_options{};
     a.pipelined = pipelined;
+    if (raw) { a.d_raw = raw->d_data; a.rawH = raw->H; a.rawW = raw->W; }
     return run_conv(*c, a, (cudaStream_t)stream);
 }
 
@@ -739,15 +964,40 @@ int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W,
     if (int e = check_threads(threads, nthreads)) return e;
     const int FH = fftconv_fft_size16(H + maxKH - 1), FW = fftconv_fft_size16(W + maxKW - 1);   // :109-112
     const int CH = FH / 2 + 1;
+    // which pipeline will serve the bank?  The overlap-save / tensor-core path tiles the raw data itself,
+    // so the full-plane R2C transform of the data (src/cudaConvolutionFFT.cu:155-168) is not needed there.
+    bool raw_path = false;
+    if (K > 0 && kernels && kh && kw && outs) {
+        int maxkh = 1, maxkw = 1;
+        for (int k = 0; k < K; ++k) {
+            maxkh = std::max(maxkh, std::min(kh[k], FH));
+            maxkw = std::max(maxkw, std::min(kw[k], FW));
+        }
+        const fftconv_options o = opt ? *opt : fftconv_options{};
+        raw_path = choose_path(o, F, FH, FW, maxkh, maxkw, K) == PATH_OSGEMM;
+    }
     void* spec = nullptr;
+    const float* d_data = data;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         DeviceGuard guard(device);
         if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
         Ctx* c;
         if (int e = ctx_get(device, &c)) return e;
-        if (int e = dev_reserve(c->dspec, sizeof(cpx) * (size_t)CH * FW * F)) return e;
-        spec = c->dspec.p;
+        if (!raw_path) {
+            if (int e = dev_reserve(c->dspec, sizeof(cpx) * (size_t)CH * FW * F)) return e;
+            spec = c->dspec.p;
+        } else if (!data_on_device) {
+            const size_t bytes = sizeof(float) * (size_t)H * W * F;
+            if (int e = dev_reserve(c->ddata, bytes)) return e;
+            CU(cudaMemcpyAsync(c->ddata.p, data, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            d_data = (const float*)c->ddata.p;
+        }
+    }
+    if (raw_path) {
+        ConvRaw raw{d_data, H, W};
+        return conv_impl(nullptr, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs, out_on_device, threads,
+                         nthreads, opt, device, stream, false, &raw);
     }
     // stream-ordered: no sync between the data transform and the bank loop (the reference
     // synchronises the device here, src/cudaConvolutionFFT.cu:168)
@@ -832,7 +1082,8 @@ long long fftconv_workspace_bytes(int device) {
     if (it == g_ctx.end()) return 0;
     const Ctx& c = it->second;
     size_t s = c.T.cap + c.Z.cap + c.stage.cap + c.desc.cap + c.outstage.cap + c.dspec.cap + c.ddata.cap +
-               c.priv.cap + c.Ag.cap + c.Wg.cap;
+               c.priv.cap + c.Ag.cap + c.Wg.cap + c.osHk.cap + c.osHd.cap + c.osA.cap + c.osB.cap + c.osP.cap +
+               c.osPlane.cap + c.osZ.cap;
     for (auto& kv : c.tw) s += sizeof(cpx) * (size_t)kv.first;
     return (long long)s;
 }
@@ -847,7 +1098,8 @@ void fftconv_release(void) {
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
         for (auto& t : c.tw) cudaFree(t.second);
-        for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg})
+        for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg,
+                          &c.osHk, &c.osHd, &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ})
             if (b->p) cudaFree(b->p);
         if (c.pinned) cudaFreeHost(c.pinned);
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);

@@ -68,7 +68,8 @@ class FFTConvError(RuntimeError):
 class Options(ctypes.Structure):
     """fftconv_options (include/fftconv.h) — all zero = exact reference behaviour."""
     _fields_ = [("correlate", ctypes.c_int), ("crop_h", ctypes.c_int), ("crop_w", ctypes.c_int),
-                ("out_ld", ctypes.c_int), ("force_generic", ctypes.c_int), ("reserved", ctypes.c_int * 3)]
+                ("out_ld", ctypes.c_int), ("force_generic", ctypes.c_int), ("path", ctypes.c_int),
+                ("reserved", ctypes.c_int * 2)]
 
 
 _lib = None

@@ -52,8 +52,11 @@ typedef struct fftconv_options {
     int crop_h;      /* >0: store only the first crop_h rows ...                              */
     int crop_w;      /* ... and crop_w columns of each plane (demoCudaConvolutionFFT.m:149)   */
     int out_ld;      /* leading dimension (floats) of a stored column; 0 = crop_h or FH       */
-    int force_generic; /* 1: bypass the 16-point-tiled fast path (testing)                    */
-    int reserved[3];
+    int force_generic; /* 1: bypass the fast paths (testing); same as path = 1               */
+    int path;        /* 0: automatic; 1: generic line-FFT pipeline; 2: 16-point-tiled SIMT
+                        pipeline; 3: overlap-save tiles + per-bin complex GEMM on tcgen05
+                        (falls back to 2 / 1 when the shape is outside that path's range)     */
+    int reserved[2];
 } fftconv_options;
 
 /* computeFFTsize16 — src/cudaConvFFTData.h:96-102.  Part of the API contract. */
