@@ -50,12 +50,12 @@ static int fail(int code, const char* fmt, ...) {
 // Optional per-kernel timing (bench.py roofline leg): every launch of a profiled kind is
 // bracketed by CUDA events on the stream it is launched on.
 enum ProfKind { PK_RELAYOUT = 0, PK_KERN_H, PK_CONV, PK_C2R, PK_DATA_H, PK_DATA_W, PK_GEN_H, PK_GEN_W, PK_GEN_C2R,
-                PK_OS_PLANE, PK_OS_DATA_H, PK_OS_DATA_W, PK_OS_KERN_H, PK_OS_KERN_W, PK_OS_GEMM, PK_OS_INV, PK_COUNT };
+                PK_OS_PLANE, PK_OS_DATA_H, PK_OS_DATA_W, PK_OS_KERN, PK_OS_GEMM, PK_OS_INV, PK_COUNT };
 static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass", "tile16_conv", "tile16_c2r",
                                            "fwd_h_pass(data)", "fwd_w_pass(data)", "fwd_h_pass(kernels)",
                                            "conv_w_pass_generic", "inv_h_pass",
                                            "os_spectrum_to_plane", "os_hpass(data tiles)", "os_wpass(data tiles)",
-                                           "os_hpass(templates)", "os_wpass(templates)", "os_gemm", "os_inverse"};
+                                           "os_kern_fft(templates)", "os_gemm", "os_inverse"};
 static bool g_prof_on = false;
 struct ProfRec { int kind; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
@@ -146,7 +146,9 @@ static int pinned_reserve(Ctx& c, size_t bytes) {
 
 template <typename K>
 static int opt_in_smem(K kernel) {
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmem));
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kernel));                 // static shared memory counts against the 227 KB
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxSmem - fa.sharedSizeBytes)));
     return 0;
 }
 
@@ -180,8 +182,8 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(tile16_conv<false>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(tile16_conv<true>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(tile16_c2r)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(os_wpass<0, 1>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(os_wpass<0, 2>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_kern_fft<1>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_kern_fft<2>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_wpass<1, 4>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
@@ -440,7 +442,7 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g) {
         if (tot <= kMaxSmem) { g.nsta = ns; g.gemm_smem = tot; break; }
     }
     if (!g.nsta) return false;
-    g.inv_smem = (size_t)OS_IG * 32 * OS_IROW * sizeof(cpx) + (size_t)OS_IG * g.Sw * (g.Sh | 1) * sizeof(float);
+    g.inv_smem = std::max((size_t)OS_IG * 32 * OS_IROW * sizeof(cpx), (size_t)OS_IG * g.Sw * (g.Sh | 1) * sizeof(float));   // staging reuses the tile buffer
     if (g.inv_smem > kMaxSmem) return false;
     return true;
 }
@@ -511,6 +513,8 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
     return 0;
 }
 
+static size_t os_kern_smem(int NF) { return (size_t)32 * (17 * 16 * NF + 2) * sizeof(cpx); }
+
 static int os_max_chunk(const OsCfg& g) {
     const int ntblk = std::max(1, os_env_int("FFTCONV_OS_NTBLK", 2));
     (void)g;
@@ -519,7 +523,6 @@ static int os_max_chunk(const OsCfg& g) {
 
 static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates) {
     const int ntblk = (KC_templates + OS_TM - 1) / OS_TM;
-    if (int e = dev_reserve(c.osHk, sizeof(cpx) * (size_t)ntblk * OS_TM * g.F * OS_CH * g.XCK)) return e;
     if (int e = dev_reserve(c.osA, (size_t)ntblk * OS_NBIN * g.NKS * g.a_stage)) return e;
     if (int e = dev_reserve(c.osP, (size_t)ntblk * g.NNB * OS_NBIN * g.p_blk)) return e;
     return 0;
@@ -529,24 +532,12 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
                     const fftconv_options& opt, cudaStream_t st) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
     {
-        OsHArgs a{};
-        a.descs = d_descs; a.nitems = nk; a.F = g.F; a.XC = g.XCK; a.H = (cpx*)c.osHk.p;
-        const long long nlines = (long long)nk * g.F * (g.XCK / 2);
-        ProfScope ps(PK_OS_KERN_H, st);
-        if (g.NFK == 1) os_hpass<0, 1><<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(a);
-        else os_hpass<0, 2><<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(a);
-        LAUNCH_CHECK();
-    }
-    {
-        OsWArgs a{};
-        a.H = (const cpx*)c.osHk.p; a.F = g.F; a.XC = g.XCK; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
-        a.rows = OS_TM; a.nblk = ntblk; a.slots_per_blk = OS_TM; a.valid_per_blk = OS_TM; a.nvalid = nk;
-        a.correlate = 0;
-        dim3 grid((ntblk * OS_TM + 31) / 32, g.NKS * g.KC, (OS_CH + OS_WR - 1) / OS_WR);
-        const size_t smem = OS_WR * 64 * 2 * 32 * sizeof(cpx);
-        ProfScope ps(PK_OS_KERN_W, st);
-        if (g.NFK == 1) os_wpass<0, 1><<<grid, 256, smem, st>>>(a);
-        else os_wpass<0, 2><<<grid, 256, smem, st>>>(a);
+        OsKArgs a{};
+        a.descs = d_descs; a.nk = nk; a.F = g.F; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
+        dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
+        ProfScope ps(PK_OS_KERN, st);
+        if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);
+        else os_kern_fft<2><<<grid, 256, os_kern_smem(2), st>>>(a);
         LAUNCH_CHECK();
     }
     {

@@ -303,6 +303,126 @@ __global__ void __launch_bounds__(256) os_wpass(OsWArgs a)
 }
 
 // ------------------------------------------------------------------------------------------------
+// os_kern_fft: templates -> A operand images in ONE kernel (pad fused into the load, 2-D 64 x 64 half
+// spectrum of a 16*NF x 16*NF support, hi/lo TF32 split, operand-image store).  Replaces the template
+// legs of os_hpass + os_wpass and their [template][F][33][XC] intermediate.
+// CTA = 16 templates x one channel pair, 256 threads.  Two phases (odd spectrum rows, then even ones) so
+// that the h-transformed rows of the 32 planes fit 70 KB (NF=1) of shared memory:
+//   h step: thread = (plane, column pair): two real columns ride as one complex sequence; the two tasks
+//           that hold rows u and 64-u are computed together and unpacked in registers
+//   w step: thread = (spectrum row, task r0, template); both channels of the pair, then 16 x (hi, lo)
+//           128-bit stores; 16 consecutive lanes write 256 contiguous bytes of the image
+// grid = (ntblk*128/16, NKS*KC).
+struct OsKArgs {
+    const SrcDesc* descs;
+    int nk, F;
+    float* img;
+    int NKS, KC;
+};
+constexpr int OS_KSL = 16;            // templates per CTA
+
+template <int NF>
+__global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
+{
+    constexpr int XC = 16 * NF, NCP = XC / 2;
+    constexpr int PS = 17 * XC + 2;                    // plane stride in cpx (+16 B: conflict-free LDS.128 across templates)
+    extern __shared__ __align__(128) unsigned char os_smem_raw[];
+    cpx* Hs = reinterpret_cast<cpx*>(os_smem_raw);     // [2 channels][16 templates][17 rows][XC]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fp = blockIdx.y;
+    const int slot0 = blockIdx.x * OS_KSL;
+    const int tblk = slot0 / OS_TM, sl0 = slot0 - tblk * OS_TM;
+    const int ks = fp / a.KC, kc = fp - ks * a.KC;
+    const size_t term_stride = (size_t)a.KC * OS_TM * 4;
+    const size_t bin_stride = (size_t)a.NKS * 2 * term_stride;
+
+#pragma unroll 1
+    for (int ph = 0; ph < 2; ++ph) {
+        // ---- h step
+        for (int line = threadIdx.x; line < 32 * NCP; line += 256) {
+            const int cp = line % NCP, pl = line / NCP;
+            const int ch = pl >> 4, slot = pl & 15;
+            const int item = slot0 + slot, f = 2 * fp + ch;
+            float4* hrow = reinterpret_cast<float4*>(Hs + (size_t)pl * PS) + cp;      // + ro * (XC/2)
+            if (item < a.nk && f < a.F) {
+                const SrcDesc d = a.descs[item];
+                const int xa = 2 * cp, xb = xa + 1;
+                const float* pa = d.ptr + ((size_t)f * d.cols + xa) * d.rows;
+                const float* pb = pa + d.rows;
+                const bool va = xa < d.cols, vb = xb < d.cols;
+                const int rows = d.rows;
+                auto ld = [&](int j) {
+                    float4 v;
+                    v.x = (va && j < rows) ? __ldg(pa + j) : 0.f;
+                    v.y = (vb && j < rows) ? __ldg(pb + j) : 0.f;
+                    v.z = (va && j + 1 < rows) ? __ldg(pa + j + 1) : 0.f;
+                    v.w = (vb && j + 1 < rows) ? __ldg(pb + j + 1) : 0.f;
+                    return v;
+                };
+                float pr[16], pi[16], qr[16], qi[16];
+                // A[u] = (Z[u] + conj Z[64-u]) / 2 (column xa),  B[u] = -i (Z[u] - conj Z[64-u]) / 2 (column xb)
+                auto put = [&](int ro, float zr, float zi, float nr, float ni) {
+                    hrow[ro * NCP] = make_float4(0.5f * (zr + nr), 0.5f * (zi - ni), 0.5f * (zi + ni), -0.5f * (zr - nr));
+                };
+                if (ph == 0) {
+                    os_fft64_task<1, NF, false>(ld, pr, pi);          // Z[4 j1 + 1]
+                    os_fft64_task<3, NF, false>(ld, qr, qi);          // Z[4 j1 + 3]
+#pragma unroll
+                    for (int j1 = 0; j1 < 8; ++j1) {
+                        put(2 * j1, pr[j1], pi[j1], qr[15 - j1], qi[15 - j1]);          // u = 4 j1 + 1
+                        put(2 * j1 + 1, qr[j1], qi[j1], pr[15 - j1], pi[15 - j1]);      // u = 4 j1 + 3
+                    }
+                } else {
+                    os_fft64_task<0, NF, false>(ld, pr, pi);          // Z[4 j1]
+                    os_fft64_task<2, NF, false>(ld, qr, qi);          // Z[4 j1 + 2]
+#pragma unroll
+                    for (int j1 = 0; j1 < 9; ++j1) put(2 * j1, pr[j1], pi[j1], pr[(16 - j1) & 15], pi[(16 - j1) & 15]);   // u = 4 j1
+#pragma unroll
+                    for (int j1 = 0; j1 < 8; ++j1) put(2 * j1 + 1, qr[j1], qi[j1], qr[15 - j1], qi[15 - j1]);              // u = 4 j1 + 2
+                }
+            } else {
+                const int nr = ph == 0 ? 16 : 17;
+                for (int ro = 0; ro < nr; ++ro) hrow[ro * NCP] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        __syncthreads();
+        // ---- w step
+        const int NR = ph == 0 ? 16 : 17;
+        const int njobs = ((NR + 1) >> 1) * 4;
+        for (int c2 = warp; c2 < njobs; c2 += 8) {
+            const int r0 = c2 & 3;
+            const int ro = (c2 >> 2) * 2 + (lane >> 4);
+            const int slot = lane & 15;
+            if (ro >= NR) continue;
+            const int u = ph == 0 ? 2 * ro + 1 : 2 * ro;
+            float re0[16], im0[16], re1[16], im1[16];
+            {
+                const float4* row = reinterpret_cast<const float4*>(Hs + (size_t)slot * PS + ro * XC);
+                auto ld = [&](int j) { return row[j >> 1]; };
+                os_fft64_task_rt<NF, false>(r0, ld, re0, im0);
+            }
+            {
+                const float4* row = reinterpret_cast<const float4*>(Hs + (size_t)(16 + slot) * PS + ro * XC);
+                auto ld = [&](int j) { return row[j >> 1]; };
+                os_fft64_task_rt<NF, false>(r0, ld, re1, im1);
+            }
+            float* base = a.img + ((size_t)tblk * OS_NBIN + (size_t)u * 64 + r0) * bin_stride + (size_t)ks * 2 * term_stride +
+                          (size_t)kc * OS_TM * 4 + (size_t)(sl0 + slot) * 4;
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                const float4 v = make_float4(re0[j1], im0[j1], re1[j1], im1[j1]);
+                const float4 hi = make_float4(os_tf32_hi(v.x), os_tf32_hi(v.y), os_tf32_hi(v.z), os_tf32_hi(v.w));
+                const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
+                float* o = base + (size_t)(4 * j1) * bin_stride;
+                *reinterpret_cast<float4*>(o) = hi;
+                *reinterpret_cast<float4*>(o + term_stride) = lo;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 / TMEM PTX wrappers (sm_100a)
 __device__ __forceinline__ void os_tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
@@ -585,37 +705,50 @@ __global__ void __launch_bounds__(512) os_inverse(OsInvArgs a)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);                        // [4][32][66]
+    float* ostage = reinterpret_cast<float*>(os_smem_raw);                 // [4][Sw][shp], reuses buf after the C2R reads
+    __shared__ int tile_y0[OS_IG], tile_x0[OS_IG];
     const int shp = a.Sh | 1;
-    float* ostage = reinterpret_cast<float*>(buf + OS_IG * 32 * OS_IROW);  // [4][Sw][shp]
     const int t = blockIdx.y;
     const int m0 = blockIdx.x * OS_IG;
     const int tblk = t / OS_TM, tl = t - tblk * OS_TM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- gather: slot = (row rr 0..31, v, g); 4 consecutive threads read one 32-byte sector of P
-    for (int s = threadIdx.x; s < 32 * 64 * OS_IG; s += 512) {
-        const int gq = s & 3, v = (s >> 2) & 63, rr = s >> 8;
+    if (threadIdx.x < OS_IG) {
+        const int m = m0 + threadIdx.x;
+        const int tj = m / a.nth, ti = m - tj * a.nth;
+        tile_y0[threadIdx.x] = m < a.NT ? ti * a.Sh : a.crop_h;            // out of range -> nothing stored
+        tile_x0[threadIdx.x] = m < a.NT ? tj * a.Sw : a.crop_w;
+    }
+    // ---- gather: thread = (tile gq, column v, row parity); 4 consecutive threads read one 32-byte sector of P;
+    //      all 17 loads of a thread are in flight together
+    {
+        const int gq = threadIdx.x & 3, v = (threadIdx.x >> 2) & 63, rh = threadIdx.x >> 8;
         const int m = m0 + gq;
-        cpx z = make_float2(0.f, 0.f);
+        cpx z[16];
         if (m < a.NT) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
-            const float* prow = a.P + ((size_t)((size_t)tblk * a.NNB + nblk) * OS_NBIN * OS_TM + tl) * a.RS + 2 * ml;
             const size_t bstride = (size_t)OS_TM * a.RS;
-            if (rr == 0) {
-                const cpx x0 = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)v * bstride));
-                const cpx x32 = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)(32 * 64 + v) * bstride));
-                z = make_float2(x0.x - x32.y, x0.y + x32.x);               // X0 + i X32
-            } else {
-                z = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)(rr * 64 + v) * bstride));
+            const float* prow = a.P + ((size_t)((size_t)tblk * a.NNB + nblk) * OS_NBIN * OS_TM + tl) * a.RS + 2 * ml +
+                                (size_t)(rh * 64 + v) * bstride;
+#pragma unroll
+            for (int it = 0; it < 16; ++it) z[it] = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)(it * 128) * bstride));
+            if (rh == 0) {
+                const cpx x32 = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)(32 * 64) * bstride));
+                z[0] = make_float2(z[0].x - x32.y, z[0].y + x32.x);        // X0 + i X32
             }
+        } else {
+#pragma unroll
+            for (int it = 0; it < 16; ++it) z[it] = make_float2(0.f, 0.f);
         }
-        buf[(gq * 32 + rr) * OS_IROW + v] = z;
+        cpx* dst = buf + (gq * 32 + rh) * OS_IROW + v;
+#pragma unroll
+        for (int it = 0; it < 16; ++it) dst[it * 2 * OS_IROW] = z[it];
     }
     __syncthreads();
+    const int r0 = warp & 3;
+    const int line = (warp >> 2) * 32 + lane;                              // 0..127
     // ---- inverse along w, in place: line = (tile, row), 4 tasks per line on 4 warps
     {
-        const int r0 = warp & 3;
-        const int line = (warp >> 2) * 32 + lane;                          // 0..127 = g*32 + rr
         cpx* rowp = buf + line * OS_IROW;
         float re[16], im[16];
         auto ld = [&](int j) { return *reinterpret_cast<const float4*>(rowp + j); };
@@ -627,13 +760,12 @@ __global__ void __launch_bounds__(512) os_inverse(OsInvArgs a)
     __syncthreads();
     // ---- C2R along h: line = (tile, column pair), only column pairs that hold valid outputs
     {
-        const int r0 = warp & 3;
-        const int line = (warp >> 2) * 32 + lane;
         const int gq = line >> 5, p = line & 31;
         const int xa = 2 * p;
-        if (xa + 1 >= a.ox0 && m0 + gq < a.NT) {
+        const bool active = xa + 1 >= a.ox0 && m0 + gq < a.NT;
+        float re[16], im[16];
+        if (active) {
             const cpx* tb = buf + gq * 32 * OS_IROW + xa;
-            float re[16], im[16];
             // Z[j] = Ya[j] + i Yb[j] for j <= 32, conj(Ya[64-j]) + i conj(Yb[64-j]) above; row 0 carries
             // (y0, y32) of both columns as (re, im)
             auto ld1 = [&](int j) -> cpx {
@@ -645,30 +777,35 @@ __global__ void __launch_bounds__(512) os_inverse(OsInvArgs a)
             };
             auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
             os_fft64_task_rt<4, true>(r0, ld, re, im);
+        }
+        __syncthreads();                                                   // every read of buf is done: reuse it as ostage
+        if (active) {
             float* oa = ostage + ((size_t)gq * a.Sw + (xa - a.ox0)) * shp;
             float* ob = oa + shp;
+            const bool wa = xa >= a.ox0;
 #pragma unroll
             for (int j1 = 0; j1 < 16; ++j1) {
                 const int y = 4 * j1 + r0 - a.oy0;
                 if (y >= 0) {
-                    if (xa >= a.ox0) oa[y] = re[j1] * a.scale;
+                    if (wa) oa[y] = re[j1] * a.scale;
                     ob[y] = im[j1] * a.scale;
                 }
             }
         }
     }
     __syncthreads();
-    // ---- store the valid block of every tile (h contiguous)
+    // ---- store the valid block of every tile: one warp per column, lanes along h (contiguous in the plane)
     float* out = a.outs[t];
-    const int per_tile = a.Sw * a.Sh;
-    for (int s = threadIdx.x; s < OS_IG * per_tile; s += 512) {
-        const int gq = s / per_tile, rem = s - gq * per_tile;
-        const int x = rem / a.Sh, y = rem - x * a.Sh;
-        const int m = m0 + gq;
-        if (m >= a.NT) continue;
-        const int ti = m % a.nth, tj = m / a.nth;
-        const int Y = ti * a.Sh + y, X = tj * a.Sw + x;
-        if (Y < a.crop_h && X < a.crop_w) out[(size_t)X * a.out_ld + Y] = ostage[((size_t)gq * a.Sw + x) * shp + y];
+#pragma unroll 1
+    for (int gq = 0; gq < OS_IG; ++gq) {
+        const int Y0 = tile_y0[gq], X0 = tile_x0[gq];
+        const int ny = min(a.Sh, a.crop_h - Y0);
+        if (ny <= 0) continue;
+        for (int x = warp; x < a.Sw && X0 + x < a.crop_w; x += 16) {
+            const float* src = ostage + ((size_t)gq * a.Sw + x) * shp;
+            float* dst = out + (size_t)(X0 + x) * a.out_ld + Y0;
+            for (int y = lane; y < ny; y += 32) dst[y] = src[y];
+        }
     }
 }
 
