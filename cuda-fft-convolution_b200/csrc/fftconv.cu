@@ -50,11 +50,11 @@ static int fail(int code, const char* fmt, ...) {
 // Optional per-kernel timing (bench.py roofline leg): every launch of a profiled kind is
 // bracketed by CUDA events on the stream it is launched on.
 enum ProfKind { PK_RELAYOUT = 0, PK_KERN_H, PK_CONV, PK_C2R, PK_DATA_H, PK_DATA_W, PK_GEN_H, PK_GEN_W, PK_GEN_C2R,
-                PK_OS_PLANE, PK_OS_DATA_H, PK_OS_DATA_W, PK_OS_KERN, PK_OS_GEMM, PK_OS_INV, PK_COUNT };
+                PK_OS_PLANE, PK_OS_DATA, PK_OS_KERN, PK_OS_GEMM, PK_OS_INV, PK_COUNT };
 static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass", "tile16_conv", "tile16_c2r",
                                            "fwd_h_pass(data)", "fwd_w_pass(data)", "fwd_h_pass(kernels)",
                                            "conv_w_pass_generic", "inv_h_pass",
-                                           "os_spectrum_to_plane", "os_hpass(data tiles)", "os_wpass(data tiles)",
+                                           "os_spectrum_to_plane", "os_data_fft(tiles)",
                                            "os_kern_fft(templates)", "os_gemm", "os_inverse"};
 static bool g_prof_on = false;
 struct ProfRec { int kind; cudaEvent_t a, b; };
@@ -109,7 +109,7 @@ struct Ctx {
     bool inited = false;
     std::map<int, cpx*> tw;          // n -> device twiddle table e^{-2 pi i j / n}
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
-    DevBuf osHk, osHd, osA, osB, osP, osPlane, osZ;     // overlap-save / tcgen05 path scratch
+    DevBuf osA, osB, osP, osPlane, osZ;     // overlap-save / tcgen05 path scratch
     void* pinned = nullptr;          // host staging (descriptors, packed kernels)
     size_t pinned_cap = 0;
     cudaEvent_t pinned_free = nullptr;   // recorded after the last async copy out of `pinned`
@@ -184,7 +184,7 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(tile16_c2r)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_kern_fft<1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_kern_fft<2>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(os_wpass<1, 4>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_data_fft)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
@@ -442,7 +442,7 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g) {
         if (tot <= kMaxSmem) { g.nsta = ns; g.gemm_smem = tot; break; }
     }
     if (!g.nsta) return false;
-    g.inv_smem = std::max((size_t)OS_IG * 32 * OS_IROW * sizeof(cpx), (size_t)OS_IG * g.Sw * (g.Sh | 1) * sizeof(float));   // staging reuses the tile buffer
+    g.inv_smem = (size_t)OS_IG * OS_ITILE * sizeof(cpx);
     if (g.inv_smem > kMaxSmem) return false;
     return true;
 }
@@ -489,25 +489,15 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
         LAUNCH_CHECK();
         src.ptr = plane; src.rows = FH; src.cols = FW;
     }
-    if (int e = dev_reserve(c.osHd, sizeof(cpx) * (size_t)g.NT * F * OS_CH * 64)) return e;
     if (int e = dev_reserve(c.osB, (size_t)g.NNB * OS_NBIN * g.b_buf)) return e;
     {
-        OsHArgs a{};
-        a.descs = nullptr; a.src = src; a.nitems = g.NT; a.F = F; a.XC = 64; a.H = (cpx*)c.osHd.p;
-        a.FH = FH; a.FW = FW; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
-        const long long nlines = (long long)g.NT * F * 32;
-        ProfScope ps(PK_OS_DATA_H, st);
-        os_hpass<1, 4><<<(unsigned)((nlines + 63) / 64), 256, 0, st>>>(a);
-        LAUNCH_CHECK();
-    }
-    {
-        OsWArgs a{};
-        a.H = (const cpx*)c.osHd.p; a.F = F; a.XC = 64; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC;
-        a.rows = g.NMMA; a.nblk = g.NNB; a.slots_per_blk = g.NMMA / 2; a.valid_per_blk = g.NTn; a.nvalid = g.NT;
+        OsDArgs a{};
+        a.src = src; a.F = F; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
+        a.FH = FH; a.FW = FW; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.NTn = g.NTn;
         a.correlate = correlate;
-        dim3 grid((g.NNB * (g.NMMA / 2) + 31) / 32, g.NKS * g.KC, (OS_CH + OS_WR - 1) / OS_WR);
-        ProfScope ps(PK_OS_DATA_W, st);
-        os_wpass<1, 4><<<grid, 256, OS_WR * 64 * 2 * 32 * sizeof(cpx), st>>>(a);
+        dim3 grid(g.NT, g.NKS * g.KC);
+        ProfScope ps(PK_OS_DATA, st);
+        os_data_fft<<<grid, 128, OS_DATA_SMEM, st>>>(a);
         LAUNCH_CHECK();
     }
     return 0;
@@ -565,10 +555,9 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
-        a.scale = 1.0f / (64.0f * 64.0f);
         dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
         ProfScope ps(PK_OS_INV, st);
-        os_inverse<<<grid, 512, g.inv_smem, st>>>(a);
+        os_inverse<<<grid, 256, g.inv_smem, st>>>(a);
         LAUNCH_CHECK();
     }
     return 0;
@@ -1073,7 +1062,7 @@ long long fftconv_workspace_bytes(int device) {
     if (it == g_ctx.end()) return 0;
     const Ctx& c = it->second;
     size_t s = c.T.cap + c.Z.cap + c.stage.cap + c.desc.cap + c.outstage.cap + c.dspec.cap + c.ddata.cap +
-               c.priv.cap + c.Ag.cap + c.Wg.cap + c.osHk.cap + c.osHd.cap + c.osA.cap + c.osB.cap + c.osP.cap +
+               c.priv.cap + c.Ag.cap + c.Wg.cap + c.osA.cap + c.osB.cap + c.osP.cap +
                c.osPlane.cap + c.osZ.cap;
     for (auto& kv : c.tw) s += sizeof(cpx) * (size_t)kv.first;
     return (long long)s;
@@ -1090,7 +1079,7 @@ void fftconv_release(void) {
         cudaDeviceSynchronize();
         for (auto& t : c.tw) cudaFree(t.second);
         for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg,
-                          &c.osHk, &c.osHd, &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ})
+                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ})
             if (b->p) cudaFree(b->p);
         if (c.pinned) cudaFreeHost(c.pinned);
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);

@@ -10,8 +10,9 @@
 // what the tensor cores want.  fp32 parity (rel-L2 <= 1e-5) rules out plain TF32, so the real-valued
 // form of the product runs as 3xTF32 (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM.
 //
-//   os_hpass<TEMPLATES|DATA>   pad / window gather fused into the load, 64-point real FFT along h
-//   os_wpass<A|B>              64-point FFT along w, hi/lo split, store as tcgen05 operand images
+//   os_kern_fft                templates -> A operand images: zero pad fused into the load, pruned 2-D 64 x 64
+//                              half spectrum in shared memory, hi/lo TF32 split, operand-image store
+//   os_data_fft                overlap-save window gather (zero fill, circular wrap) -> 2-D spectrum -> B images
 //   os_gemm                    TMA bulk copies -> smem operand images -> tcgen05.mma (kind::tf32,
 //                              M=128 templates, N=2*tiles, K=2*F) -> TMEM -> bulk store of P
 //   os_inverse                 per (template, tile): 2-D C2R inverse, scale, valid-region store (crop fused)
@@ -24,7 +25,8 @@
 // Operand images (K-major, no swizzle; one 16-byte unit = 4 consecutive k = channels (2c,2c+1) x (re,im)):
 //   Aimg [tblk][bin][ks][term hi/lo][kc][128 templates][4]      (MMA A: rows = templates)
 //   Bimg [nblk][bin][ks][term hi/lo][kc][NMMA rows     ][4]      (MMA B: rows = (tile, re/im column))
-//   P    [tblk][nblk][bin][128 templates][RS]  fp32, (re,im) per tile
+//   P    [tblk][nblk][u][128 templates][v][RS]  fp32, (re,im) per tile (bin = u*64 + v); a template's 64 bins of a
+//        spectrum row are one contiguous 64*RS*4-byte run, which is what os_inverse gathers
 // Core matrix = 8 rows x 16 B contiguous -> SBO = 128 B, LBO (next 16-byte k unit) = rows * 16 B.
 #pragma once
 #include <cstdint>
@@ -40,6 +42,10 @@ constexpr int OS_CH = 33;             // half-spectrum rows of a tile
 constexpr int OS_NBIN = OS_CH * OS_T; // 2112 frequency bins per tile
 constexpr int OS_TM = 128;            // templates per GEMM block (MMA M)
 constexpr int OS_ACC_COLS = 128;      // TMEM columns per accumulator buffer (2 buffers)
+constexpr int OS_IG = 4;              // tiles per CTA of os_inverse
+constexpr int OS_IROW = 66;           // complex row stride of a 64-point line in shared memory (16-byte aligned rows)
+constexpr int OS_ICOL = 33;           // os_inverse: complex stride of a spectrum column (odd: conflict-free 64-bit accesses)
+constexpr int OS_ITILE = 64 * OS_ICOL + 4;   // os_inverse: tile stride (columns >= 32 sit 2 elements further; +32 B per tile)
 
 // ------------------------------------------------------------------------------------------------
 // compile-time twiddles  w64^e = cos(2 pi e/64) - i sin(2 pi e/64)  (double Taylor series, folded to
@@ -118,189 +124,46 @@ __device__ __forceinline__ void os_fft64_task_rt(int r0, Load&& ld, float* re, f
     }
 }
 
+// Two tasks of a full 64-sample sequence that share their loads and the first radix-4 butterfly:
+// outputs X[4*j1 + P] -> (reA, imA) and X[4*j1 + P + 2] -> (reB, imB), P = 0 or 1.
+//     P = 0:  a = x0 + x2, b = x1 + x3:  z_0 = a + b,            z_2 = (a - b) w64^{2c}
+//     P = 1:  a = x0 - x2, b = x1 - x3:  z_1 = (a -+ i b) w64^c, z_3 = (a +- i b) w64^{3c}    (x_q = x[c + 16 q])
+template <int P, bool INV, class Load>
+__device__ __forceinline__ void os_fft64_pair(Load&& ld, float* reA, float* imA, float* reB, float* imB) {
+    os_static_for<0, 8>([&](auto c2c) {
+        constexpr int c2 = decltype(c2c)::value;
+        const float4 v0 = ld(2 * c2), v1 = ld(2 * c2 + 16), v2 = ld(2 * c2 + 32), v3 = ld(2 * c2 + 48);
+        os_static_for<0, 2>([&](auto hc) {
+            constexpr int h = decltype(hc)::value;
+            constexpr int c = 2 * c2 + h;
+            const float x0r = h ? v0.z : v0.x, x0i = h ? v0.w : v0.y;
+            const float x1r = h ? v1.z : v1.x, x1i = h ? v1.w : v1.y;
+            const float x2r = h ? v2.z : v2.x, x2i = h ? v2.w : v2.y;
+            const float x3r = h ? v3.z : v3.x, x3i = h ? v3.w : v3.y;
+            if (P == 0) {
+                const float ar = x0r + x2r, ai = x0i + x2i, br = x1r + x3r, bi = x1i + x3i;
+                reA[c] = ar + br; imA[c] = ai + bi;
+                os_twiddle<2 * c, INV>(ar - br, ai - bi, reB[c], imB[c]);
+            } else {
+                const float ar = x0r - x2r, ai = x0i - x2i, br = x1r - x3r, bi = x1i - x3i;
+                // forward: z1 = a - i b, z3 = a + i b ; inverse: the other way round
+                const float mr = ar + bi, mi = ai - br;     // a - i b
+                const float pr = ar - bi, pi = ai + br;     // a + i b
+                os_twiddle<c, INV>(INV ? pr : mr, INV ? pi : mi, reA[c], imA[c]);
+                os_twiddle<3 * c, INV>(INV ? mr : pr, INV ? mi : pi, reB[c], imB[c]);
+            }
+        });
+    });
+    dft_regs<16, INV>(reA, imA);
+    dft_regs<16, INV>(reB, imB);
+}
+
 __device__ __forceinline__ int os_wrap(int i, int n) {
     i %= n;
     return i < 0 ? i + n : i;
 }
 
-// ------------------------------------------------------------------------------------------------
-// os_hpass: 64-point real-to-half-complex transform along h of every column of every plane.
-//   MODE 0 (templates): plane = (template, channel), XC = 16*NF columns, 16*NF rows, zero pad fused
-//   MODE 1 (data tiles): plane = (tile, channel), 64 columns x 64 rows gathered from the source plane
-//                        with zero fill beyond (srcH, srcW) and circular wrap at (FH, FW)
-// Two real columns are packed into one complex line; a line is 4 tasks (r0 = 0..3) on 4 warps.
-// out H: [plane][33][XC] complex.   grid.x = ceil(planes * XC/2 / 64), 256 threads.
-struct OsHArgs {
-    const SrcDesc* descs;   // MODE 0: one per template
-    SrcDesc src;            // MODE 1: the source plane [F][cols][rows]
-    int nitems, F, XC;
-    cpx* H;
-    int FH, FW, nth, Sh, Sw, oy0, ox0;    // MODE 1 only
-};
-
-template <int MODE, int NF>
-__global__ void __launch_bounds__(256) os_hpass(OsHArgs a)
-{
-    __shared__ cpx Zs[64][65];
-    const int ncp = a.XC >> 1;
-    const long long nlines = (long long)a.nitems * a.F * ncp;
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int r0 = wq & 3;
-    const int ll = (wq >> 2) * 32 + lane;
-    const long long line = (long long)blockIdx.x * 64 + ll;
-    if (line < nlines) {
-        const int cp = (int)(line % ncp);
-        const long long plane = line / ncp;
-        const int f = (int)(plane % a.F);
-        const int item = (int)(plane / a.F);
-        float re[16], im[16];
-        if (MODE == 0) {
-            const SrcDesc d = a.descs[item];
-            const int xa = 2 * cp, xb = xa + 1;
-            const float* pa = d.ptr + ((size_t)f * d.cols + xa) * d.rows;
-            const float* pb = pa + d.rows;
-            const bool va = xa < d.cols, vb = xb < d.cols;
-            const int rows = d.rows;
-            auto ld = [&](int j) {
-                float4 v;
-                v.x = (va && j < rows) ? __ldg(pa + j) : 0.f;
-                v.y = (vb && j < rows) ? __ldg(pb + j) : 0.f;
-                v.z = (va && j + 1 < rows) ? __ldg(pa + j + 1) : 0.f;
-                v.w = (vb && j + 1 < rows) ? __ldg(pb + j + 1) : 0.f;
-                return v;
-            };
-            os_fft64_task_rt<NF, false>(r0, ld, re, im);
-        } else {
-            const SrcDesc d = a.src;
-            const int ti = item % a.nth, tj = item / a.nth;
-            const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
-            const int gxa = os_wrap(ox + 2 * cp, a.FW), gxb = os_wrap(ox + 2 * cp + 1, a.FW);
-            const bool va = gxa < d.cols, vb = gxb < d.cols;
-            const float* pa = d.ptr + ((size_t)f * d.cols + gxa) * d.rows;
-            const float* pb = d.ptr + ((size_t)f * d.cols + gxb) * d.rows;
-            const int rows = d.rows, FH = a.FH;
-            auto ld = [&](int j) {
-                const int g0 = os_wrap(oy + j, FH), g1 = os_wrap(oy + j + 1, FH);
-                float4 v;
-                v.x = (va && g0 < rows) ? __ldg(pa + g0) : 0.f;
-                v.y = (vb && g0 < rows) ? __ldg(pb + g0) : 0.f;
-                v.z = (va && g1 < rows) ? __ldg(pa + g1) : 0.f;
-                v.w = (vb && g1 < rows) ? __ldg(pb + g1) : 0.f;
-                return v;
-            };
-            os_fft64_task_rt<NF, false>(r0, ld, re, im);
-        }
-#pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) Zs[ll][4 * j1 + r0] = make_float2(re[j1], im[j1]);
-    }
-    __syncthreads();
-    // split the packed pair:  A[u] = (Z[u] + conj Z[64-u])/2,  B[u] = -i (Z[u] - conj Z[64-u])/2
-    const int ppc = 64 / ncp;                                 // whole planes per CTA
-    const long long nplanes = (long long)a.nitems * a.F;
-    const int total = ppc * OS_CH * a.XC;
-    for (int idx = threadIdx.x; idx < total; idx += 256) {
-        const int x = idx % a.XC;
-        const int u = (idx / a.XC) % OS_CH;
-        const int pl = idx / (a.XC * OS_CH);
-        const long long plane = (long long)blockIdx.x * ppc + pl;
-        if (plane >= nplanes) continue;
-        const int l2 = pl * ncp + (x >> 1);
-        const cpx zu = Zs[l2][u];
-        const cpx zn = Zs[l2][(64 - u) & 63];
-        cpx o;
-        if (x & 1) o = make_float2(0.5f * (zu.y + zn.y), -0.5f * (zu.x - zn.x));
-        else       o = make_float2(0.5f * (zu.x + zn.x), 0.5f * (zu.y - zn.y));
-        a.H[((size_t)plane * OS_CH + u) * a.XC + x] = o;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// os_wpass: 64-point transform along w of the rows of H, written as tcgen05 operand images.
-//   MODE 0 -> Aimg (rows = templates);  MODE 1 -> Bimg (rows = (tile, re/im column))
-// CTA = 32 slots (lane = slot) x one channel pair x R=2 spectrum rows; the 16 outputs of a task go through
-// a shared staging buffer so that the image is written in 512-byte (A) / 1-KB (B) runs.
-// grid = (ceil(nblk*slots_per_blk/32), NKS*KC channel pairs, ceil(33/2)); 256 threads; smem 64 KB.
-struct OsWArgs {
-    const cpx* H;           // [item][F][33][XC]
-    int F, XC;
-    float* img;
-    int NKS, KC;
-    int rows;               // rows of one operand block (A: 128, B: NMMA)
-    int nblk;               // operand blocks (A: template blocks, B: tile blocks)
-    int slots_per_blk;      // A: 128, B: NMMA/2
-    int valid_per_blk;      // A: 128, B: tiles per block
-    int nvalid;             // A: templates in this chunk, B: NT
-    int correlate;
-};
-constexpr int OS_WR = 2;
-
 __device__ __forceinline__ float os_tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
-template <int MODE, int NF>
-__global__ void __launch_bounds__(256) os_wpass(OsWArgs a)
-{
-    extern __shared__ __align__(128) unsigned char os_smem_raw[];
-    cpx (*stag)[2][32] = reinterpret_cast<cpx (*)[2][32]>(os_smem_raw);      // [R*64 bins][2 channels][32 slots]
-    const int lane = threadIdx.x & 31, wq = threadIdx.x >> 5;
-    const int slot0 = blockIdx.x * 32, fp = blockIdx.y, u0 = blockIdx.z * OS_WR;
-    int item = -1;
-    {
-        const int slot = slot0 + lane;
-        const int blk = slot / a.slots_per_blk, sl = slot - blk * a.slots_per_blk;
-        const int it = blk * a.valid_per_blk + sl;
-        if (blk < a.nblk && sl < a.valid_per_blk && it < a.nvalid) item = it;
-    }
-    for (int wt = wq; wt < 2 * OS_WR * 4; wt += 8) {
-        const int r0 = wt & 3, fq = (wt >> 2) & 1, r = wt >> 3;
-        const int u = u0 + r, f = 2 * fp + fq;
-        float re[16], im[16];
-        if (item >= 0 && f < a.F && u < OS_CH) {
-            const float4* row = reinterpret_cast<const float4*>(a.H + (((size_t)item * a.F + f) * OS_CH + u) * a.XC);
-            auto ld = [&](int j) { return __ldg(row + (j >> 1)); };
-            os_fft64_task_rt<NF, false>(r0, ld, re, im);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { re[j] = 0.f; im[j] = 0.f; }
-        }
-#pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) stag[r * 64 + 4 * j1 + r0][fq][lane] = make_float2(re[j1], im[j1]);
-    }
-    __syncthreads();
-    const int ks = fp / a.KC, kc = fp - ks * a.KC;
-    const size_t term_stride = (size_t)a.KC * a.rows * 4;                 // floats between hi and lo images
-    for (int idx = threadIdx.x; idx < OS_WR * 64 * 32; idx += 256) {
-        const int sl_lane = idx & 31, bl = idx >> 5;
-        const int u = u0 + (bl >> 6);
-        if (u >= OS_CH) continue;
-        const int slot = slot0 + sl_lane;
-        const int blk = slot / a.slots_per_blk, sl = slot - blk * a.slots_per_blk;
-        if (blk >= a.nblk) continue;
-        const int bin = u * 64 + (bl & 63);
-        const cpx c0 = stag[bl][0][sl_lane], c1 = stag[bl][1][sl_lane];
-        float* base = a.img + ((((size_t)blk * OS_NBIN + bin) * a.NKS + ks) * 2) * term_stride + (size_t)kc * a.rows * 4;
-        if (MODE == 0) {
-            const float4 v = make_float4(c0.x, c0.y, c1.x, c1.y);
-            const float4 hi = make_float4(os_tf32_hi(v.x), os_tf32_hi(v.y), os_tf32_hi(v.z), os_tf32_hi(v.w));
-            const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-            float4* o = reinterpret_cast<float4*>(base + (size_t)sl * 4);
-            o[0] = hi;
-            *reinterpret_cast<float4*>(base + term_stride + (size_t)sl * 4) = lo;
-        } else {
-            // out_re = sum a*c - b*d, out_im = sum a*d + b*c  with K^ = a + i b (A rows), D^ = c + i d
-            // correlate: K^ -> conj(K^):  out_re = sum a*c + b*d, out_im = sum a*d - b*c
-            float4 vr, vi;
-            if (!a.correlate) { vr = make_float4(c0.x, -c0.y, c1.x, -c1.y); vi = make_float4(c0.y, c0.x, c1.y, c1.x); }
-            else              { vr = make_float4(c0.x, c0.y, c1.x, c1.y);   vi = make_float4(c0.y, -c0.x, c1.y, -c1.x); }
-            const float4 hr = make_float4(os_tf32_hi(vr.x), os_tf32_hi(vr.y), os_tf32_hi(vr.z), os_tf32_hi(vr.w));
-            const float4 hq = make_float4(os_tf32_hi(vi.x), os_tf32_hi(vi.y), os_tf32_hi(vi.z), os_tf32_hi(vi.w));
-            float4* o = reinterpret_cast<float4*>(base + (size_t)(2 * sl) * 4);
-            o[0] = hr; o[1] = hq;
-            float4* ol = reinterpret_cast<float4*>(base + term_stride + (size_t)(2 * sl) * 4);
-            ol[0] = make_float4(vr.x - hr.x, vr.y - hr.y, vr.z - hr.z, vr.w - hr.w);
-            ol[1] = make_float4(vi.x - hq.x, vi.y - hq.y, vi.z - hq.z, vi.w - hq.w);
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------
 // os_kern_fft: templates -> A operand images in ONE kernel (pad fused into the load, 2-D 64 x 64 half
@@ -419,6 +282,133 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
             }
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// os_data_fft: source plane -> B operand images in ONE kernel.  CTA = (overlap-save tile, channel pair):
+// the two 64 x 64 windows are gathered with coalesced loads (zero fill beyond the source, circular wrap at
+// FH x FW), transformed along h (two real columns per complex sequence, two threads per line) and along w
+// in shared memory, split hi/lo and stored as the (re-row, im-row) pair of the tile in the B image.
+// grid = (NT, NKS*KC), 128 threads.
+struct OsDArgs {
+    SrcDesc src;            // [F][cols][rows]
+    int F, nth, Sh, Sw, oy0, ox0, FH, FW;
+    float* img;
+    int NKS, KC, NMMA, NTn;
+    int correlate;
+};
+constexpr int OS_DRAW = 65;           // raw window column stride (floats)
+constexpr size_t OS_DATA_SMEM = 2 * 64 * OS_DRAW * sizeof(float) + 2 * 33 * OS_IROW * sizeof(cpx);
+
+__global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
+{
+    extern __shared__ __align__(128) unsigned char os_smem_raw[];
+    float* raw = reinterpret_cast<float*>(os_smem_raw);                              // [2][64][65]
+    cpx* Hs = reinterpret_cast<cpx*>(os_smem_raw + 2 * 64 * OS_DRAW * sizeof(float));   // [2][33][66]
+    const int m = blockIdx.x, fp = blockIdx.y;
+    const int tj = m / a.nth, ti = m - tj * a.nth;
+    const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- gather: thread = (row y, column parity); lanes run along h (contiguous in the source)
+    {
+        const int y = threadIdx.x & 63;
+        const int gy = os_wrap(oy + y, a.FH);
+        const bool vy = gy < a.src.rows;
+        for (int ch = 0; ch < 2; ++ch) {
+            const int f = 2 * fp + ch;
+            const float* pl = a.src.ptr + (size_t)f * a.src.cols * a.src.rows + gy;
+            float* dst = raw + (size_t)ch * 64 * OS_DRAW + y;
+            int gx = os_wrap(ox + (threadIdx.x >> 6), a.FW);
+            const bool vf = vy && f < a.F;
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                float v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {                      // 16 independent loads in flight
+                    v[k] = (vf && gx < a.src.cols) ? __ldg(pl + (size_t)gx * a.src.rows) : 0.f;
+                    gx += 2;
+                    if (gx >= a.FW) gx -= a.FW;                     // FW >= 16 > 2: one conditional subtract is enough
+                }
+#pragma unroll
+                for (int k = 0; k < 16; ++k) dst[((threadIdx.x >> 6) + 2 * (16 * b + k)) * OS_DRAW] = v[k];
+            }
+        }
+    }
+    __syncthreads();
+    const int par = warp >> 1;                       // warp-uniform: tasks (par, par + 2)
+    // ---- h step: line = (channel, column pair)
+    {
+        const int line = threadIdx.x & 63;
+        const int ch = line >> 5, cp = line & 31;
+        const float* ca = raw + ((size_t)ch * 64 + 2 * cp) * OS_DRAW;
+        const float* cb = ca + OS_DRAW;
+        auto ld = [&](int j) { return make_float4(ca[j], cb[j], ca[j + 1], cb[j + 1]); };
+        float pr[16], pi[16], qr[16], qi[16];
+        float4* hcol = reinterpret_cast<float4*>(Hs + (size_t)ch * 33 * OS_IROW) + cp;       // + u * (OS_IROW/2)
+        auto put = [&](int u, float zr, float zi, float nr, float ni) {
+            hcol[u * (OS_IROW / 2)] = make_float4(0.5f * (zr + nr), 0.5f * (zi - ni), 0.5f * (zi + ni), -0.5f * (zr - nr));
+        };
+        if (par == 0) {
+            os_fft64_pair<0, false>(ld, pr, pi, qr, qi);              // Z[4 j1], Z[4 j1 + 2]
+#pragma unroll
+            for (int j1 = 0; j1 < 9; ++j1) put(4 * j1, pr[j1], pi[j1], pr[(16 - j1) & 15], pi[(16 - j1) & 15]);
+#pragma unroll
+            for (int j1 = 0; j1 < 8; ++j1) put(4 * j1 + 2, qr[j1], qi[j1], qr[15 - j1], qi[15 - j1]);
+        } else {
+            os_fft64_pair<1, false>(ld, pr, pi, qr, qi);              // Z[4 j1 + 1], Z[4 j1 + 3]
+#pragma unroll
+            for (int j1 = 0; j1 < 8; ++j1) {
+                put(4 * j1 + 1, pr[j1], pi[j1], qr[15 - j1], qi[15 - j1]);
+                put(4 * j1 + 3, qr[j1], qi[j1], pr[15 - j1], pi[15 - j1]);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- w step: thread = (spectrum row u, task pair); both channels, then the operand-image stores
+    {
+        const int u = threadIdx.x & 63;
+        if (u < OS_CH) {
+            const int nblk = m / a.NTn, sl = m - nblk * a.NTn;
+            const int ks = fp / a.KC, kc = fp - ks * a.KC;
+            const size_t term_stride = (size_t)a.KC * a.NMMA * 4;
+            const size_t bin_stride = (size_t)a.NKS * 2 * term_stride;
+            float* base = a.img + ((size_t)nblk * OS_NBIN + (size_t)u * 64 + par) * bin_stride + (size_t)ks * 2 * term_stride +
+                          (size_t)kc * a.NMMA * 4 + (size_t)(2 * sl) * 4;
+            float r0A[16], i0A[16], r0B[16], i0B[16], r1A[16], i1A[16], r1B[16], i1B[16];
+            {
+                const cpx* row = Hs + (size_t)u * OS_IROW;
+                auto ld = [&](int j) { return *reinterpret_cast<const float4*>(row + j); };
+                if (par == 0) os_fft64_pair<0, false>(ld, r0A, i0A, r0B, i0B);
+                else          os_fft64_pair<1, false>(ld, r0A, i0A, r0B, i0B);
+            }
+            {
+                const cpx* row = Hs + (size_t)(33 + u) * OS_IROW;
+                auto ld = [&](int j) { return *reinterpret_cast<const float4*>(row + j); };
+                if (par == 0) os_fft64_pair<0, false>(ld, r1A, i1A, r1B, i1B);
+                else          os_fft64_pair<1, false>(ld, r1A, i1A, r1B, i1B);
+            }
+            // out_re = sum a*c - b*d, out_im = sum a*d + b*c  with K^ = a + i b (A rows), D^ = c + i d
+            // correlate: K^ -> conj(K^):  out_re = sum a*c + b*d, out_im = sum a*d - b*c
+            // the 1/(64*64) of the inverse transform rides here: a power of two, so the scaling is exact
+            const float sc = 1.0f / 4096.0f, sg = a.correlate ? -sc : sc;
+            auto emit = [&](float* o, float c0x, float c0y, float c1x, float c1y) {
+                const float4 vr = make_float4(sc * c0x, -sg * c0y, sc * c1x, -sg * c1y);
+                const float4 vi = make_float4(sc * c0y, sg * c0x, sc * c1y, sg * c1x);
+                const float4 hr = make_float4(os_tf32_hi(vr.x), os_tf32_hi(vr.y), os_tf32_hi(vr.z), os_tf32_hi(vr.w));
+                const float4 hq = make_float4(os_tf32_hi(vi.x), os_tf32_hi(vi.y), os_tf32_hi(vi.z), os_tf32_hi(vi.w));
+                float4* oh = reinterpret_cast<float4*>(o);
+                oh[0] = hr; oh[1] = hq;
+                float4* ol = reinterpret_cast<float4*>(o + term_stride);
+                ol[0] = make_float4(vr.x - hr.x, vr.y - hr.y, vr.z - hr.z, vr.w - hr.w);
+                ol[1] = make_float4(vi.x - hq.x, vi.y - hq.y, vi.z - hq.z, vi.w - hq.w);
+            };
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                emit(base + (size_t)(4 * j1) * bin_stride, r0A[j1], i0A[j1], r1A[j1], i1A[j1]);
+                emit(base + (size_t)(4 * j1 + 2) * bin_stride, r0B[j1], i0B[j1], r1B[j1], i1B[j1]);
+            }
+        }
     }
 }
 
@@ -617,8 +607,7 @@ __global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
             const uint32_t acc = nit & 1;
             mbar_wait(&acc_full[acc], (nit >> 1) & 1);
             os_tc_fence_after();
-            if (et == 0) os_bulk_wait_read0();        // previous bulk store has finished reading the staging
-            os_named_bar_sync(1, 128);
+            os_bulk_wait_read0();                     // this thread's previous bulk store has finished reading its staging row
             const uint32_t taddr = tmem_base + acc * OS_ACC_COLS + ((uint32_t)(q * 32) << 16);
             float* srow = stage_sm + (size_t)row * g.RS;
             for (int c0 = 0; c0 < g.RS; c0 += 16) {
@@ -637,14 +626,14 @@ __global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
             }
             os_tc_fence_before();
             os_mbar_arrive(&acc_empty[acc]);
-            fence_proxy_async();
-            os_named_bar_sync(2, 128);
-            if (et == 0) {
-                float* dst = g.P + ((size_t)((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM * g.RS;
-                os_bulk_s2g(dst, stage_sm, p_blk);
+            fence_proxy_async();                      // this thread's staging writes -> visible to the bulk-copy engine
+            {   // row `row` (template) of the block -> P[tblk][nblk][u][template][v][RS]: one 16*k-byte bulk copy per thread
+                const int u = bin >> 6, v = bin & 63;
+                float* dst = g.P + ((((size_t)((size_t)tblk * g.NNB + nblk) * OS_CH + u) * OS_TM + row) * 64 + v) * g.RS;
+                os_bulk_s2g(dst, srow, (uint32_t)g.RS * 4u);
             }
         }
-        if (et == 0) os_bulk_wait0();
+        os_bulk_wait0();
     }
     os_tc_fence_before();
     __syncthreads();
@@ -666,8 +655,8 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
     const size_t a_stage = (size_t)2 * g.KC * OS_TM * 4, b_stage = (size_t)2 * g.KC * g.NMMA * 4;   // floats
     const float* A = g.Aimg + ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
     const float* B = g.Bimg + (size_t)key * g.NKS * b_stage;
-    float* P = g.P + ((size_t)((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM * g.RS;
     const int t = threadIdx.x;
+    float* P = g.P + ((((size_t)((size_t)tblk * g.NNB + nblk) * OS_CH + (bin >> 6)) * OS_TM + t) * 64 + (bin & 63)) * g.RS;
     for (int n = 0; n < g.RS; ++n) {
         float acc = 0.f;
         for (int ks = 0; ks < g.NKS; ++ks)
@@ -681,130 +670,146 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
                 acc = fmaf(ah.z + al.z, bh.z + bl.z, acc);
                 acc = fmaf(ah.w + al.w, bh.w + bl.w, acc);
             }
-        P[(size_t)t * g.RS + n] = acc;
+        P[n] = acc;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// os_inverse: CTA = (template, group of 4 tiles).  Per tile: gather the 33 x 64 product spectrum from P,
-// inverse 64-point transform along w (rows u = 1..31 complex; rows 0 and 32 are spectra of real sequences
-// and ride together as one complex row), then C2R along h (two columns per complex line), scale by
-// 1/4096, and store the valid (65-maxkh) x (65-maxkw) block of the tile into the output plane.
-// grid = (ceil(NT/4), templates in chunk); 512 threads; smem = 4*32*66*8 + 4*Sw*(Sh|1)*4.
+// os_inverse: CTA = (template, group of 4 tiles), 256 threads, two threads per 64-point line.
+//   gather   the 33 x 64 product spectrum of each tile from P into shared memory, column (v) major;
+//            columns 0 and 32 (spectra of real sequences along h) are combined into one complex column
+//   pass 1   inverse along h: line v (0..31) = column v for rows 0..32 and the conjugate of column 64-v above
+//            (Hermitian symmetry of the 2-D spectrum of a real tile); result in place
+//   pass 2   C2R along w: line y packs rows y and y+32 into one complex sequence; lanes run along h, so every
+//            store instruction writes one contiguous run of a plane column -- the valid (65-maxkh) x (65-maxkw)
+//            block goes straight from registers to the output plane (crop fused), no staging
+// The 1/4096 of the inverse transform is folded into the B operand images (os_data_fft).
+// grid = (ceil(NT/4), templates in chunk); smem = 4 * OS_ITILE * 8 B.
 struct OsInvArgs {
     const float* P;
     float* const* outs;
     int nk, NNB, NTn, RS, NT, nth, Sh, Sw, oy0, ox0;
     int FH, FW, crop_h, crop_w, out_ld;
-    float scale;
 };
-constexpr int OS_IG = 4;          // tiles per CTA
-constexpr int OS_IROW = 66;       // complex row stride (16-byte aligned rows, conflict-free LDS.128)
 
-__global__ void __launch_bounds__(512) os_inverse(OsInvArgs a)
+__device__ __forceinline__ int os_icol(int v) { return v * OS_ICOL + ((v >> 5) << 1); }
+
+// gather of one spectrum column (33 rows) of one tile from P; FIX: combine columns 0 and 32 (lanes l, l^4)
+template <bool FIX>
+__device__ __forceinline__ void os_inv_gather(const cpx* pp, size_t ustride, cpx* dst, bool c0, bool c32) {
+    const unsigned mask = FIX ? __activemask() : 0u;       // lanes l and l^4 belong to the same tile: both valid or both not
+    auto put = [&](int u, cpx z) {
+        if (FIX) {
+            const float ox = __shfl_xor_sync(mask, z.x, 4), oy = __shfl_xor_sync(mask, z.y, 4);
+            if (c0) z = make_float2(z.x - oy, z.y + ox);                   // column 0 := Z[u][0] + i Z[u][32]
+            if (c32) z = make_float2(ox + z.y, oy - z.x);                  // column 32 := Z[u][0] - i Z[u][32]
+        }
+        dst[u] = z;
+    };
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        cpx z[16];
+#pragma unroll
+        for (int it = 0; it < 16; ++it) { z[it] = __ldg(pp); pp += ustride; }      // 16 loads in flight
+#pragma unroll
+        for (int it = 0; it < 16; ++it) put(half * 16 + it, z[it]);
+    }
+    put(32, __ldg(pp));
+}
+
+__global__ void __launch_bounds__(256, 3) os_inverse(OsInvArgs a)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
-    cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);                        // [4][32][66]
-    float* ostage = reinterpret_cast<float*>(os_smem_raw);                 // [4][Sw][shp], reuses buf after the C2R reads
-    __shared__ int tile_y0[OS_IG], tile_x0[OS_IG];
-    const int shp = a.Sh | 1;
+    cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);                        // [4][OS_ITILE]
     const int t = blockIdx.y;
     const int m0 = blockIdx.x * OS_IG;
     const int tblk = t / OS_TM, tl = t - tblk * OS_TM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    if (threadIdx.x < OS_IG) {
-        const int m = m0 + threadIdx.x;
-        const int tj = m / a.nth, ti = m - tj * a.nth;
-        tile_y0[threadIdx.x] = m < a.NT ? ti * a.Sh : a.crop_h;            // out of range -> nothing stored
-        tile_x0[threadIdx.x] = m < a.NT ? tj * a.Sw : a.crop_w;
-    }
-    // ---- gather: thread = (tile gq, column v, row parity); 4 consecutive threads read one 32-byte sector of P;
-    //      all 17 loads of a thread are in flight together
+    // ---- gather: thread = (tile gq, column v); the 4 tiles of a group share one 32-byte sector of P;
+    //      lanes l and l^4 hold columns v and v+32, so columns 0 and 32 can be combined with shuffles
     {
-        const int gq = threadIdx.x & 3, v = (threadIdx.x >> 2) & 63, rh = threadIdx.x >> 8;
+        const int gq = threadIdx.x & 3, v = ((threadIdx.x >> 3) & 31) | (((threadIdx.x >> 2) & 1) << 5);
         const int m = m0 + gq;
-        cpx z[16];
+        cpx* dst = buf + gq * OS_ITILE + os_icol(v);
         if (m < a.NT) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
-            const size_t bstride = (size_t)OS_TM * a.RS;
-            const float* prow = a.P + ((size_t)((size_t)tblk * a.NNB + nblk) * OS_NBIN * OS_TM + tl) * a.RS + 2 * ml +
-                                (size_t)(rh * 64 + v) * bstride;
-#pragma unroll
-            for (int it = 0; it < 16; ++it) z[it] = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)(it * 128) * bstride));
-            if (rh == 0) {
-                const cpx x32 = __ldg(reinterpret_cast<const cpx*>(prow + (size_t)(32 * 64) * bstride));
-                z[0] = make_float2(z[0].x - x32.y, z[0].y + x32.x);        // X0 + i X32
+            const size_t ustride = (size_t)OS_TM * 32 * a.RS;              // cpx units; P[tblk][nblk][u][template][v][RS]
+            const cpx* pp = reinterpret_cast<const cpx*>(
+                a.P + (((size_t)((size_t)tblk * a.NNB + nblk) * OS_CH * OS_TM + tl) * 64 + v) * a.RS + 2 * ml);
+            if (warp != 0) {
+                os_inv_gather<false>(pp, ustride, dst, false, false);
+            } else {                                                       // warp 0 holds columns 0..3 and 32..35
+                os_inv_gather<true>(pp, ustride, dst, v == 0, v == 32);
             }
         } else {
 #pragma unroll
-            for (int it = 0; it < 16; ++it) z[it] = make_float2(0.f, 0.f);
+            for (int u = 0; u <= 32; ++u) dst[u] = make_float2(0.f, 0.f);
         }
-        cpx* dst = buf + (gq * 32 + rh) * OS_IROW + v;
-#pragma unroll
-        for (int it = 0; it < 16; ++it) dst[it * 2 * OS_IROW] = z[it];
     }
     __syncthreads();
-    const int r0 = warp & 3;
-    const int line = (warp >> 2) * 32 + lane;                              // 0..127
-    // ---- inverse along w, in place: line = (tile, row), 4 tasks per line on 4 warps
+    const int par = warp >> 2;                                             // warp-uniform: tasks (par, par + 2)
+    const int gq = warp & 3;                                               // one warp = the 32 lines of one tile
+    cpx* tile = buf + gq * OS_ITILE;
+    // ---- pass 1: inverse along h, in place.  x[u] = col_v[u] (u <= 32), conj(col_mv[64-u]) (u > 32)
     {
-        cpx* rowp = buf + line * OS_IROW;
-        float re[16], im[16];
-        auto ld = [&](int j) { return *reinterpret_cast<const float4*>(rowp + j); };
-        os_fft64_task_rt<4, true>(r0, ld, re, im);
+        const int v = lane, mv = lane ? 64 - lane : 32;
+        cpx* cv = tile + os_icol(v);
+        cpx* cm = tile + os_icol(mv);
+        float reA[16], imA[16], reB[16], imB[16];
+        auto ld1 = [&](int u) -> cpx {
+            if (u <= 32) return cv[u];
+            const cpx q = cm[64 - u];
+            return make_float2(q.x, -q.y);
+        };
+        auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
+        if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
+        else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
         __syncthreads();
 #pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) rowp[4 * j1 + r0] = make_float2(re[j1], im[j1]);
+        for (int j1 = 0; j1 < 16; ++j1) {                                  // Y[y]: y < 32 -> col v, y >= 32 -> col mv
+            const int ya = 4 * j1 + par, yb = ya + 2;                      // (compile-time split: j1 < 8 <=> y < 32)
+            if (j1 < 8) { cv[ya] = make_float2(reA[j1], imA[j1]); cv[yb] = make_float2(reB[j1], imB[j1]); }
+            else        { cm[ya - 32] = make_float2(reA[j1], imA[j1]); cm[yb - 32] = make_float2(reB[j1], imB[j1]); }
+        }
     }
     __syncthreads();
-    // ---- C2R along h: line = (tile, column pair), only column pairs that hold valid outputs
+    // ---- pass 2: C2R along w.  W[v] = Y[y][v] + i Y[y+32][v]; outputs straight to the plane
     {
-        const int gq = line >> 5, p = line & 31;
-        const int xa = 2 * p;
-        const bool active = xa + 1 >= a.ox0 && m0 + gq < a.NT;
-        float re[16], im[16];
-        if (active) {
-            const cpx* tb = buf + gq * 32 * OS_IROW + xa;
-            // Z[j] = Ya[j] + i Yb[j] for j <= 32, conj(Ya[64-j]) + i conj(Yb[64-j]) above; row 0 carries
-            // (y0, y32) of both columns as (re, im)
-            auto ld1 = [&](int j) -> cpx {
-                if (j == 0) { const float4 q = *reinterpret_cast<const float4*>(tb); return make_float2(q.x, q.z); }
-                if (j == 32) { const float4 q = *reinterpret_cast<const float4*>(tb); return make_float2(q.y, q.w); }
-                if (j < 32) { const float4 q = *reinterpret_cast<const float4*>(tb + j * OS_IROW); return make_float2(q.x - q.w, q.y + q.z); }
-                const float4 q = *reinterpret_cast<const float4*>(tb + (64 - j) * OS_IROW);
-                return make_float2(q.x + q.w, q.z - q.y);
-            };
-            auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
-            os_fft64_task_rt<4, true>(r0, ld, re, im);
-        }
-        __syncthreads();                                                   // every read of buf is done: reuse it as ostage
-        if (active) {
-            float* oa = ostage + ((size_t)gq * a.Sw + (xa - a.ox0)) * shp;
-            float* ob = oa + shp;
-            const bool wa = xa >= a.ox0;
+        const int y = lane;
+        const int m = m0 + gq;
+        if (m >= a.NT) return;                                             // (no barrier below)
+        const cpx* ty = tile + y;
+        float reA[16], imA[16], reB[16], imB[16];
+        auto ld1 = [&](int v) -> cpx {
+            if (v == 0) { const cpx p0 = ty[os_icol(0)], p32 = ty[os_icol(32)]; return make_float2(p0.x, p32.x); }
+            if (v == 32) { const cpx p0 = ty[os_icol(0)], p32 = ty[os_icol(32)]; return make_float2(p0.y, p32.y); }
+            if (v < 32) { const cpx p = ty[os_icol(v)], q = ty[os_icol(64 - v)]; return make_float2(p.x - q.y, p.y + q.x); }
+            const cpx p = ty[os_icol(64 - v)], q = ty[os_icol(v)];
+            return make_float2(p.x + q.y, q.x - p.y);
+        };
+        auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
+        if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
+        else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
+        const int tj = m / a.nth, ti = m - tj * a.nth;
+        const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
+        const int ny = min(a.Sh, a.crop_h - Y0), nx = min(a.Sw, a.crop_w - X0);
+        const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
+        const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
+        float* dst = a.outs[t] + (size_t)X0 * a.out_ld + Y0 + ylo;
 #pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {
-                const int y = 4 * j1 + r0 - a.oy0;
-                if (y >= 0) {
-                    if (wa) oa[y] = re[j1] * a.scale;
-                    ob[y] = im[j1] * a.scale;
-                }
+        for (int j1 = 0; j1 < 16; ++j1) {
+            const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+            if (xa >= 0 && xa < nx) {
+                float* d = dst + (size_t)xa * a.out_ld;
+                if (wlo) d[0] = reA[j1];
+                if (whi) d[32] = imA[j1];
             }
-        }
-    }
-    __syncthreads();
-    // ---- store the valid block of every tile: one warp per column, lanes along h (contiguous in the plane)
-    float* out = a.outs[t];
-#pragma unroll 1
-    for (int gq = 0; gq < OS_IG; ++gq) {
-        const int Y0 = tile_y0[gq], X0 = tile_x0[gq];
-        const int ny = min(a.Sh, a.crop_h - Y0);
-        if (ny <= 0) continue;
-        for (int x = warp; x < a.Sw && X0 + x < a.crop_w; x += 16) {
-            const float* src = ostage + ((size_t)gq * a.Sw + x) * shp;
-            float* dst = out + (size_t)(X0 + x) * a.out_ld + Y0;
-            for (int y = lane; y < ny; y += 32) dst[y] = src[y];
+            if (xb >= 0 && xb < nx) {
+                float* d = dst + (size_t)xb * a.out_ld;
+                if (wlo) d[0] = reB[j1];
+                if (whi) d[32] = imB[j1];
+            }
         }
     }
 }
