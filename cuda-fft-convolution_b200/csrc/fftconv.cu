@@ -408,7 +408,8 @@ static int tile16_chunk(Ctx& c, int FH, int FW, int F, int maxkh, int maxkw, con
 struct OsCfg {
     int F, FH, FW, maxkh, maxkw;
     int NFK, XCK;                 // template transform: 16*NFK leading samples per side
-    int Sh, Sw, nth, ntw, NT;     // valid outputs per tile side, tile grid
+    int Sh, Sw, nth, ntw, NT;     // valid outputs per tile side, tile grid, tiles of the whole batch
+    int nimg, NTimg;              // images in the batch, tiles per image
     int NKS, KC;                  // K stages per item, 16-byte k units per stage (even)
     int NNB, NTn, NMMA, RS;       // tile blocks, tiles per block, MMA N, P row stride (floats)
     int nsta;                     // A ring depth
@@ -416,7 +417,7 @@ struct OsCfg {
     size_t a_stage, b_buf, p_blk; // bytes
 };
 
-static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g) {
+static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int nimg = 1) {
     g = OsCfg{};
     if (maxkh > 32 || maxkw > 32 || maxkh < 1 || maxkw < 1) return false;
     g.F = F; g.FH = FH; g.FW = FW; g.maxkh = maxkh; g.maxkw = maxkw;
@@ -424,7 +425,8 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g) {
     g.XCK = 16 * g.NFK;
     g.Sh = 65 - maxkh; g.Sw = 65 - maxkw;
     g.nth = (FH + g.Sh - 1) / g.Sh; g.ntw = (FW + g.Sw - 1) / g.Sw;
-    g.NT = g.nth * g.ntw;
+    g.nimg = nimg; g.NTimg = g.nth * g.ntw;
+    g.NT = g.nimg * g.NTimg;
     g.NKS = (2 * F + 31) / 32;
     const int units = (2 * F + 3) / 4;
     g.KC = ((units + g.NKS - 1) / g.NKS + 1) & ~1;
@@ -492,7 +494,7 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
     if (int e = dev_reserve(c.osB, (size_t)g.NNB * OS_NBIN * g.b_buf)) return e;
     {
         OsDArgs a{};
-        a.src = src; a.F = F; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
+        a.src = src; a.F = F; a.nth = g.nth; a.NTimg = g.NTimg; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = FH; a.FW = FW; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.NTn = g.NTn;
         a.correlate = correlate;
         dim3 grid(g.NT, g.NKS * g.KC);
@@ -519,7 +521,7 @@ static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates) {
 }
 
 static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
-                    const fftconv_options& opt, cudaStream_t st) {
+                    const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
     {
         OsKArgs a{};
@@ -550,8 +552,8 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
     {
         OsInvArgs a{};
         a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS;
-        a.NT = g.NT; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
-        a.FH = g.FH; a.FW = g.FW;
+        a.NT = g.NT; a.NTimg = g.NTimg; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
+        a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
@@ -580,6 +582,8 @@ struct ConvArgs {
     bool pipelined;                // use the side copy stream (Streams entry point)
     const float* d_raw = nullptr;  // one-shot entry point: the raw data [F][rawW][rawH] on the device
     int rawH = 0, rawW = 0;
+    int nimg = 1;                  // batched entry point: nimg images [nimg][F][rawW][rawH] (raw, device, overlap-save path
+                                   // only); outs then holds nimg*K device planes, image-major
 };
 
 enum ConvPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TILE16 = 2, PATH_OSGEMM = 3 };
@@ -671,11 +675,13 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         maxkh = std::max(maxkh, std::min(a.kernels[k].kh, FH));
         maxkw = std::max(maxkw, std::min(a.kernels[k].kw, FW));
     }
-    const int path = choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
+    const int path = a.nimg > 1 ? PATH_OSGEMM : choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
     const bool tile16 = path == PATH_TILE16;
     const bool osg = path == PATH_OSGEMM;
     OsCfg og;
-    if (osg) os_config(F, FH, FW, maxkh, maxkw, og);
+    if (osg && !os_config(F, FH, FW, maxkh, maxkw, og, a.nimg))
+        return fail(FFTCONV_ERR_UNSUPPORTED, "batch outside the range of the overlap-save path");
+    const size_t NO = (size_t)K * a.nimg;                          // output planes
 
     // ---- chunking: bound the scratch held per chunk
     const size_t plane = plane_floats(a, FH);
@@ -716,7 +722,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (int e = dev_reserve(c.outstage, sizeof(float) * plane * KC * 2)) return e;
 
     // descriptors / kcols / out pointers for ALL kernels go through pinned staging once
-    const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int) + sizeof(float*)) * (size_t)K + 64;
+    const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int)) * (size_t)K + sizeof(float*) * NO + 64;
     size_t host_kernel_bytes = 0;
     for (int k = 0; k < K; ++k)
         if (!a.kernels[k].on_device) host_kernel_bytes += sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
@@ -728,56 +734,61 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     CU(cudaEventSynchronize(c.pinned_free));
     SrcDesc* h_desc = reinterpret_cast<SrcDesc*>(c.pinned);
     float** h_outp = reinterpret_cast<float**>(h_desc + K);
-    int* h_kcols = reinterpret_cast<int*>(h_outp + K);
+    int* h_kcols = reinterpret_cast<int*>(h_outp + NO);
     SrcDesc* d_desc = reinterpret_cast<SrcDesc*>(c.desc.p);
     float** d_outp = reinterpret_cast<float**>(d_desc + K);
-    int* d_kcols = reinterpret_cast<int*>(d_outp + K);
+    int* d_kcols = reinterpret_cast<int*>(d_outp + NO);
 
-    // upload host kernels: contiguous runs are coalesced into single copies
+    // chunk boundaries.  Host outputs: the D2H stream is the bottleneck (PCIe), so the first chunk is kept
+    // small -- its results start flowing to the host while the rest of the bank is still being computed.
+    std::vector<int> bounds{0};
     {
-        size_t off = 0;
-        int k = 0;
-        while (k < K) {
-            if (a.kernels[k].on_device) {
-                h_desc[k].ptr = a.kernels[k].ptr;
-                ++k;
-                continue;
-            }
-            const float* run_src = a.kernels[k].ptr;
-            const size_t run_off = off;
-            size_t run_bytes = 0;
-            int j = k;
-            while (j < K && !a.kernels[j].on_device &&
-                   reinterpret_cast<const char*>(a.kernels[j].ptr) == reinterpret_cast<const char*>(run_src) + run_bytes) {
-                const size_t b = sizeof(float) * (size_t)a.kernels[j].kh * a.kernels[j].kw * F;
-                h_desc[j].ptr = reinterpret_cast<const float*>(reinterpret_cast<char*>(c.stage.p) + off);
-                off += b; run_bytes += b;
-                ++j;
-            }
-            CU(cudaMemcpyAsync(reinterpret_cast<char*>(c.stage.p) + run_off, run_src, run_bytes,
-                               cudaMemcpyHostToDevice, st));
-            k = j;
+        int first = KC;
+        if (!a.out_on_device && K > KC) first = std::max(1, osg ? std::min(KC, OS_TM) : KC / 4);
+        for (int k = std::min(first, K); ; k = std::min(k + KC, K)) {
+            bounds.push_back(k);
+            if (k == K) break;
         }
     }
+    // device address of every kernel (host kernels are staged; offsets fixed up front, copies issued per chunk)
+    std::vector<size_t> stage_off((size_t)K + 1, 0);
     for (int k = 0; k < K; ++k) {
+        const size_t b = a.kernels[k].on_device ? 0 : sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
+        stage_off[k + 1] = stage_off[k] + b;
+        h_desc[k].ptr = a.kernels[k].on_device ? a.kernels[k].ptr
+                                               : reinterpret_cast<const float*>(reinterpret_cast<char*>(c.stage.p) + stage_off[k]);
         h_desc[k].rows = a.kernels[k].kh;
         h_desc[k].cols = a.kernels[k].kw;
         h_kcols[k] = a.kernels[k].kw;
-        h_outp[k] = a.out_on_device ? a.outs[k]
-                                    : reinterpret_cast<float*>(c.outstage.p) + plane * (size_t)((k % KC) + ((k / KC) & 1) * KC);
     }
+    for (size_t ch = 0; ch + 1 < bounds.size(); ++ch)
+        for (int k = bounds[ch]; k < bounds[ch + 1]; ++k)
+            h_outp[k] = a.out_on_device ? a.outs[k]
+                                        : reinterpret_cast<float*>(c.outstage.p) + plane * (size_t)((k - bounds[ch]) + (ch & 1) * KC);
+    for (size_t i = K; i < NO; ++i) h_outp[i] = a.outs[i];         // images 1.. of a batch (device planes)
     CU(cudaMemcpyAsync(c.desc.p, c.pinned, desc_bytes, cudaMemcpyHostToDevice, st));
     CU(cudaEventRecord(c.pinned_free, st));
 
     // ---- chunk loop.  Device outputs: one stream.  Host outputs: the D2H of chunk i runs on the
-    // side stream while chunk i+1 computes (double-buffered out staging).
-    int chunk = 0;
-    for (int k0 = 0; k0 < K; k0 += KC, ++chunk) {
-        const int nk = std::min(KC, K - k0);
+    // side stream while chunk i+1 uploads its kernels and computes (double-buffered out staging).
+    for (size_t chunk = 0; chunk + 1 < bounds.size(); ++chunk) {
+        const int k0 = bounds[chunk], nk = bounds[chunk + 1] - k0;
+        // upload this chunk's host kernels: contiguous runs are coalesced into single copies
+        for (int k = k0; k < k0 + nk;) {
+            if (a.kernels[k].on_device) { ++k; continue; }
+            const char* run_src = reinterpret_cast<const char*>(a.kernels[k].ptr);
+            int j = k;
+            while (j < k0 + nk && !a.kernels[j].on_device &&
+                   reinterpret_cast<const char*>(a.kernels[j].ptr) == run_src + (stage_off[j] - stage_off[k]))
+                ++j;
+            CU(cudaMemcpyAsync(reinterpret_cast<char*>(c.stage.p) + stage_off[k], run_src, stage_off[j] - stage_off[k],
+                               cudaMemcpyHostToDevice, st));
+            k = j;
+        }
         if (!a.out_on_device && chunk >= 2) CU(cudaStreamWaitEvent(st, c.ev[chunk & 1], 0));   // staging half free?
         int e;
         if (osg)
-            e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st);
+            e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
@@ -886,7 +897,7 @@ int fftconv_fft_data_clamp(const float* data, int data_on_device, int H, int W, 
     return fft_data_impl(data, data_on_device, H, W, F, KH, KW, PAD_CLAMP, kernel_y, kernel_x, d_spec, device, stream);
 }
 
-struct ConvRaw { const float* d_data; int H, W; };
+struct ConvRaw { const float* d_data; int H, W; int nimg = 1; };
 
 static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* const* kernels,
                      const int* kh, const int* kw, const int* kf, const unsigned char* kernel_on_device,
@@ -902,7 +913,8 @@ static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
         return fail(FFTCONV_ERR_INVALID_INPUT, "spectrum dims (%d x %d) do not come from computeFFTsize16", CH, FW);
     std::vector<KernelRef> refs;
     if (int e = build_kernel_refs(K, kernels, kh, kw, kf, kernel_on_device, F, FH, FW, refs)) return e;
-    for (int k = 0; k < K; ++k)
+    const size_t nout = (size_t)K * (raw ? raw->nimg : 1);
+    for (size_t k = 0; k < nout; ++k)
         if (!outs[k]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceGuard guard(device);
@@ -914,7 +926,7 @@ static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
     a.kernels = refs.data(); a.outs = outs; a.out_on_device = out_on_device != 0;
     a.opt = opt ? *opt : fftconv_options{};
     a.pipelined = pipelined;
-    if (raw) { a.d_raw = raw->d_data; a.rawH = raw->H; a.rawW = raw->W; }
+    if (raw) { a.d_raw = raw->d_data; a.rawH = raw->H; a.rawW = raw->W; a.nimg = raw->nimg; }
     return run_conv(*c, a, (cudaStream_t)stream);
 }
 
@@ -985,6 +997,58 @@ int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W,
     if (e) return e;
     return conv_impl((const fftconv_float2*)spec, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs,
                      out_on_device, threads, nthreads, opt, device, stream, false);
+}
+
+int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int W, int F, int maxKH, int maxKW, int K,
+                       const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                       const unsigned char* kernel_on_device, float* const* outs, int out_on_device,
+                       const fftconv_options* opt, int device, void* stream) {
+    g_err.clear();
+    if (!data || N <= 0 || H <= 0 || W <= 0 || F <= 0 || maxKH <= 0 || maxKW <= 0)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
+    if (K > 0 && (!kernels || !kh || !kw || !outs)) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    const int FH = fftconv_fft_size16(H + maxKH - 1), FW = fftconv_fft_size16(W + maxKW - 1);
+    const int CH = FH / 2 + 1;
+    const size_t img = (size_t)H * W * F;
+    const fftconv_options o = opt ? *opt : fftconv_options{};
+    int maxkh = 1, maxkw = 1;
+    for (int k = 0; k < K; ++k) {
+        maxkh = std::max(maxkh, std::min(kh[k], FH));
+        maxkw = std::max(maxkw, std::min(kw[k], FW));
+    }
+    OsCfg g1;
+    const bool batched = K > 0 && N > 1 && out_on_device && !o.correlate && !o.force_generic &&
+                         (o.path == PATH_AUTO || o.path == PATH_OSGEMM) && os_config(F, FH, FW, maxkh, maxkw, g1, 1);
+    if (!batched) {                     // image by image through the single-image entry point
+        for (int n = 0; n < N; ++n)
+            if (int e = fftconv_convolution_fft(data + (size_t)n * img, data_on_device, H, W, F, maxKH, maxKW, K, kernels, kh,
+                                                kw, kf, kernel_on_device, outs + (size_t)n * K, out_on_device, nullptr, 0,
+                                                opt, device, stream))
+                return e;
+        return 0;
+    }
+    // the images of a group only add tiles to the N dimension of the per-bin GEMM; the group is sized so that
+    // the product spectra of one template chunk stay within a few GB
+    const int G = std::max(1, std::min(N, 1280 / g1.NTimg));
+    for (int n0 = 0; n0 < N; n0 += G) {
+        const int nimg = std::min(G, N - n0);
+        const float* d_data = data + (size_t)n0 * img;
+        if (!data_on_device) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            DeviceGuard guard(device);
+            if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+            Ctx* c;
+            if (int e = ctx_get(device, &c)) return e;
+            if (int e = dev_reserve(c->ddata, sizeof(float) * img * nimg)) return e;
+            CU(cudaMemcpyAsync(c->ddata.p, d_data, sizeof(float) * img * nimg, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            d_data = (const float*)c->ddata.p;
+        }
+        ConvRaw raw{d_data, H, W, nimg};
+        if (int e = conv_impl(nullptr, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs + (size_t)n0 * K, 1,
+                              nullptr, 0, opt, device, stream, false, &raw))
+            return e;
+    }
+    return 0;
 }
 
 int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* d_bank, int kh, int kw,

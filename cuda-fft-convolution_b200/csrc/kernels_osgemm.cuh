@@ -290,10 +290,10 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
 // the two 64 x 64 windows are gathered with coalesced loads (zero fill beyond the source, circular wrap at
 // FH x FW), transformed along h (two real columns per complex sequence, two threads per line) and along w
 // in shared memory, split hi/lo and stored as the (re-row, im-row) pair of the tile in the B image.
-// grid = (NT, NKS*KC), 128 threads.
+// grid = (NT, NKS*KC), 128 threads.  NT = images * tiles per image (batched calls: the images only add tiles).
 struct OsDArgs {
-    SrcDesc src;            // [F][cols][rows]
-    int F, nth, Sh, Sw, oy0, ox0, FH, FW;
+    SrcDesc src;            // image 0: [F][cols][rows]; image n follows at n*F*cols*rows
+    int F, nth, NTimg, Sh, Sw, oy0, ox0, FH, FW;
     float* img;
     int NKS, KC, NMMA, NTn;
     int correlate;
@@ -307,7 +307,8 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     float* raw = reinterpret_cast<float*>(os_smem_raw);                              // [2][64][65]
     cpx* Hs = reinterpret_cast<cpx*>(os_smem_raw + 2 * 64 * OS_DRAW * sizeof(float));   // [2][33][66]
     const int m = blockIdx.x, fp = blockIdx.y;
-    const int tj = m / a.nth, ti = m - tj * a.nth;
+    const int img = m / a.NTimg, mt = m - img * a.NTimg;          // tiles of a batch are numbered image-major
+    const int tj = mt / a.nth, ti = mt - tj * a.nth;
     const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // ---- gather: thread = (row y, column parity); lanes run along h (contiguous in the source)
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
         const bool vy = gy < a.src.rows;
         for (int ch = 0; ch < 2; ++ch) {
             const int f = 2 * fp + ch;
-            const float* pl = a.src.ptr + (size_t)f * a.src.cols * a.src.rows + gy;
+            const float* pl = a.src.ptr + ((size_t)img * a.F + f) * a.src.cols * a.src.rows + gy;
             float* dst = raw + (size_t)ch * 64 * OS_DRAW + y;
             int gx = os_wrap(ox + (threadIdx.x >> 6), a.FW);
             const bool vf = vy && f < a.F;
@@ -688,8 +689,9 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
 struct OsInvArgs {
     const float* P;
     float* const* outs;
-    int nk, NNB, NTn, RS, NT, nth, Sh, Sw, oy0, ox0;
+    int nk, NNB, NTn, RS, NT, NTimg, nth, Sh, Sw, oy0, ox0;
     int FH, FW, crop_h, crop_w, out_ld;
+    int out_img_stride;     // plane of (image n, template t) = outs[n * out_img_stride + t]
 };
 
 __device__ __forceinline__ int os_icol(int v) { return v * OS_ICOL + ((v >> 5) << 1); }
@@ -791,12 +793,13 @@ __global__ void __launch_bounds__(256, 3) os_inverse(OsInvArgs a)
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
         else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
-        const int tj = m / a.nth, ti = m - tj * a.nth;
+        const int img = m / a.NTimg, mt = m - img * a.NTimg;
+        const int tj = mt / a.nth, ti = mt - tj * a.nth;
         const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
         const int ny = min(a.Sh, a.crop_h - Y0), nx = min(a.Sw, a.crop_w - X0);
         const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
         const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
-        float* dst = a.outs[t] + (size_t)X0 * a.out_ld + Y0 + ylo;
+        float* dst = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0 + ylo;
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) {
             const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;

@@ -29,7 +29,7 @@ __all__ = [
     "FFTConvError", "GpuArray", "gpuArray", "gather", "computeFFTsize16", "computeFFTsize",
     "cudaFFTData", "cudaConvFFTData", "cudaConvolutionFFT", "cudaConvFFTDataStreams",
     "cudaFFTDataClamp", "modulateAndNormalize", "Options", "conv_bank", "fft_data_device",
-    "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
+    "conv_batch", "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -38,7 +38,7 @@ LIB_PATH = os.environ.get("FFTCONV_LIB") or os.path.join(_HERE, "libfftconv.so")
 EXPORTED_SYMBOLS = [
     "fftconv_fft_size16", "fftconv_fft_size_pow2", "fftconv_fft_data", "fftconv_fft_data_clamp",
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
-    "fftconv_conv_bank", "fftconv_modulate_and_normalize", "fftconv_launch_count",
+    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
 ]
@@ -95,6 +95,8 @@ def lib() -> ctypes.CDLL:
                                                     c_vp, c_vp, c_int, c_vp, c_int]
         L.fftconv_convolution_fft.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                               c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_conv_batch.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]
         L.fftconv_conv_bank.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]
         L.fftconv_modulate_and_normalize.argtypes = [c_vp, c_vp, c_ll, c_int, c_vp]
         L.fftconv_launch_count.restype = c_ll
@@ -413,6 +415,32 @@ def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Op
     st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
     op = ctypes.byref(options) if options is not None else None
     rc = lib().fftconv_conv_bank(spec_t.data_ptr(), CH, FW, F, K, bank_t.data_ptr(), kh, kw, out_t.data_ptr(), op, dev, st)
+    _check(rc, ERRID_CONV)
+    return out_t
+
+
+def conv_batch(data_t, bank_t, out_t=None, options: Optional[Options] = None, stream=None):
+    """Batched images against one device-resident bank (fftconv_conv_batch): data_t float32 [N][F][W][H],
+    bank_t float32 [K][F][kw][kh] (torch, cuda) -> out_t [N][K][FW][FH].  Stream-ordered, no host sync."""
+    torch = _torch()
+    N, F, W, H = (int(x) for x in data_t.shape)
+    K, Fk, kw, kh = (int(x) for x in bank_t.shape)
+    if Fk != F:
+        raise FFTConvError(ERRID_CONV, "Kernel and Data must have the same number of features and kernel size "
+                                       "should be smaller than data size", -5)
+    FH, FW = computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)
+    dev = int(data_t.device.index or 0)
+    if out_t is None:
+        out_t = torch.empty((N, K, FW, FH), dtype=torch.float32, device=data_t.device)
+    plane = FW * FH * 4
+    kp = (ctypes.c_void_p * K)(*[bank_t.data_ptr() + 4 * k * F * kw * kh for k in range(K)])
+    op = (ctypes.c_void_p * (N * K))(*[out_t.data_ptr() + plane * i for i in range(N * K)])
+    khs = (ctypes.c_int * K)(*([kh] * K))
+    kws = (ctypes.c_int * K)(*([kw] * K))
+    ond = (ctypes.c_ubyte * K)(*([1] * K))
+    st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    o = ctypes.byref(options) if options is not None else None
+    rc = lib().fftconv_conv_batch(data_t.data_ptr(), 1, N, H, W, F, kh, kw, K, kp, khs, kws, None, ond, op, 1, o, dev, st)
     _check(rc, ERRID_CONV)
     return out_t
 

@@ -115,6 +115,19 @@ int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F,
                       int K, const float* d_bank, int kh, int kw,
                       float* d_out, const fftconv_options* opt, int device, void* stream);
 
+/* Extension (BASELINE config "batched"): N images of identical H x W x F stored back to back
+ * (data: C array [N][F][W][H]) against ONE bank; plane (n, k) goes to outs[n*K + k].  With device outputs
+ * and kernels up to 32 x 32 the images only add overlap-save tiles to the N dimension of the per-frequency-bin
+ * complex GEMM (tcgen05, one kernel-spectrum pass for the whole group of images); otherwise the call is
+ * N calls of fftconv_convolution_fft.  Same argument conventions as fftconv_convolution_fft
+ * (src/cudaConvolutionFFT.cu:27-311 is its single-image counterpart). */
+int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int W, int F,
+                       int maxKH, int maxKW,
+                       int K, const float* const* kernels, const int* kh, const int* kw,
+                       const int* kf, const unsigned char* kernel_on_device,
+                       float* const* outs, int out_on_device,
+                       const fftconv_options* opt, int device, void* stream);
+
 /* modulateAndNormalize — src/convolutionFFTkernel.cu:84-100: in place a = a*b/dataN. */
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
                                    long long n, int device, void* stream);

@@ -1,0 +1,56 @@
+"""GPU parity of the batched entry point (BASELINE config "batched": N images x one bank, the channel
+reduction done as a per-frequency-bin complex GEMM on the tensor cores): fftconv_conv_batch against the
+float64 direct convolution and against the single-image entry point.  Tolerance rel-L2 <= 1e-5."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _case(fc, oracle, N, H, W, F, kh, kw, K, seed):
+    import torch
+    rng = np.random.default_rng(seed)
+    data = rng.random((N, H, W, F), dtype=np.float32)                      # MATLAB order per image
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.05).astype(np.float32)
+    FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+    d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(0, 3, 2, 1))).cuda()     # [N][F][W][H]
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()     # [K][F][kw][kh]
+    before = fc.launch_count()
+    out = fc.conv_batch(d_t, b_t)
+    torch.cuda.synchronize()
+    assert fc.launch_count() > before
+    assert tuple(out.shape) == (N, K, FW, FH)
+    got = out.cpu().numpy().transpose(0, 1, 3, 2)                           # [N][K][FH][FW]
+    for n in range(N):
+        for k in sorted({0, K // 2, K - 1}):
+            ref = oracle.direct_conv64_c(data[n], bank[k], FH, FW)
+            assert oracle.rel_l2(got[n, k], ref) < TOL, (n, k)
+    return data, bank, got
+
+
+def test_batch_small_kernels(fc, oracle):
+    _case(fc, oracle, N=3, H=100, W=90, F=6, kh=9, kw=12, K=37, seed=41)
+
+
+def test_batch_32x32_kernels_c4_shape_scaled(fc, oracle):
+    """config 4 scaled down: 5 images 96x80x32 x 130 kernels 32x32x32 (two 128-row MMA blocks, NF = 2)."""
+    _case(fc, oracle, N=5, H=96, W=80, F=32, kh=32, kw=32, K=130, seed=42)
+
+
+def test_batch_matches_single_image_calls(fc, oracle):
+    data, bank, got = _case(fc, oracle, N=2, H=64, W=48, F=5, kh=7, kw=5, K=70, seed=43)
+    for n in range(2):
+        outs = fc.cudaConvolutionFFT(data[n], 7, 5, [bank[k] for k in range(70)])
+        for k in (0, 33, 69):
+            assert oracle.rel_l2(got[n, k], outs[k]) < 2e-6
+
+
+def test_batch_many_tile_blocks(fc, oracle):
+    """more than 40 tiles per group -> several B operand blocks (NNB > 1), groups that straddle images."""
+    _case(fc, oracle, N=4, H=200, W=150, F=3, kh=5, kw=6, K=9, seed=44)
+
+
+def test_batch_falls_back_for_large_kernels(fc, oracle):
+    """kernels beyond 32x32 are outside the overlap-save path: the call loops over the images."""
+    _case(fc, oracle, N=2, H=80, W=70, F=2, kh=40, kw=33, K=3, seed=45)
