@@ -54,3 +54,26 @@ def test_batch_many_tile_blocks(fc, oracle):
 def test_batch_falls_back_for_large_kernels(fc, oracle):
     """kernels beyond 32x32 are outside the overlap-save path: the call loops over the images."""
     _case(fc, oracle, N=2, H=80, W=70, F=2, kh=40, kw=33, K=3, seed=45)
+
+
+def test_pyramid_schedule_single_rank(fc, oracle):
+    """config 5 scaled down: 4-level pyramid x 80 templates through the sharded schedule (world = 1)."""
+    import torch
+    from fftconv_b200.pyramid import pyramid_convolution_cuda, pyramid_sides, level_plane
+    rng = np.random.default_rng(51)
+    F, kh, kw, K = 7, 6, 6, 80
+    sides = pyramid_sides(60, 4, 2)
+    levels = [(rng.random((s, s, F), dtype=np.float32) * 0.2).astype(np.float32) for s in sides]
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.05).astype(np.float32)
+    lt = [torch.from_numpy(np.ascontiguousarray(lv.transpose(2, 1, 0))).cuda() for lv in levels]
+    bt = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    b, e, outs = pyramid_convolution_cuda(lt, [(s, s, F) for s in sides], bt, kh, kw)
+    torch.cuda.synchronize()
+    assert (b, e) == (0, K)
+    for l, s in enumerate(sides):
+        FH, FW = level_plane(s, s, kh, kw)
+        got = outs[l].cpu().numpy()
+        assert got.shape == (K, FW, FH)
+        for k in (0, 41, K - 1):
+            ref = oracle.direct_conv64_c(levels[l], bank[k], FH, FW)
+            assert oracle.rel_l2(got[k].T, ref) < TOL

@@ -78,3 +78,68 @@ def test_sharded_convolution_gloo_world2(fc):
         assert p.exitcode == 0
     assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 7
     assert all(r[3] for r in res)
+
+
+def _pyr_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-fft-convolution_b200")]
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from fftconv_b200.pyramid import pyramid_convolution, pyramid_sides
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)                      # same inputs on every rank
+        sides = pyramid_sides(40, 4, 2)
+        assert sides == [40, 28, 20, 14]
+        levels = [rng.random((s, s, 3), dtype=np.float32) for s in sides]
+        kernels = [rng.standard_normal((int(rng.integers(3, 7)), int(rng.integers(3, 7)), 3)).astype(np.float32)
+                   for _ in range(5)]
+        shapes = [(s, s, 3) for s in sides]
+
+        def fft_fn(lv, kh, kw):
+            return torch.from_numpy(oracle.fft_data(lv, kh, kw))
+
+        def alloc(H, W, F):
+            return torch.zeros(oracle.fft_data(np.zeros((H, W, F), np.float32), 6, 6).shape, dtype=torch.complex64)
+
+        def conv_fn(l, spec, b, e):
+            return oracle.conv_fft_data(spec.numpy(), kernels[b:e])
+
+        b, e, res = pyramid_convolution(levels if rank == 0 else None, 6, 6, len(kernels),
+                                        [float(k.shape[0] * k.shape[1]) for k in kernels], fft_fn, alloc, conv_fn, shapes)
+        ok = True
+        for l, lv in enumerate(levels):
+            ref = oracle.convolution_fft(lv, 6, 6, kernels)
+            ok = ok and len(res[l]) == e - b and all(np.array_equal(p, ref[b + i]) for i, p in enumerate(res[l]))
+        q.put((rank, b, e, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pyramid_schedule_gloo_world2(fc):
+    """config 5 plumbing: every level spectrum broadcast from rank 0, bank sharded, outputs stay sharded."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pyr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 0 and res[0][2] == res[1][1] and res[1][2] == 5
+    assert all(r[3] for r in res)
+
+
+def test_pyramid_sides_config5(fc):
+    from fftconv_b200.pyramid import pyramid_sides, level_plane
+    sides = pyramid_sides()
+    assert sides == [256, 223, 194, 169, 147, 128, 111, 97, 84, 74]
+    assert [level_plane(s, s, 16, 16)[0] for s in sides] == [272, 240, 224, 192, 176, 144, 128, 112, 112, 96]
