@@ -438,9 +438,9 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
     g.b_buf = (size_t)g.NKS * 2 * g.KC * g.NMMA * 16;
     g.p_blk = (size_t)OS_TM * g.RS * 4;
     if (g.b_buf >= (1u << 20) || g.a_stage >= (1u << 20)) return false;       // mbarrier tx-count range
-    g.nsta = 0;
-    for (int ns = 4; ns >= 2; --ns) {
-        const size_t tot = (size_t)ns * g.a_stage + 2 * g.b_buf + g.p_blk + 256;
+    g.nsta = 0;                                                           // raw A ring depth (fp32 K-stages in flight)
+    for (int ns = 8; ns >= 2; --ns) {
+        const size_t tot = (size_t)(ns + 2) * (g.a_stage / 2) + 2 * g.b_buf + g.p_blk + 512;
         if (tot <= kMaxSmem) { g.nsta = ns; g.gemm_smem = tot; break; }
     }
     if (!g.nsta) return false;
@@ -515,7 +515,7 @@ static int os_max_chunk(const OsCfg& g) {
 
 static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates) {
     const int ntblk = (KC_templates + OS_TM - 1) / OS_TM;
-    if (int e = dev_reserve(c.osA, (size_t)ntblk * OS_NBIN * g.NKS * g.a_stage)) return e;
+    if (int e = dev_reserve(c.osA, (size_t)ntblk * OS_NBIN * g.NKS * (g.a_stage / 2))) return e;     // fp32 images
     if (int e = dev_reserve(c.osP, (size_t)ntblk * g.NNB * OS_NBIN * g.p_blk)) return e;
     return 0;
 }
@@ -545,7 +545,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
             os_gemm_simt<<<(unsigned)a.nitems, 128, 0, st>>>(a);
         } else {
             const unsigned grid = (unsigned)std::min<long long>(a.nitems, (long long)c.sm_count);
-            os_gemm<<<grid, 192, g.gemm_smem, st>>>(a);
+            os_gemm<<<grid, 320, g.gemm_smem, st>>>(a);
         }
         LAUNCH_CHECK();
     }

@@ -23,7 +23,7 @@
 // src/cudaConvFFTData.cu:233-271).
 //
 // Operand images (K-major, no swizzle; one 16-byte unit = 4 consecutive k = channels (2c,2c+1) x (re,im)):
-//   Aimg [tblk][bin][ks][term hi/lo][kc][128 templates][4]      (MMA A: rows = templates)
+//   Aimg [tblk][bin][ks][kc][128 templates][4]  plain fp32      (MMA A: rows = templates; hi/lo split on chip)
 //   Bimg [nblk][bin][ks][term hi/lo][kc][NMMA rows     ][4]      (MMA B: rows = (tile, re/im column))
 //   P    [tblk][nblk][u][128 templates][v][RS]  fp32, (re,im) per tile (bin = u*64 + v); a template's 64 bins of a
 //        spectrum row are one contiguous 64*RS*4-byte run, which is what os_inverse gathers
@@ -167,14 +167,14 @@ __device__ __forceinline__ float os_tf32_hi(float x) { return __uint_as_float(__
 
 // ------------------------------------------------------------------------------------------------
 // os_kern_fft: templates -> A operand images in ONE kernel (pad fused into the load, 2-D 64 x 64 half
-// spectrum of a 16*NF x 16*NF support, hi/lo TF32 split, operand-image store).  Replaces the template
+// spectrum of a 16*NF x 16*NF support, operand-image store in plain fp32 -- os_gemm splits hi/lo on chip).  Replaces the template
 // legs of os_hpass + os_wpass and their [template][F][33][XC] intermediate.
 // CTA = 16 templates x one channel pair, 256 threads.  Two phases (odd spectrum rows, then even ones) so
 // that the h-transformed rows of the 32 planes fit 70 KB (NF=1) of shared memory:
 //   h step: thread = (plane, column pair): two real columns ride as one complex sequence; the two tasks
 //           that hold rows u and 64-u are computed together and unpacked in registers
-//   w step: thread = (spectrum row, task r0, template); both channels of the pair, then 16 x (hi, lo)
-//           128-bit stores; 16 consecutive lanes write 256 contiguous bytes of the image
+//   w step: thread = (spectrum row, task r0, template); both channels of the pair, then 16 128-bit stores;
+//           16 consecutive lanes write 256 contiguous bytes of the image
 // grid = (ntblk*128/16, NKS*KC).
 struct OsKArgs {
     const SrcDesc* descs;
@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
     const int slot0 = blockIdx.x * OS_KSL;
     const int tblk = slot0 / OS_TM, sl0 = slot0 - tblk * OS_TM;
     const int ks = fp / a.KC, kc = fp - ks * a.KC;
-    const size_t term_stride = (size_t)a.KC * OS_TM * 4;
-    const size_t bin_stride = (size_t)a.NKS * 2 * term_stride;
+    const size_t stage_floats = (size_t)a.KC * OS_TM * 4;           // one K-stage of one bin
+    const size_t bin_stride = (size_t)a.NKS * stage_floats;
 
 #pragma unroll 1
     for (int ph = 0; ph < 2; ++ph) {
@@ -269,17 +269,11 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
                 auto ld = [&](int j) { return row[j >> 1]; };
                 os_fft64_task_rt<NF, false>(r0, ld, re1, im1);
             }
-            float* base = a.img + ((size_t)tblk * OS_NBIN + (size_t)u * 64 + r0) * bin_stride + (size_t)ks * 2 * term_stride +
+            float* base = a.img + ((size_t)tblk * OS_NBIN + (size_t)u * 64 + r0) * bin_stride + (size_t)ks * stage_floats +
                           (size_t)kc * OS_TM * 4 + (size_t)(sl0 + slot) * 4;
 #pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {
-                const float4 v = make_float4(re0[j1], im0[j1], re1[j1], im1[j1]);
-                const float4 hi = make_float4(os_tf32_hi(v.x), os_tf32_hi(v.y), os_tf32_hi(v.z), os_tf32_hi(v.w));
-                const float4 lo = make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w);
-                float* o = base + (size_t)(4 * j1) * bin_stride;
-                *reinterpret_cast<float4*>(o) = hi;
-                *reinterpret_cast<float4*>(o + term_stride) = lo;
-            }
+            for (int j1 = 0; j1 < 16; ++j1)
+                *reinterpret_cast<float4*>(base + (size_t)(4 * j1) * bin_stride) = make_float4(re0[j1], im0[j1], re1[j1], im1[j1]);
         }
         __syncthreads();
     }
@@ -475,7 +469,10 @@ __host__ __device__ constexpr uint32_t os_idesc_tf32(int M, int N) {
 // contiguous range of items ordered so that consecutive items share the B operand (same tile block & bin).
 //   warp 0 : TMA producer (cp.async.bulk + mbarrier expect_tx), A ring of `nsta` K-stages, 2 B buffers
 //   warp 1 : TMEM allocation + single-thread tcgen05.mma issue; 3 passes (lo*hi, hi*lo, hi*hi) per K-stage
-//   warps 2-5 : epilogue, tcgen05.ld -> registers -> smem staging -> one bulk store of the 128 x RS block
+//   warps 2-5 : epilogue, tcgen05.ld -> registers -> smem staging -> one bulk store per template row
+//   warps 6-9 : A splitter.  The A images travel through HBM as plain fp32 (half the bytes of a hi/lo pair);
+//               once a K-stage has landed in the deep raw ring these warps rewrite it in place as hi = tf32(a) and
+//               write a - hi into a 2-deep lo ring, then hand both to the MMA warp (fence.proxy.async + mbarrier)
 struct OsGemmArgs {
     const float* Aimg;
     const float* Bimg;
@@ -486,32 +483,55 @@ struct OsGemmArgs {
     int lbo_swap;     // debug: swap the LBO / SBO fields of the smem descriptors
 };
 
-__global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
+// Walks the work items (tile block, bin, template block) of one CTA without 64-bit divisions in the loop
+// (the single-thread producer / MMA roles execute every instruction at full dependent latency).
+struct OsItemIter {
+    int tblk, bin, nblk, ntblk;
+    long long key;
+    __device__ __forceinline__ OsItemIter(long long it, int NTBLK) : ntblk(NTBLK) {
+        key = it / NTBLK;
+        tblk = (int)(it - key * NTBLK);
+        nblk = (int)(key / OS_NBIN);
+        bin = (int)(key - (long long)nblk * OS_NBIN);
+    }
+    __device__ __forceinline__ void next() {
+        if (++tblk == ntblk) {
+            tblk = 0; ++key;
+            if (++bin == OS_NBIN) { bin = 0; ++nblk; }
+        }
+    }
+    __device__ __forceinline__ bool last_of_key() const { return tblk + 1 == ntblk; }
+};
+
+__global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
-    const uint32_t a_stage = 2u * g.KC * OS_TM * 16u;
-    const uint32_t b_stage = 2u * g.KC * g.NMMA * 16u;
+    const uint32_t a_half = (uint32_t)g.KC * OS_TM * 16u;       // one K-stage of A (fp32 as it travels; one hi or lo image)
+    const uint32_t b_stage = 2u * g.KC * g.NMMA * 16u;          // one K-stage of B: [hi | lo]
     const uint32_t b_buf = b_stage * g.NKS;
-    const uint32_t p_blk = (uint32_t)OS_TM * g.RS * 4u;
-    unsigned char* a_sm = os_smem_raw;
-    unsigned char* b_sm = a_sm + (size_t)g.nsta * a_stage;
-    float* stage_sm = reinterpret_cast<float*>(b_sm + 2 * (size_t)b_buf);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage_sm) + p_blk);
-    uint64_t* a_full = bars;                 // [nsta]
-    uint64_t* a_empty = bars + 8;            // [nsta]
-    uint64_t* b_full = bars + 16;            // [2]
-    uint64_t* b_empty = bars + 18;           // [2]
-    uint64_t* acc_full = bars + 20;          // [2]
-    uint64_t* acc_empty = bars + 22;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    unsigned char* a_sm = os_smem_raw;                          // raw ring [nsta][a_half]: TMA target, rewritten in place as hi
+    unsigned char* lo_sm = a_sm + (size_t)g.nsta * a_half;      // lo ring [2][a_half]
+    unsigned char* b_sm = lo_sm + 2 * (size_t)a_half;           // [2][b_buf]
+    float* stage_sm = reinterpret_cast<float*>(b_sm + 2 * (size_t)b_buf);     // [128][RS] epilogue staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage_sm) + (size_t)OS_TM * g.RS * 4u);
+    uint64_t* a_full = bars;                 // [nsta]  TMA -> splitter
+    uint64_t* a_empty = bars + 8;            // [nsta]  MMA -> TMA
+    uint64_t* a_ready = bars + 16;           // [nsta]  splitter -> MMA
+    uint64_t* lo_empty = bars + 24;          // [2]     MMA -> splitter
+    uint64_t* b_full = bars + 26;            // [2]
+    uint64_t* b_empty = bars + 28;           // [2]
+    uint64_t* acc_full = bars + 30;          // [2]
+    uint64_t* acc_empty = bars + 32;         // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long lo = g.nitems * (long long)blockIdx.x / gridDim.x;
     const long long hi = g.nitems * (long long)(blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < g.nsta; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < g.nsta; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&a_ready[i], 128); }
         for (int i = 0; i < 2; ++i) {
+            mbar_init(&lo_empty[i], 1);
             mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128);
         }
@@ -527,10 +547,10 @@ __global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
         if (lane == 0) {
             long long curkey = -1;
             uint32_t nb = 0, na = 0;
-            for (long long it = lo; it < hi; ++it) {
-                const long long key = it / g.NTBLK;
-                const int tblk = (int)(it - key * g.NTBLK);
-                const int bin = (int)(key % OS_NBIN);
+            OsItemIter w(lo, g.NTBLK);
+            for (long long it = lo; it < hi; ++it, w.next()) {
+                const long long key = w.key;
+                const int tblk = w.tblk, bin = w.bin;
                 if (key != curkey) {
                     const uint32_t bb = nb & 1;
                     if (nb >= 2) mbar_wait(&b_empty[bb], ((nb >> 1) - 1) & 1);
@@ -541,12 +561,12 @@ __global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
                     curkey = key;
                 }
                 const unsigned char* asrc = reinterpret_cast<const unsigned char*>(g.Aimg) +
-                                            ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
+                                            ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_half;
                 for (int ks = 0; ks < g.NKS; ++ks) {
                     const uint32_t st = na % g.nsta, fill = na / g.nsta;
                     if (fill >= 1) mbar_wait(&a_empty[st], (fill - 1) & 1);
-                    mbar_expect_tx(&a_full[st], a_stage);
-                    bulk_g2s(a_sm + (size_t)st * a_stage, asrc + (size_t)ks * a_stage, a_stage, &a_full[st]);
+                    mbar_expect_tx(&a_full[st], a_half);
+                    bulk_g2s(a_sm + (size_t)st * a_half, asrc + (size_t)ks * a_half, a_half, &a_full[st]);
                     ++na;
                 }
             }
@@ -555,10 +575,15 @@ __global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
         if (lane == 0) {
             const uint32_t idesc = os_idesc_tf32(OS_TM, g.NMMA);
             const uint32_t a_lbo = OS_TM * 16u, b_lbo = (uint32_t)g.NMMA * 16u, sbo = 128u;
+            const uint32_t b_term = (uint32_t)g.KC * g.NMMA * 16u;
             long long curkey = -1;
             uint32_t nb = 0, na = 0, nit = 0, bcur = 0;
-            for (long long it = lo; it < hi; ++it, ++nit) {
-                const long long key = it / g.NTBLK;
+            OsItemIter w(lo, g.NTBLK);
+            // descriptor templates: only the 14-bit start-address field changes between instructions
+            const uint64_t adesc0 = g.lbo_swap ? os_smem_desc(0, sbo, a_lbo) : os_smem_desc(0, a_lbo, sbo);
+            const uint64_t bdesc0 = g.lbo_swap ? os_smem_desc(0, sbo, b_lbo) : os_smem_desc(0, b_lbo, sbo);
+            for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
+                const long long key = w.key;
                 if (key != curkey) {
                     bcur = nb & 1;
                     mbar_wait(&b_full[bcur], (nb >> 1) & 1);
@@ -570,65 +595,83 @@ __global__ void __launch_bounds__(192, 1) os_gemm(OsGemmArgs g)
                 os_tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * OS_ACC_COLS;
                 for (int ks = 0; ks < g.NKS; ++ks) {
-                    const uint32_t st = na % g.nsta;
-                    mbar_wait(&a_full[st], (na / g.nsta) & 1);
+                    const uint32_t st = na % g.nsta, ls = na & 1;
+                    mbar_wait(&a_ready[st], (na / g.nsta) & 1);
                     os_tc_fence_after();
-                    const uint32_t a_base = smem_u32(a_sm + (size_t)st * a_stage);
+                    const uint32_t hi_base = smem_u32(a_sm + (size_t)st * a_half);
+                    const uint32_t lo_base = smem_u32(lo_sm + (size_t)ls * a_half);
                     const uint32_t b_base = smem_u32(b_sm + (size_t)bcur * b_buf + (size_t)ks * b_stage);
-                    const uint32_t a_term = (uint32_t)g.KC * OS_TM * 16u, b_term = (uint32_t)g.KC * g.NMMA * 16u;
-#pragma unroll 1
-                    for (int pass = 0; pass < 3; ++pass) {
-                        // small terms first: (A lo, B hi), (A hi, B lo), then (A hi, B hi)
-                        const uint32_t ta = pass == 0 ? 1u : 0u, tb = pass == 1 ? 1u : 0u;
-                        for (int j = 0; j < g.KC / 2; ++j) {
-                            const uint32_t aaddr = a_base + ta * a_term + (uint32_t)j * 2u * a_lbo;
-                            const uint32_t baddr = b_base + tb * b_term + (uint32_t)j * 2u * b_lbo;
-                            const uint64_t ad = g.lbo_swap ? os_smem_desc(aaddr, sbo, a_lbo) : os_smem_desc(aaddr, a_lbo, sbo);
-                            const uint64_t bd = g.lbo_swap ? os_smem_desc(baddr, sbo, b_lbo) : os_smem_desc(baddr, b_lbo, sbo);
-                            os_mma_tf32(tmem_d, ad, bd, idesc, (ks | pass | j) != 0 ? 1u : 0u);
-                        }
-                    }
+                    // small terms first: (A lo, B hi), (A hi, B lo), then (A hi, B hi); per instruction only the
+                    // start-address fields of the two descriptors move (K advances by 2 units of 16 bytes)
+                    const uint64_t ad_lo = adesc0 | (uint64_t)((lo_base >> 4) & 0x3FFFu);
+                    const uint64_t ad_hi = adesc0 | (uint64_t)((hi_base >> 4) & 0x3FFFu);
+                    const uint64_t bd_hi = bdesc0 | (uint64_t)((b_base >> 4) & 0x3FFFu);
+                    const uint64_t bd_lo = bdesc0 | (uint64_t)(((b_base + b_term) >> 4) & 0x3FFFu);
+                    const uint64_t a_step = (uint64_t)(2u * a_lbo >> 4), b_step = (uint64_t)(2u * b_lbo >> 4);
+                    const int nj = g.KC >> 1;
+                    for (int j = 0; j < nj; ++j) os_mma_tf32(tmem_d, ad_lo + j * a_step, bd_hi + j * b_step, idesc, (ks | j) != 0 ? 1u : 0u);
+                    for (int j = 0; j < nj; ++j) os_mma_tf32(tmem_d, ad_hi + j * a_step, bd_lo + j * b_step, idesc, 1u);
+                    for (int j = 0; j < nj; ++j) os_mma_tf32(tmem_d, ad_hi + j * a_step, bd_hi + j * b_step, idesc, 1u);
                     os_mma_commit(&a_empty[st]);
+                    os_mma_commit(&lo_empty[ls]);
                     ++na;
                 }
                 os_mma_commit(&acc_full[acc]);
-                if (it + 1 == hi || (it + 1) / g.NTBLK != key) os_mma_commit(&b_empty[bcur]);
+                if (it + 1 == hi || w.last_of_key()) os_mma_commit(&b_empty[bcur]);
+            }
+        }
+    } else if (warp >= 6) {
+        const int sp = threadIdx.x - 192;             // 0..127
+        const uint32_t nvec = a_half / 16u;           // float4 per stage (a multiple of 128)
+        uint32_t na = 0;
+        for (long long it = lo; it < hi; ++it) {
+            for (int ks = 0; ks < g.NKS; ++ks, ++na) {
+                const uint32_t st = na % g.nsta, ls = na & 1;
+                mbar_wait(&a_full[st], (na / g.nsta) & 1);
+                if (na >= 2) mbar_wait(&lo_empty[ls], ((na >> 1) - 1) & 1);
+                float4* hp = reinterpret_cast<float4*>(a_sm + (size_t)st * a_half);
+                float4* lp = reinterpret_cast<float4*>(lo_sm + (size_t)ls * a_half);
+                for (uint32_t i = sp; i < nvec; i += 128) {
+                    const float4 v = hp[i];
+                    const float4 h = make_float4(os_tf32_hi(v.x), os_tf32_hi(v.y), os_tf32_hi(v.z), os_tf32_hi(v.w));
+                    hp[i] = h;
+                    lp[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+                }
+                fence_proxy_async();                  // generic-proxy writes -> visible to tcgen05.mma (async proxy)
+                os_mbar_arrive(&a_ready[st]);
             }
         }
     } else {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
-        const int row = q * 32 + lane;
-        const int et = threadIdx.x - 64;              // 0..127
+        const int row = q * 32 + lane;                // template row of the block
         uint32_t nit = 0;
-        for (long long it = lo; it < hi; ++it, ++nit) {
-            const long long key = it / g.NTBLK;
-            const int tblk = (int)(it - key * g.NTBLK);
-            const int bin = (int)(key % OS_NBIN);
-            const int nblk = (int)(key / OS_NBIN);
+        OsItemIter w(lo, g.NTBLK);
+        for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
+            const int tblk = w.tblk, bin = w.bin, nblk = w.nblk;
             const uint32_t acc = nit & 1;
             mbar_wait(&acc_full[acc], (nit >> 1) & 1);
             os_tc_fence_after();
-            os_bulk_wait_read0();                     // this thread's previous bulk store has finished reading its staging row
             const uint32_t taddr = tmem_base + acc * OS_ACC_COLS + ((uint32_t)(q * 32) << 16);
+            os_bulk_wait_read0();                     // this thread's previous bulk store has finished reading its staging row
             float* srow = stage_sm + (size_t)row * g.RS;
-            for (int c0 = 0; c0 < g.RS; c0 += 16) {
-                uint32_t r[16];
-                os_tmem_ld8(taddr + c0, r);
-                const bool two = c0 + 8 < g.RS;
-                if (two) os_tmem_ld8(taddr + c0 + 8, r + 8);
+            {   // all TMEM loads of the row in flight, one wait (RS <= 80 columns)
+                uint32_t r[80];
+#pragma unroll
+                for (int i = 0; i < 10; ++i)
+                    if (8 * i < g.RS) os_tmem_ld8(taddr + 8 * i, r + 8 * i);
                 os_tmem_ld_wait();
-                float4* o = reinterpret_cast<float4*>(srow + c0);
-                o[0] = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
-                o[1] = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
-                if (two) {
-                    o[2] = make_float4(__uint_as_float(r[8]), __uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
-                    o[3] = make_float4(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]), __uint_as_float(r[15]));
-                }
+#pragma unroll
+                for (int i = 0; i < 10; ++i)
+                    if (8 * i < g.RS) {
+                        float4* o = reinterpret_cast<float4*>(srow + 8 * i);
+                        o[0] = make_float4(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]), __uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+                        o[1] = make_float4(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]), __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+                    }
             }
             os_tc_fence_before();
             os_mbar_arrive(&acc_empty[acc]);
             fence_proxy_async();                      // this thread's staging writes -> visible to the bulk-copy engine
-            {   // row `row` (template) of the block -> P[tblk][nblk][u][template][v][RS]: one 16*k-byte bulk copy per thread
+            {   // row `row` (template) of the block -> P[tblk][nblk][u][template][v][RS]: one bulk copy per thread
                 const int u = bin >> 6, v = bin & 63;
                 float* dst = g.P + ((((size_t)((size_t)tblk * g.NNB + nblk) * OS_CH + u) * OS_TM + row) * 64 + v) * g.RS;
                 os_bulk_s2g(dst, srow, (uint32_t)g.RS * 4u);
@@ -653,7 +696,7 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
     const int tblk = (int)(it - key * g.NTBLK);
     const int bin = (int)(key % OS_NBIN);
     const int nblk = (int)(key / OS_NBIN);
-    const size_t a_stage = (size_t)2 * g.KC * OS_TM * 4, b_stage = (size_t)2 * g.KC * g.NMMA * 4;   // floats
+    const size_t a_stage = (size_t)g.KC * OS_TM * 4, b_stage = (size_t)2 * g.KC * g.NMMA * 4;   // floats
     const float* A = g.Aimg + ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
     const float* B = g.Bimg + (size_t)key * g.NKS * b_stage;
     const int t = threadIdx.x;
@@ -663,7 +706,7 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
         for (int ks = 0; ks < g.NKS; ++ks)
             for (int kc = 0; kc < g.KC; ++kc) {
                 const float4 ah = *reinterpret_cast<const float4*>(A + ks * a_stage + ((size_t)kc * OS_TM + t) * 4);
-                const float4 al = *reinterpret_cast<const float4*>(A + ks * a_stage + ((size_t)(g.KC + kc) * OS_TM + t) * 4);
+                const float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 bh = *reinterpret_cast<const float4*>(B + ks * b_stage + ((size_t)kc * g.NMMA + n) * 4);
                 const float4 bl = *reinterpret_cast<const float4*>(B + ks * b_stage + ((size_t)(g.KC + kc) * g.NMMA + n) * 4);
                 acc = fmaf(ah.x + al.x, bh.x + bl.x, acc);
