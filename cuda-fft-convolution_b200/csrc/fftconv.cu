@@ -507,9 +507,15 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
 
 static size_t os_kern_smem(int NF) { return (size_t)32 * (17 * 16 * NF + 2) * sizeof(cpx); }
 
-static int os_max_chunk(const OsCfg& g) {
-    const int ntblk = std::max(1, os_env_int("FFTCONV_OS_NTBLK", 2));
-    (void)g;
+// Templates per chunk.  Device outputs: as large as the scratch budget allows (fewer launch tails, the B images are
+// streamed once per chunk).  Host outputs: small chunks, so that the D2H of one chunk overlaps the next one's compute.
+static int os_max_chunk(const OsCfg& g, bool out_on_device) {
+    int ntblk = os_env_int("FFTCONV_OS_NTBLK", 0);
+    if (ntblk <= 0) {
+        ntblk = out_on_device ? 8 : 2;
+        const size_t per_blk = (size_t)OS_NBIN * g.NKS * (g.a_stage / 2) + (size_t)g.NNB * OS_NBIN * g.p_blk;   // A + P
+        while (ntblk > 1 && per_blk * ntblk > ((size_t)6 << 30)) ntblk >>= 1;
+    }
     return ntblk * OS_TM;
 }
 
@@ -559,7 +565,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
         dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
         ProfScope ps(PK_OS_INV, st);
-        os_inverse<<<grid, 256, g.inv_smem, st>>>(a);
+        os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);
         LAUNCH_CHECK();
     }
     return 0;
@@ -693,7 +699,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     const size_t budget = (size_t)96 << 20;    // keep a chunk's intermediates L2-resident (126 MB L2)
     int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
     if (osg) {
-        KC = std::min(K, os_max_chunk(og));
+        KC = std::min(K, os_max_chunk(og, a.out_on_device));
         if (int e = os_reserve_chunk(c, og, KC)) return e;
         if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, a.opt.correlate, st)) return e;
     } else if (tile16) {

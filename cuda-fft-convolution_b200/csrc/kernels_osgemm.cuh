@@ -42,10 +42,12 @@ constexpr int OS_CH = 33;             // half-spectrum rows of a tile
 constexpr int OS_NBIN = OS_CH * OS_T; // 2112 frequency bins per tile
 constexpr int OS_TM = 128;            // templates per GEMM block (MMA M)
 constexpr int OS_ACC_COLS = 128;      // TMEM columns per accumulator buffer (2 buffers)
-constexpr int OS_IG = 4;              // tiles per CTA of os_inverse
+constexpr int OS_IG = 4;              // tiles per CTA of os_inverse (64 threads per tile): one 32-byte sector of P per bin
+constexpr int OS_IGB = 2;             // log2(OS_IG)
 constexpr int OS_IROW = 66;           // complex row stride of a 64-point line in shared memory (16-byte aligned rows)
 constexpr int OS_ICOL = 33;           // os_inverse: complex stride of a spectrum column (odd: conflict-free 64-bit accesses)
-constexpr int OS_ITILE = 64 * OS_ICOL + 4;   // os_inverse: tile stride (columns >= 32 sit 2 elements further; +32 B per tile)
+constexpr int OS_ITILE = 64 * OS_ICOL + 8;   // os_inverse: tile stride (columns >= 32 sit 4 elements further; +32 B per tile):
+                                             // the 16 lanes of a gather half-warp (2 tiles x 2 column halves x 4 columns) hit 32 distinct banks
 
 // ------------------------------------------------------------------------------------------------
 // compile-time twiddles  w64^e = cos(2 pi e/64) - i sin(2 pi e/64)  (double Taylor series, folded to
@@ -719,16 +721,16 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
 }
 
 // ------------------------------------------------------------------------------------------------
-// os_inverse: CTA = (template, group of 4 tiles), 256 threads, two threads per 64-point line.
-//   gather   the 33 x 64 product spectrum of each tile from P into shared memory, column (v) major;
-//            columns 0 and 32 (spectra of real sequences along h) are combined into one complex column
+// os_inverse: CTA = (template, group of OS_IG tiles), 64 threads per tile, two threads per 64-point line.
+//   gather   the 33 x 64 product spectrum of each tile from P into shared memory (cp.async), column (v) major;
+//            columns 0 and 32 (spectra of real sequences along h) are then combined into one complex column
 //   pass 1   inverse along h: line v (0..31) = column v for rows 0..32 and the conjugate of column 64-v above
 //            (Hermitian symmetry of the 2-D spectrum of a real tile); result in place
 //   pass 2   C2R along w: line y packs rows y and y+32 into one complex sequence; lanes run along h, so every
 //            store instruction writes one contiguous run of a plane column -- the valid (65-maxkh) x (65-maxkw)
 //            block goes straight from registers to the output plane (crop fused), no staging
 // The 1/4096 of the inverse transform is folded into the B operand images (os_data_fft).
-// grid = (ceil(NT/4), templates in chunk); smem = 4 * OS_ITILE * 8 B.
+// grid = (ceil(NT/OS_IG), templates in chunk); smem = OS_IG * OS_ITILE * 8 B.
 struct OsInvArgs {
     const float* P;
     float* const* outs;
@@ -737,32 +739,9 @@ struct OsInvArgs {
     int out_img_stride;     // plane of (image n, template t) = outs[n * out_img_stride + t]
 };
 
-__device__ __forceinline__ int os_icol(int v) { return v * OS_ICOL + ((v >> 5) << 1); }
+__device__ __forceinline__ int os_icol(int v) { return v * OS_ICOL + ((v >> 5) << 2); }
 
-// gather of one spectrum column (33 rows) of one tile from P; FIX: combine columns 0 and 32 (lanes l, l^4)
-template <bool FIX>
-__device__ __forceinline__ void os_inv_gather(const cpx* pp, size_t ustride, cpx* dst, bool c0, bool c32) {
-    const unsigned mask = FIX ? __activemask() : 0u;       // lanes l and l^4 belong to the same tile: both valid or both not
-    auto put = [&](int u, cpx z) {
-        if (FIX) {
-            const float ox = __shfl_xor_sync(mask, z.x, 4), oy = __shfl_xor_sync(mask, z.y, 4);
-            if (c0) z = make_float2(z.x - oy, z.y + ox);                   // column 0 := Z[u][0] + i Z[u][32]
-            if (c32) z = make_float2(ox + z.y, oy - z.x);                  // column 32 := Z[u][0] - i Z[u][32]
-        }
-        dst[u] = z;
-    };
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        cpx z[16];
-#pragma unroll
-        for (int it = 0; it < 16; ++it) { z[it] = __ldg(pp); pp += ustride; }      // 16 loads in flight
-#pragma unroll
-        for (int it = 0; it < 16; ++it) put(half * 16 + it, z[it]);
-    }
-    put(32, __ldg(pp));
-}
-
-__global__ void __launch_bounds__(256, 3) os_inverse(OsInvArgs a)
+__global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);                        // [4][OS_ITILE]
@@ -771,10 +750,11 @@ __global__ void __launch_bounds__(256, 3) os_inverse(OsInvArgs a)
     const int tblk = t / OS_TM, tl = t - tblk * OS_TM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // ---- gather: thread = (tile gq, column v); the 4 tiles of a group share one 32-byte sector of P;
-    //      lanes l and l^4 hold columns v and v+32, so columns 0 and 32 can be combined with shuffles
+    // ---- gather: thread = (tile gq, column v); the 4 tiles of a group share one 32-byte sector of P.
+    //      33 asynchronous 8-byte copies per thread (cp.async, no register staging): all of them in flight at once
     {
-        const int gq = threadIdx.x & 3, v = ((threadIdx.x >> 3) & 31) | (((threadIdx.x >> 2) & 1) << 5);
+        const int gq = threadIdx.x & (OS_IG - 1);
+        const int v = threadIdx.x >> OS_IGB;
         const int m = m0 + gq;
         cpx* dst = buf + gq * OS_ITILE + os_icol(v);
         if (m < a.NT) {
@@ -782,19 +762,32 @@ __global__ void __launch_bounds__(256, 3) os_inverse(OsInvArgs a)
             const size_t ustride = (size_t)OS_TM * 32 * a.RS;              // cpx units; P[tblk][nblk][u][template][v][RS]
             const cpx* pp = reinterpret_cast<const cpx*>(
                 a.P + (((size_t)((size_t)tblk * a.NNB + nblk) * OS_CH * OS_TM + tl) * 64 + v) * a.RS + 2 * ml);
-            if (warp != 0) {
-                os_inv_gather<false>(pp, ustride, dst, false, false);
-            } else {                                                       // warp 0 holds columns 0..3 and 32..35
-                os_inv_gather<true>(pp, ustride, dst, v == 0, v == 32);
+            const uint32_t d0 = smem_u32(dst);
+#pragma unroll
+            for (int u = 0; u <= 32; ++u) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 8u * u), "l"(pp) : "memory");
+                pp += ustride;
             }
         } else {
 #pragma unroll
             for (int u = 0; u <= 32; ++u) dst[u] = make_float2(0.f, 0.f);
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
-    const int par = warp >> 2;                                             // warp-uniform: tasks (par, par + 2)
-    const int gq = warp & 3;                                               // one warp = the 32 lines of one tile
+    // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
+    //     col0[u] := Z[u][0] + i Z[u][32],   col32[u] := Z[u][0] - i Z[u][32]
+    if (threadIdx.x < OS_IG * 33) {
+        const int gq = threadIdx.x / 33, u = threadIdx.x - gq * 33;
+        cpx* c0 = buf + gq * OS_ITILE + os_icol(0) + u;
+        cpx* c32 = buf + gq * OS_ITILE + os_icol(32) + u;
+        const cpx za = *c0, zb = *c32;
+        *c0 = make_float2(za.x - zb.y, za.y + zb.x);
+        *c32 = make_float2(za.x + zb.y, za.y - zb.x);
+    }
+    __syncthreads();
+    const int par = warp >> OS_IGB;                                        // warp-uniform: tasks (par, par + 2)
+    const int gq = warp & (OS_IG - 1);                                     // one warp = the 32 lines of one tile
     cpx* tile = buf + gq * OS_ITILE;
     // ---- pass 1: inverse along h, in place.  x[u] = col_v[u] (u <= 32), conj(col_mv[64-u]) (u > 32)
     {
