@@ -749,6 +749,22 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
     const int m0 = blockIdx.x * OS_IG;
     const int tblk = t / OS_TM, tl = t - tblk * OS_TM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per-tile store parameters, fetched / computed now by one thread per tile so that the plane-pointer load hides
+    // behind the gather: base of the valid block in the plane, rows / columns to store
+    __shared__ float* tile_dst[OS_IG];
+    __shared__ int tile_ny[OS_IG], tile_nx[OS_IG];
+    if (threadIdx.x < OS_IG) {
+        const int m = m0 + threadIdx.x;
+        float* d = nullptr; int ny = 0, nx = 0;
+        if (m < a.NT) {
+            const int img = m / a.NTimg, mt = m - img * a.NTimg;
+            const int tj = mt / a.nth, ti = mt - tj * a.nth;
+            const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
+            ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
+            d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
+        }
+        tile_dst[threadIdx.x] = d; tile_ny[threadIdx.x] = ny; tile_nx[threadIdx.x] = nx;
+    }
 
     // ---- gather: thread = (tile gq, column v); the 4 tiles of a group share one 32-byte sector of P.
     //      33 asynchronous 8-byte copies per thread (cp.async, no register staging): all of them in flight at once
@@ -829,13 +845,10 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
         else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
-        const int img = m / a.NTimg, mt = m - img * a.NTimg;
-        const int tj = mt / a.nth, ti = mt - tj * a.nth;
-        const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
-        const int ny = min(a.Sh, a.crop_h - Y0), nx = min(a.Sw, a.crop_w - X0);
+        const int ny = tile_ny[gq], nx = tile_nx[gq];
         const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
         const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
-        float* dst = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0 + ylo;
+        float* dst = tile_dst[gq] + ylo;
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) {
             const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
