@@ -10,6 +10,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <memory>
 #include <vector>
 
 #include "../../include/fftconv.h"
@@ -519,17 +520,17 @@ static int os_max_chunk(const OsCfg& g, bool out_on_device) {
     return ntblk * OS_TM;
 }
 
-static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates) {
+static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates, bool need_A = true) {
     const int ntblk = (KC_templates + OS_TM - 1) / OS_TM;
-    if (int e = dev_reserve(c.osA, (size_t)ntblk * OS_NBIN * g.NKS * (g.a_stage / 2))) return e;     // fp32 images
+    if (need_A) if (int e = dev_reserve(c.osA, (size_t)ntblk * OS_NBIN * g.NKS * (g.a_stage / 2))) return e;     // fp32 images
     if (int e = dev_reserve(c.osP, (size_t)ntblk * g.NNB * OS_NBIN * g.p_blk)) return e;
     return 0;
 }
 
 static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
-                    const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0) {
+                    const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0, const float* bankA = nullptr) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
-    {
+    if (!bankA) {
         OsKArgs a{};
         a.descs = d_descs; a.nk = nk; a.F = g.F; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
         dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
@@ -540,7 +541,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
     }
     {
         OsGemmArgs a{};
-        a.Aimg = (const float*)c.osA.p; a.Bimg = (const float*)c.osB.p; a.P = (float*)c.osP.p;
+        a.Aimg = bankA ? bankA : (const float*)c.osA.p; a.Bimg = (const float*)c.osB.p; a.P = (float*)c.osP.p;
         a.NTBLK = ntblk; a.NNB = g.NNB; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.RS = g.RS;
         a.nitems = (long long)g.NNB * OS_NBIN * ntblk;
         a.nsta = g.nsta;
@@ -588,6 +589,8 @@ struct ConvArgs {
     bool pipelined;                // use the side copy stream (Streams entry point)
     const float* d_raw = nullptr;  // one-shot entry point: the raw data [F][rawW][rawH] on the device
     int rawH = 0, rawW = 0;
+    const float* bankA = nullptr;  // prepared bank (fftconv_bank_*): A operand images of all K templates, path 3 only
+    int bank_maxkh = 0, bank_maxkw = 0;
     int nimg = 1;                  // batched entry point: nimg images [nimg][F][rawW][rawH] (raw, device, overlap-save path
                                    // only); outs then holds nimg*K device planes, image-major
 };
@@ -677,11 +680,12 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         return fail(FFTCONV_ERR_INVALID_INPUT, "crop larger than the FFT plane or out_ld too small");
 
     int maxkh = 1, maxkw = 1;
-    for (int k = 0; k < K; ++k) {
+    if (a.bankA) { maxkh = a.bank_maxkh; maxkw = a.bank_maxkw; }
+    else for (int k = 0; k < K; ++k) {
         maxkh = std::max(maxkh, std::min(a.kernels[k].kh, FH));
         maxkw = std::max(maxkw, std::min(a.kernels[k].kw, FW));
     }
-    const int path = a.nimg > 1 ? PATH_OSGEMM : choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
+    const int path = (a.nimg > 1 || a.bankA) ? PATH_OSGEMM : choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
     const bool tile16 = path == PATH_TILE16;
     const bool osg = path == PATH_OSGEMM;
     OsCfg og;
@@ -700,7 +704,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
     if (osg) {
         KC = std::min(K, os_max_chunk(og, a.out_on_device));
-        if (int e = os_reserve_chunk(c, og, KC)) return e;
+        if (int e = os_reserve_chunk(c, og, KC, a.bankA == nullptr)) return e;
         if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, a.opt.correlate, st)) return e;
     } else if (tile16) {
         // one CTA per SM: size the chunk so that NT * ceil(KC/KB) CTAs fill whole waves
@@ -730,7 +734,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     // descriptors / kcols / out pointers for ALL kernels go through pinned staging once
     const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int)) * (size_t)K + sizeof(float*) * NO + 64;
     size_t host_kernel_bytes = 0;
-    for (int k = 0; k < K; ++k)
+    for (int k = 0; k < K && !a.bankA; ++k)
         if (!a.kernels[k].on_device) host_kernel_bytes += sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
     if (int e = pinned_reserve(c, desc_bytes)) return e;
     if (int e = dev_reserve(c.desc, desc_bytes)) return e;
@@ -758,7 +762,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     }
     // device address of every kernel (host kernels are staged; offsets fixed up front, copies issued per chunk)
     std::vector<size_t> stage_off((size_t)K + 1, 0);
-    for (int k = 0; k < K; ++k) {
+    for (int k = 0; k < K && !a.bankA; ++k) {
         const size_t b = a.kernels[k].on_device ? 0 : sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
         stage_off[k + 1] = stage_off[k] + b;
         h_desc[k].ptr = a.kernels[k].on_device ? a.kernels[k].ptr
@@ -780,7 +784,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     for (size_t chunk = 0; chunk + 1 < bounds.size(); ++chunk) {
         const int k0 = bounds[chunk], nk = bounds[chunk + 1] - k0;
         // upload this chunk's host kernels: contiguous runs are coalesced into single copies
-        for (int k = k0; k < k0 + nk;) {
+        for (int k = k0; k < k0 + nk && !a.bankA;) {
             if (a.kernels[k].on_device) { ++k; continue; }
             const char* run_src = reinterpret_cast<const char*>(a.kernels[k].ptr);
             int j = k;
@@ -794,7 +798,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (!a.out_on_device && chunk >= 2) CU(cudaStreamWaitEvent(st, c.ev[chunk & 1], 0));   // staging half free?
         int e;
         if (osg)
-            e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K);
+            e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K,
+                         a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
@@ -1055,6 +1060,127 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
             return e;
     }
     return 0;
+}
+
+// ---- prepared banks: the template spectra (tcgen05 A operand images) are independent of the image size on the
+// overlap-save path (64 x 64 tiles), so they are computed once and stay resident in HBM.
+struct fftconv_bank {
+    int device, K, F, maxkh, maxkw, NKS, KC;
+    float* A;             // [ceil(K/128)][bin][ks][kc][128][4] fp32
+    size_t bytes;
+};
+
+int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                        const unsigned char* kernel_on_device, int F, int device, void* stream, fftconv_bank** out) {
+    g_err.clear();
+    if (!out || K <= 0 || F <= 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    *out = nullptr;
+    std::vector<KernelRef> refs;
+    if (int e = build_kernel_refs(K, kernels, kh, kw, kf, kernel_on_device, F, 1 << 30, 1 << 30, refs)) return e;
+    int maxkh = 1, maxkw = 1;
+    for (int k = 0; k < K; ++k) { maxkh = std::max(maxkh, refs[k].kh); maxkw = std::max(maxkw, refs[k].kw); }
+    OsCfg g;
+    if (!os_config(F, 64, 64, maxkh, maxkw, g))
+        return fail(FFTCONV_ERR_UNSUPPORTED, "prepared banks need templates of at most 32 x 32 (got %d x %d)", maxkh, maxkw);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    Ctx* c;
+    if (int e = ctx_get(device, &c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ntblk = (K + OS_TM - 1) / OS_TM;
+    std::unique_ptr<fftconv_bank> b(new fftconv_bank{device, K, F, maxkh, maxkw, g.NKS, g.KC, nullptr, 0});
+    b->bytes = (size_t)ntblk * OS_NBIN * g.NKS * (g.a_stage / 2);
+    CU(cudaMalloc(&b->A, b->bytes));
+    // stage host kernels + descriptors (the call is synchronous, so the shared staging buffers can be reused)
+    size_t host_bytes = 0;
+    for (int k = 0; k < K; ++k)
+        if (!refs[k].on_device) host_bytes += sizeof(float) * (size_t)refs[k].kh * refs[k].kw * F;
+    const size_t desc_bytes = sizeof(SrcDesc) * (size_t)K;
+    int e = 0;
+    if (!e) e = pinned_reserve(*c, desc_bytes);
+    if (!e) e = dev_reserve(c->desc, desc_bytes);
+    if (!e && host_bytes) e = dev_reserve(c->stage, host_bytes);
+    if (!e && cudaEventSynchronize(c->pinned_free) != cudaSuccess) e = fail(FFTCONV_ERR_CUDA, "event sync failed");
+    if (!e) {
+        SrcDesc* h_desc = reinterpret_cast<SrcDesc*>(c->pinned);
+        size_t off = 0;
+        for (int k = 0; k < K && !e; ++k) {
+            h_desc[k].rows = refs[k].kh; h_desc[k].cols = refs[k].kw;
+            if (refs[k].on_device) { h_desc[k].ptr = refs[k].ptr; continue; }
+            const size_t nb = sizeof(float) * (size_t)refs[k].kh * refs[k].kw * F;
+            h_desc[k].ptr = reinterpret_cast<const float*>(reinterpret_cast<char*>(c->stage.p) + off);
+            if (cudaMemcpyAsync(reinterpret_cast<char*>(c->stage.p) + off, refs[k].ptr, nb, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                e = fail(FFTCONV_ERR_CUDA, "kernel upload failed");
+            off += nb;
+        }
+        if (!e && cudaMemcpyAsync(c->desc.p, c->pinned, desc_bytes, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            e = fail(FFTCONV_ERR_CUDA, "descriptor upload failed");
+    }
+    if (!e) {
+        OsKArgs a{};
+        a.descs = (const SrcDesc*)c->desc.p; a.nk = K; a.F = F; a.img = b->A; a.NKS = g.NKS; a.KC = g.KC;
+        dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
+        ProfScope ps(PK_OS_KERN, st);
+        if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);
+        else os_kern_fft<2><<<grid, 256, os_kern_smem(2), st>>>(a);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            e = fail(FFTCONV_ERR_CUDA, "bank transform failed");
+    }
+    if (e) { cudaFree(b->A); return e; }
+    *out = b.release();
+    return 0;
+}
+
+int fftconv_bank_info(const fftconv_bank* b, int* K, int* F, int* maxKH, int* maxKW, long long* bytes) {
+    if (!b) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    if (K) *K = b->K;
+    if (F) *F = b->F;
+    if (maxKH) *maxKH = b->maxkh;
+    if (maxKW) *maxKW = b->maxkw;
+    if (bytes) *bytes = (long long)b->bytes;
+    return 0;
+}
+
+int fftconv_bank_conv(const fftconv_bank* b, const float* data, int data_on_device, int H, int W,
+                      float* const* outs, int out_on_device, const fftconv_options* opt, void* stream) {
+    g_err.clear();
+    if (!b || !data || !outs || H <= 0 || W <= 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    const fftconv_options o = opt ? *opt : fftconv_options{};
+    if (o.correlate) return fail(FFTCONV_ERR_UNSUPPORTED, "prepared banks do not serve correlation mode");
+    const int F = b->F, K = b->K;
+    const int FH = fftconv_fft_size16(H + b->maxkh - 1), FW = fftconv_fft_size16(W + b->maxkw - 1);
+    for (int k = 0; k < K; ++k)
+        if (!outs[k]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
+    Ctx* c;
+    if (int e = ctx_get(b->device, &c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* d_data = data;
+    if (!data_on_device) {
+        const size_t bytes = sizeof(float) * (size_t)H * W * F;
+        if (int e = dev_reserve(c->ddata, bytes)) return e;
+        CU(cudaMemcpyAsync(c->ddata.p, data, bytes, cudaMemcpyHostToDevice, st));
+        d_data = (const float*)c->ddata.p;
+    }
+    ConvArgs a;
+    a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = F; a.K = K;
+    a.kernels = nullptr; a.outs = outs; a.out_on_device = out_on_device != 0;
+    a.opt = o; a.pipelined = false;
+    a.d_raw = d_data; a.rawH = H; a.rawW = W;
+    a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw;
+    return run_conv(*c, a, st);
+}
+
+void fftconv_bank_destroy(fftconv_bank* b) {
+    if (!b) return;
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(b->device);
+    cudaFree(b->A);
+    delete b;
 }
 
 int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* d_bank, int kh, int kw,

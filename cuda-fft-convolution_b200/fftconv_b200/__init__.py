@@ -29,7 +29,7 @@ __all__ = [
     "FFTConvError", "GpuArray", "gpuArray", "gather", "computeFFTsize16", "computeFFTsize",
     "cudaFFTData", "cudaConvFFTData", "cudaConvolutionFFT", "cudaConvFFTDataStreams",
     "cudaFFTDataClamp", "modulateAndNormalize", "Options", "conv_bank", "fft_data_device",
-    "conv_batch", "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
+    "conv_batch", "Bank", "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -38,7 +38,8 @@ LIB_PATH = os.environ.get("FFTCONV_LIB") or os.path.join(_HERE, "libfftconv.so")
 EXPORTED_SYMBOLS = [
     "fftconv_fft_size16", "fftconv_fft_size_pow2", "fftconv_fft_data", "fftconv_fft_data_clamp",
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
-    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_modulate_and_normalize", "fftconv_launch_count",
+    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv",
+    "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
 ]
@@ -50,6 +51,8 @@ MSG_INVALID = "Invalid input to MEX file."                      # src/cudaFFTDat
 MSG_NOT_GPU = "The data must be FFT-ed real array in GPU"       # src/cudaConvFFTData.cu:69
 MSG_NOT_CELL = "Kernel must be a cell array"                    # src/cudaConvFFTData.cu:107
 MSG_KERNEL_TYPE = "Kernels must be of type float and have features larger than 1"   # :198
+MSG_KERNEL_SHAPE = ("Kernel and Data must have the same number of features and kernel size should be smaller "
+                    "than data size")                            # src/cudaConvFFTData.cu:230
 MSG_WRONG_NARGS = "Wrong number of inputs"                      # src/cudaConvolutionFFT.cu:46
 MSG_INVALID_DATA = "Invalid data input"                         # src/cudaConvolutionFFT.cu:54
 
@@ -97,6 +100,11 @@ def lib() -> ctypes.CDLL:
                                               c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp]
         L.fftconv_conv_batch.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                          c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_bank_create.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]
+        L.fftconv_bank_info.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
+        L.fftconv_bank_conv.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]
+        L.fftconv_bank_destroy.argtypes = [c_vp]
+        L.fftconv_bank_destroy.restype = None
         L.fftconv_conv_bank.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]
         L.fftconv_modulate_and_normalize.argtypes = [c_vp, c_vp, c_ll, c_int, c_vp]
         L.fftconv_launch_count.restype = c_ll
@@ -443,6 +451,78 @@ def conv_batch(data_t, bank_t, out_t=None, options: Optional[Options] = None, st
     rc = lib().fftconv_conv_batch(data_t.data_ptr(), 1, N, H, W, F, kh, kw, K, kp, khs, kws, None, ond, op, 1, o, dev, st)
     _check(rc, ERRID_CONV)
     return out_t
+
+
+class Bank:
+    """Prepared template bank (fftconv_bank_*): the kernel-side counterpart of cudaFFTData.  The template spectra
+    are computed once and stay on the device; conv() then serves any image size.
+
+        bank = fc.Bank(cell_of_kernels)              # kh x kw x F float32 arrays (host) or GpuArrays
+        planes = bank.conv(data)                     # list of (FH, FW) float32 arrays, like cudaConvolutionFFT
+        out_t = bank.conv_device(data_t)             # torch [F][W][H] on the device -> [K][FW][FH] on the device
+    """
+
+    def __init__(self, cell, device: int = 0):
+        torch = _torch()
+        c = _Cell(cell, None)
+        if c.K == 0:
+            raise FFTConvError(ERRID_CONV, MSG_INVALID)
+        c.F = int(c.kf[0])
+        self._keep = c
+        self.device = device
+        h = ctypes.c_void_p(0)
+        st = torch.cuda.current_stream(device).cuda_stream
+        rc = lib().fftconv_bank_create(c.K, c.ptrs, c.kh, c.kw, c.kf, c.on_dev, c.F, device, st, ctypes.byref(h))
+        _check(rc, ERRID_CONV)
+        self._h = h
+        K, F, mh, mw, nb = (ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_int(0), ctypes.c_longlong(0))
+        lib().fftconv_bank_info(h, ctypes.byref(K), ctypes.byref(F), ctypes.byref(mh), ctypes.byref(mw), ctypes.byref(nb))
+        self.K, self.F, self.maxKH, self.maxKW, self.bytes = K.value, F.value, mh.value, mw.value, nb.value
+        self._keep = None                            # the kernels are no longer needed once transformed
+
+    def plane(self, H: int, W: int):
+        return computeFFTsize16(H + self.maxKH - 1), computeFFTsize16(W + self.maxKW - 1)
+
+    def conv(self, data, options: Optional[Options] = None) -> List[np.ndarray]:
+        d_fwh = _as_single_3d(data, ERRID_CONV, MSG_INVALID)        # marshalled to [F][W][H]
+        F, W, H = d_fwh.shape
+        if F != self.F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        FH, FW = self.plane(H, W)
+        outs, ptrs = _alloc_outs(self.K, FH, FW)
+        torch = _torch()
+        op = ctypes.byref(options) if options is not None else None
+        rc = lib().fftconv_bank_conv(self._h, d_fwh.ctypes.data, 0, H, W, ptrs, 0, op,
+                                     torch.cuda.current_stream(self.device).cuda_stream)
+        _check(rc, ERRID_CONV)
+        return _wrap_outs(outs)
+
+    def conv_device(self, data_t, out_t=None, options: Optional[Options] = None, stream=None):
+        torch = _torch()
+        F, W, H = (int(x) for x in data_t.shape)
+        if F != self.F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        FH, FW = self.plane(H, W)
+        if out_t is None:
+            out_t = torch.empty((self.K, FW, FH), dtype=torch.float32, device=data_t.device)
+        plane = FW * FH * 4
+        ptrs = (ctypes.c_void_p * self.K)(*[out_t.data_ptr() + plane * k for k in range(self.K)])
+        st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        op = ctypes.byref(options) if options is not None else None
+        rc = lib().fftconv_bank_conv(self._h, data_t.data_ptr(), 1, H, W, ptrs, 1, op, st)
+        _check(rc, ERRID_CONV)
+        return out_t
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fftconv_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def modulateAndNormalize(a: GpuArray, b: GpuArray) -> None:

@@ -83,3 +83,30 @@ def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Se
         return fc.conv_bank(spec, bank_t[b:e], kh, kw, out, options=options)
 
     return pyramid_convolution(level_tensors, kh, kw, K, None, fft_fn, alloc_spec, conv_fn, level_shapes, group)
+
+
+def pyramid_convolution_prepared(level_tensors: Optional[Sequence], level_shapes: Sequence[Tuple[int, int, int]],
+                                 bank, outs: Optional[List] = None, options=None, group=None):
+    """The same schedule over a PREPARED bank shard (fftconv_b200.Bank built by each rank from its own templates):
+    the template spectra are resident, so a level costs data tiles -> per-bin GEMM -> inverse.  What travels is the
+    raw level (smaller than its spectrum): rank 0 broadcasts every level up front, every rank convolves all levels
+    with its shard.  level_tensors[l]: float32 [F][W][H] on the device (rank 0; allocated here on the others).
+    Returns [out_l float32 [bank.K][FW_l][FH_l]]."""
+    import torch
+    import torch.distributed as dist
+    on = dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    dev = torch.device("cuda", bank.device)
+    levels, pending = [], []
+    for l, (H, W, F) in enumerate(level_shapes):
+        t = level_tensors[l] if rank == 0 else torch.empty((F, W, H), dtype=torch.float32, device=dev)
+        if world > 1:
+            pending.append(dist.broadcast(t, src=0, group=group, async_op=True))
+        levels.append(t)
+    results = []
+    for l, t in enumerate(levels):
+        if world > 1:
+            pending[l].wait()
+        results.append(bank.conv_device(t, outs[l] if outs is not None else None, options=options))
+    return results

@@ -128,6 +128,22 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
                        float* const* outs, int out_on_device,
                        const fftconv_options* opt, int device, void* stream);
 
+/* Extension (the counterpart of cudaFFTData for the kernel side, src/cudaFFTData.cu:1-160): a PREPARED
+ * BANK.  On the overlap-save path the template spectra (64 x 64 tiles, tensor-core operand order) do not depend on
+ * the image size, so a bank is transformed once, stays resident in HBM (256 KB per template at F = 31) and serves
+ * every image / pyramid level / video frame after that: a call is then data tiles -> per-bin GEMM -> inverse.
+ * Templates of at most 32 x 32; kernels host or device as in fftconv_conv_fft_data (src/cudaConvFFTData.cu:194-231).
+ * fftconv_bank_conv: data H x W x F (host or device), outs[k] = FH x FW plane of template k with
+ * FH = fft_size16(H + maxKH - 1), maxKH/maxKW = the largest template of the bank (fftconv_bank_info). */
+typedef struct fftconv_bank fftconv_bank;
+int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                        const unsigned char* kernel_on_device, int F, int device, void* stream,
+                        fftconv_bank** out);
+int fftconv_bank_info(const fftconv_bank* bank, int* K, int* F, int* maxKH, int* maxKW, long long* bytes);
+int fftconv_bank_conv(const fftconv_bank* bank, const float* data, int data_on_device, int H, int W,
+                      float* const* outs, int out_on_device, const fftconv_options* opt, void* stream);
+void fftconv_bank_destroy(fftconv_bank* bank);
+
 /* modulateAndNormalize — src/convolutionFFTkernel.cu:84-100: in place a = a*b/dataN. */
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
                                    long long n, int device, void* stream);

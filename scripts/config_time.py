@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-fft-convolution_b200")]
 import torch
 import fftconv_b200 as fc
-from fftconv_b200.pyramid import pyramid_convolution_cuda, pyramid_sides, level_plane
+from fftconv_b200.pyramid import pyramid_convolution_cuda, pyramid_convolution_prepared, pyramid_sides, level_plane
 
 which = [a for a in sys.argv[1:] if a.startswith("c")] or ["c4", "c5"]
 scale = next((float(a) for a in sys.argv[1:] if not a.startswith("c")), 1.0)
@@ -58,6 +58,19 @@ if "c5" in which:
     ref = ref_fft(levels[3], bank[:2], FW, FH)
     err = float((outs[3][:2].double() - ref).norm() / ref.norm())
     print(f"[c5] 10-level pyramid x {K} templates 16x16x31: {ms:.2f} ms -> {nout/ms/1e6:.2f} G outputs/s, rel-L2 {err:.2e}", flush=True)
+    t0 = time.time()
+    import ctypes        # device-resident templates handed to fftconv_bank_create without a host round trip
+    h = ctypes.c_void_p(0)
+    kp = (ctypes.c_void_p * K)(*[bank.data_ptr() + 4 * k * F * kw * kh for k in range(K)])
+    khs = (ctypes.c_int * K)(*([kh] * K)); kws = (ctypes.c_int * K)(*([kw] * K)); ond = (ctypes.c_ubyte * K)(*([1] * K))
+    rc = fc.lib().fftconv_bank_create(K, kp, khs, kws, None, ond, F, 0, torch.cuda.current_stream().cuda_stream, ctypes.byref(h))
+    assert rc == 0, fc.last_error()
+    pb = fc.Bank.__new__(fc.Bank); pb._h = h; pb.K, pb.F, pb.maxKH, pb.maxKW, pb.device = K, F, kh, kw, 0
+    torch.cuda.synchronize(); t_prep = (time.time() - t0) * 1e3
+    ms = timeit(lambda: pyramid_convolution_prepared(levels, shapes, pb, outs), 2)
+    err = float((outs[3][:2].double() - ref).norm() / ref.norm())
+    print(f"[c5] same, PREPARED bank (one-off transform {t_prep:.1f} ms): {ms:.2f} ms -> {nout/ms/1e6:.2f} G outputs/s, rel-L2 {err:.2e}", flush=True)
+    pb.close()
     del outs
     fc.lib().fftconv_release()
 

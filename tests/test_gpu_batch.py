@@ -77,3 +77,48 @@ def test_pyramid_schedule_single_rank(fc, oracle):
         for k in (0, 41, K - 1):
             ref = oracle.direct_conv64_c(levels[l], bank[k], FH, FW)
             assert oracle.rel_l2(got[k].T, ref) < TOL
+
+
+def test_prepared_bank_matches_one_shot_and_oracle(fc, oracle):
+    """fftconv_bank_*: the bank is transformed once, then serves images of different sizes (pyramid levels)."""
+    rng = np.random.default_rng(61)
+    F, K = 6, 150
+    ks = []
+    for k in range(K):
+        a, b = (13, 16) if k % 4 == 0 else (int(rng.integers(3, 14)), int(rng.integers(2, 17)))
+        ks.append((rng.standard_normal((a, b, F)) * 0.05).astype(np.float32))
+    bank = fc.Bank(ks)
+    assert (bank.K, bank.F, bank.maxKH, bank.maxKW) == (K, F, 13, 16) and bank.bytes > 0
+    for (H, W) in ((90, 70), (41, 133)):
+        data = (rng.random((H, W, F), dtype=np.float32) * 0.2).astype(np.float32)
+        FH, FW = bank.plane(H, W)
+        before = fc.launch_count()
+        outs = bank.conv(data)
+        assert fc.launch_count() - before >= 3 and len(outs) == K
+        one = fc.cudaConvolutionFFT(data, 13, 16, ks, options=fc.Options(path=3))
+        for k in (0, 1, 77, K - 1):
+            assert outs[k].shape == (FH, FW)
+            assert np.array_equal(outs[k], one[k])                      # same kernels, same arithmetic
+            assert oracle.rel_l2(outs[k], oracle.direct_conv64_c(data, ks[k], FH, FW)) < TOL
+    bank.close()
+
+
+def test_prepared_bank_device_path_and_errors(fc, oracle):
+    import torch
+    rng = np.random.default_rng(62)
+    F, K, kh, kw = 4, 40, 8, 8
+    ks = [(rng.standard_normal((kh, kw, F)) * 0.1).astype(np.float32) for _ in range(K)]
+    bank = fc.Bank(ks)
+    data = rng.random((70, 50, F), dtype=np.float32)
+    d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(2, 1, 0))).cuda()
+    out = bank.conv_device(d_t)
+    torch.cuda.synchronize()
+    FH, FW = bank.plane(70, 50)
+    got = out.cpu().numpy()
+    for k in (0, 19, 39):
+        assert oracle.rel_l2(got[k].T, oracle.direct_conv64_c(data, ks[k], FH, FW)) < TOL
+    with pytest.raises(fc.FFTConvError):
+        bank.conv(rng.random((70, 50, F + 1), dtype=np.float32))        # feature mismatch (src/cudaConvFFTData.cu:229-230)
+    with pytest.raises(fc.FFTConvError):
+        fc.Bank([np.zeros((40, 8, F), np.float32)])                     # beyond 32 x 32: not a prepared-bank shape
+    bank.close()
