@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1]
 
 A "step" is one pass of the hot path over one batch of synthetic input:
-    pad -> R2C FFT of the data -> [per template: pruned FFT, multiply, sum over channels,
-    inverse FFT, scale] -> one fp32 plane per template.
+    pad -> R2C FFT of the data (cudaFFTData) -> [overlap-save tiles of the data; per template: pruned 64x64 FFT;
+    per frequency bin: complex GEMM over the channels on tcgen05; inverse FFT, crop] -> one fp32 plane per template.
 Workload at N = 1 (BASELINE.json configs[1], the HOG-DPM case): one 31-channel 256x256 feature
 map x 1,000 templates of 16x16x31 -> 1,000 planes of 272x272.  With N > 1 every rank holds its
 own shard of 1,000 templates (weak scaling: the bank grows with N), rank 0 transforms the data
@@ -14,7 +14,8 @@ and the spectrum is broadcast with NCCL inside the timed step.
 `value`   : conv outputs/s (pixels x kernels, whole job) with inputs already resident in HBM.
 `e2e`     : same metric through the C-ABI call with HOST (pinned) buffers, H2D and D2H inside
             the timed region.
-`roofline`: dominant kernel (tile16_conv) timed with CUDA events on its launch stream.
+`roofline`: dominant kernel (os_inverse on the overlap-save / tcgen05 path) timed with CUDA events on its
+            launch stream; `traffic` = ncu dram bytes of that kernel per launch (profiles/traffic.json).
 `cpu_baseline` / `--impl reference`: the reference's CPU path (demoCudaConvolutionFFT.m:76-102,
             fft2/ifft2 and conv2) restated in oracle/ and timed on this host's cores.
 """
@@ -291,7 +292,7 @@ def run_ours(args):
         "kernel_share_of_step": {k: v[0] / sum(x[0] for x in prof.values()) for k, v in prof.items()},
         "fp32_note": "fused pipeline is fp32-FMA bound, not HBM bound (SURVEY 8d): nominal "
                      f"{nominal_flops / 1e9:.1f} GFLOP/step (cuFFT convention) -> "
-                     f"{nominal_flops / (ms_per_step * 1e-3) / 1e12 * world:.2f} TFLOP/s nominal-equivalent "
+                     f"{nominal_flops / (ms_per_step * 1e-3) / 1e12:.2f} TFLOP/s per GPU nominal-equivalent "
                      "vs 74.4 TFLOP/s fp32 peak",
     }
 

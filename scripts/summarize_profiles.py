@@ -37,7 +37,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__sass_inst_executed_op_local_ld.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
 traffic = {}
 with open(os.path.join(P, f"{R}_hot_kernels_ncu.md"), "w") as f:
-    f.write(f"# {R}: `ncu --set full --clock-control none` of the hot kernels (one launch each, C2 workload, chunk of 256 templates)\n\n")
+    f.write(f"# {R}: `ncu --set full --clock-control none` of the hot kernels (one launch each, C2 workload, one chunk of 1000 templates)\n\n")
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "").replace("fftconv::", "")
         f.write(f"## {name}\n\n| metric | value | unit |\n|---|---|---|\n")
