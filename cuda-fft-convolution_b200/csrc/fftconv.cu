@@ -110,7 +110,7 @@ struct Ctx {
     bool inited = false;
     std::map<int, cpx*> tw;          // n -> device twiddle table e^{-2 pi i j / n}
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
-    DevBuf osA, osB, osP, osPlane, osZ;     // overlap-save / tcgen05 path scratch
+    DevBuf osA, osB, osP, osPlane, osZ, osPeaks;     // overlap-save / tcgen05 path scratch
     void* pinned = nullptr;          // host staging (descriptors, packed kernels)
     size_t pinned_cap = 0;
     cudaEvent_t pinned_free = nullptr;   // recorded after the last async copy out of `pinned`
@@ -528,7 +528,8 @@ static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates, bool need_
 }
 
 static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
-                    const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0, const float* bankA = nullptr) {
+                    const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0, const float* bankA = nullptr,
+                    unsigned long long* peak_keys = nullptr, const int2* khw = nullptr, int H = 0, int W = 0) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
     if (!bankA) {
         OsKArgs a{};
@@ -561,6 +562,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS;
         a.NT = g.NT; a.NTimg = g.NTimg; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
+        a.peak_keys = peak_keys; a.khw = khw; a.H = H; a.W = W;
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
@@ -591,6 +593,8 @@ struct ConvArgs {
     int rawH = 0, rawW = 0;
     const float* bankA = nullptr;  // prepared bank (fftconv_bank_*): A operand images of all K templates, path 3 only
     int bank_maxkh = 0, bank_maxkw = 0;
+    unsigned long long* peak_keys = nullptr;   // fused maximum (fftconv_bank_conv_max): K packed keys, no planes
+    const int2* bank_khw = nullptr;            // (kh, kw) of every template of the bank (device)
     int nimg = 1;                  // batched entry point: nimg images [nimg][F][rawW][rawH] (raw, device, overlap-save path
                                    // only); outs then holds nimg*K device planes, image-major
 };
@@ -773,7 +777,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     }
     for (size_t ch = 0; ch + 1 < bounds.size(); ++ch)
         for (int k = bounds[ch]; k < bounds[ch + 1]; ++k)
-            h_outp[k] = a.out_on_device ? a.outs[k]
+            h_outp[k] = a.peak_keys ? nullptr : a.out_on_device ? a.outs[k]
                                         : reinterpret_cast<float*>(c.outstage.p) + plane * (size_t)((k - bounds[ch]) + (ch & 1) * KC);
     for (size_t i = K; i < NO; ++i) h_outp[i] = a.outs[i];         // images 1.. of a batch (device planes)
     CU(cudaMemcpyAsync(c.desc.p, c.pinned, desc_bytes, cudaMemcpyHostToDevice, st));
@@ -799,7 +803,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         int e;
         if (osg)
             e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K,
-                         a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr);
+                         a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr,
+                         a.peak_keys ? a.peak_keys + k0 : nullptr, a.bank_khw ? a.bank_khw + k0 : nullptr, a.rawH, a.rawW);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
@@ -1068,6 +1073,7 @@ struct fftconv_bank {
     int device, K, F, maxkh, maxkw, NKS, KC;
     float* A;             // [ceil(K/128)][bin][ks][kc][128][4] fp32
     size_t bytes;
+    int2* khw;            // (kh, kw) per template, device
 };
 
 int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
@@ -1089,9 +1095,18 @@ int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const
     if (int e = ctx_get(device, &c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int ntblk = (K + OS_TM - 1) / OS_TM;
-    std::unique_ptr<fftconv_bank> b(new fftconv_bank{device, K, F, maxkh, maxkw, g.NKS, g.KC, nullptr, 0});
+    std::unique_ptr<fftconv_bank> b(new fftconv_bank{device, K, F, maxkh, maxkw, g.NKS, g.KC, nullptr, 0, nullptr});
     b->bytes = (size_t)ntblk * OS_NBIN * g.NKS * (g.a_stage / 2);
     CU(cudaMalloc(&b->A, b->bytes));
+    {
+        std::vector<int2> khw(K);
+        for (int k = 0; k < K; ++k) khw[k] = make_int2(refs[k].kh, refs[k].kw);
+        if (cudaMalloc(&b->khw, sizeof(int2) * (size_t)K) != cudaSuccess ||
+            cudaMemcpy(b->khw, khw.data(), sizeof(int2) * (size_t)K, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaFree(b->A); cudaFree(b->khw);
+            return fail(FFTCONV_ERR_CUDA, "bank allocation failed");
+        }
+    }
     // stage host kernels + descriptors (the call is synchronous, so the shared staging buffers can be reused)
     size_t host_bytes = 0;
     for (int k = 0; k < K; ++k)
@@ -1128,7 +1143,7 @@ int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const
         if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
             e = fail(FFTCONV_ERR_CUDA, "bank transform failed");
     }
-    if (e) { cudaFree(b->A); return e; }
+    if (e) { cudaFree(b->A); cudaFree(b->khw); return e; }
     *out = b.release();
     return 0;
 }
@@ -1175,11 +1190,54 @@ int fftconv_bank_conv(const fftconv_bank* b, const float* data, int data_on_devi
     return run_conv(*c, a, st);
 }
 
+int fftconv_bank_conv_max(const fftconv_bank* b, const float* data, int data_on_device, int H, int W,
+                          fftconv_peak* peaks, int peaks_on_device, void* stream) {
+    g_err.clear();
+    if (!b || !data || !peaks || H <= 0 || W <= 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    const int F = b->F, K = b->K;
+    const int FH = fftconv_fft_size16(H + b->maxkh - 1), FW = fftconv_fft_size16(W + b->maxkw - 1);
+    if (FH > 65535 || FW > 65535) return fail(FFTCONV_ERR_UNSUPPORTED, "plane too large for packed peak positions");
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard guard(b->device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
+    Ctx* c;
+    if (int e = ctx_get(b->device, &c)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* d_data = data;
+    if (!data_on_device) {
+        const size_t bytes = sizeof(float) * (size_t)H * W * F;
+        if (int e = dev_reserve(c->ddata, bytes)) return e;
+        CU(cudaMemcpyAsync(c->ddata.p, data, bytes, cudaMemcpyHostToDevice, st));
+        d_data = (const float*)c->ddata.p;
+    }
+    if (int e = dev_reserve(c->osPeaks, (sizeof(unsigned long long) + sizeof(fftconv_peak)) * (size_t)K)) return e;
+    unsigned long long* keys = (unsigned long long*)c->osPeaks.p;
+    fftconv_peak* d_peaks = peaks_on_device ? peaks : reinterpret_cast<fftconv_peak*>(keys + K);
+    CU(cudaMemsetAsync(keys, 0, sizeof(unsigned long long) * (size_t)K, st));
+    ConvArgs a;
+    a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = F; a.K = K;
+    a.kernels = nullptr; a.outs = nullptr; a.out_on_device = true;
+    a.opt = fftconv_options{}; a.pipelined = false;
+    a.d_raw = d_data; a.rawH = H; a.rawW = W;
+    a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw;
+    a.peak_keys = keys; a.bank_khw = b->khw;
+    if (int e = run_conv(*c, a, st)) return e;
+    static_assert(sizeof(fftconv_peak) == sizeof(fftconv_peak_dev), "peak layouts differ");
+    os_peak_finalize<<<(K + 255) / 256, 256, 0, st>>>(keys, K, reinterpret_cast<fftconv_peak_dev*>(d_peaks));
+    LAUNCH_CHECK();
+    if (!peaks_on_device) {
+        CU(cudaMemcpyAsync(peaks, d_peaks, sizeof(fftconv_peak) * (size_t)K, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return 0;
+}
+
 void fftconv_bank_destroy(fftconv_bank* b) {
     if (!b) return;
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceGuard guard(b->device);
     cudaFree(b->A);
+    cudaFree(b->khw);
     delete b;
 }
 
@@ -1275,7 +1333,7 @@ void fftconv_release(void) {
         cudaDeviceSynchronize();
         for (auto& t : c.tw) cudaFree(t.second);
         for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg,
-                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ})
+                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks})
             if (b->p) cudaFree(b->p);
         if (c.pinned) cudaFreeHost(c.pinned);
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);

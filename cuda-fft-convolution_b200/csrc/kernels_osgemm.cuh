@@ -737,7 +737,32 @@ struct OsInvArgs {
     int nk, NNB, NTn, RS, NT, NTimg, nth, Sh, Sw, oy0, ox0;
     int FH, FW, crop_h, crop_w, out_ld;
     int out_img_stride;     // plane of (image n, template t) = outs[n * out_img_stride + t]
+    // fused reduction (fftconv_bank_conv_max): when peak_keys != nullptr no plane is written; every template keeps the
+    // maximum of its full linear convolution (H + kh - 1) x (W + kw - 1) as a packed (ordered value, position) key
+    unsigned long long* peak_keys;
+    const int2* khw;        // (kh, kw) per template of the chunk
+    int H, W;
 };
+
+// order-preserving map float -> uint32 (larger float <=> larger uint)
+__device__ __forceinline__ unsigned os_ordered(float f) {
+    const unsigned u = __float_as_uint(f);
+    return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+// key = ordered value << 32 | ~(x << 16 | y): ties resolve to the smallest position
+__device__ __forceinline__ unsigned long long os_peak_key(float v, int y, int x) {
+    return ((unsigned long long)os_ordered(v) << 32) | (unsigned long long)(0xFFFFFFFFu - (((unsigned)x << 16) | (unsigned)y));
+}
+
+struct fftconv_peak_dev { float value; int y, x, pad; };
+__global__ void os_peak_finalize(const unsigned long long* keys, int K, fftconv_peak_dev* out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    const unsigned long long key = keys[k];
+    const unsigned o = (unsigned)(key >> 32), pos = 0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFu);
+    const unsigned u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+    out[k].value = __uint_as_float(u); out[k].y = (int)(pos & 0xFFFFu); out[k].x = (int)(pos >> 16); out[k].pad = 0;
+}
 
 __device__ __forceinline__ int os_icol(int v) { return v * OS_ICOL + ((v >> 5) << 2); }
 
@@ -752,7 +777,7 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
     // per-tile store parameters, fetched / computed now by one thread per tile so that the plane-pointer load hides
     // behind the gather: base of the valid block in the plane, rows / columns to store
     __shared__ float* tile_dst[OS_IG];
-    __shared__ int tile_ny[OS_IG], tile_nx[OS_IG];
+    __shared__ int tile_ny[OS_IG], tile_nx[OS_IG], tile_y0[OS_IG], tile_x0[OS_IG];
     if (threadIdx.x < OS_IG) {
         const int m = m0 + threadIdx.x;
         float* d = nullptr; int ny = 0, nx = 0;
@@ -760,8 +785,14 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
             const int img = m / a.NTimg, mt = m - img * a.NTimg;
             const int tj = mt / a.nth, ti = mt - tj * a.nth;
             const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
-            ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
-            d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
+            if (a.peak_keys) {                    // region of the full linear convolution of THIS template
+                const int2 k = a.khw[t];
+                ny = min(a.Sh, a.H + k.x - 1 - Y0); nx = min(a.Sw, a.W + k.y - 1 - X0);
+                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+            } else {
+                ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
+                d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
+            }
         }
         tile_dst[threadIdx.x] = d; tile_ny[threadIdx.x] = ny; tile_nx[threadIdx.x] = nx;
     }
@@ -848,6 +879,24 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         const int ny = tile_ny[gq], nx = tile_nx[gq];
         const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
         const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
+        if (a.peak_keys) {
+            float best = -INFINITY; int by = 0, bx = 0;
+            auto upd = [&](float v, int yy, int xx) { if (v > best) { best = v; by = yy; bx = xx; } };
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {                             // ascending x: the first maximum wins
+                const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+                if (xa >= 0 && xa < nx) { if (wlo) upd(reA[j1], ylo, xa); if (whi) upd(imA[j1], yhi, xa); }
+                if (xb >= 0 && xb < nx) { if (wlo) upd(reB[j1], ylo, xb); if (whi) upd(imB[j1], yhi, xb); }
+            }
+            unsigned long long key = best > -INFINITY ? os_peak_key(best, tile_y0[gq] + by, tile_x0[gq] + bx) : 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            if (lane == 0 && key) atomicMax(a.peak_keys + t, key);
+            return;
+        }
         float* dst = tile_dst[gq] + ylo;
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) {

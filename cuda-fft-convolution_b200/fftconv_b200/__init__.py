@@ -38,7 +38,7 @@ LIB_PATH = os.environ.get("FFTCONV_LIB") or os.path.join(_HERE, "libfftconv.so")
 EXPORTED_SYMBOLS = [
     "fftconv_fft_size16", "fftconv_fft_size_pow2", "fftconv_fft_data", "fftconv_fft_data_clamp",
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
-    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv",
+    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv", "fftconv_bank_conv_max",
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
@@ -103,6 +103,7 @@ def lib() -> ctypes.CDLL:
         L.fftconv_bank_create.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]
         L.fftconv_bank_info.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.fftconv_bank_conv.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]
+        L.fftconv_bank_conv_max.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]
         L.fftconv_bank_destroy.argtypes = [c_vp]
         L.fftconv_bank_destroy.restype = None
         L.fftconv_conv_bank.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]
@@ -512,6 +513,20 @@ class Bank:
         rc = lib().fftconv_bank_conv(self._h, data_t.data_ptr(), 1, H, W, ptrs, 1, op, st)
         _check(rc, ERRID_CONV)
         return out_t
+
+    def conv_max(self, data):
+        """Fused detection reduction (fftconv_bank_conv_max): -> (value[K] float32, y[K], x[K] int32), the maximum of
+        every template's full linear convolution and its 0-based position; no plane is written or copied."""
+        d_fwh = _as_single_3d(data, ERRID_CONV, MSG_INVALID)
+        F, W, H = d_fwh.shape
+        if F != self.F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        peaks = np.zeros((self.K, 4), dtype=np.int32)
+        torch = _torch()
+        rc = lib().fftconv_bank_conv_max(self._h, d_fwh.ctypes.data, 0, H, W, peaks.ctypes.data, 0,
+                                         torch.cuda.current_stream(self.device).cuda_stream)
+        _check(rc, ERRID_CONV)
+        return peaks[:, 0].copy().view(np.float32), peaks[:, 1].copy(), peaks[:, 2].copy()
 
     def close(self):
         if getattr(self, "_h", None):

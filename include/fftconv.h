@@ -144,6 +144,14 @@ int fftconv_bank_conv(const fftconv_bank* bank, const float* data, int data_on_d
                       float* const* outs, int out_on_device, const fftconv_options* opt, void* stream);
 void fftconv_bank_destroy(fftconv_bank* bank);
 
+/* Extension: the detection consumers of the reference crop each plane and take its maximum on the host
+ * (demoCudaConvolutionFFT.m:149 onward).  Here the reduction is fused into the store of the inverse transform: no
+ * plane is written or copied; template k yields the maximum of its full linear convolution, i.e. of the
+ * (H + kh_k - 1) x (W + kw_k - 1) top-left block of its plane, and its 0-based position (ties: smallest x, then y). */
+typedef struct fftconv_peak { float value; int y; int x; int pad; } fftconv_peak;
+int fftconv_bank_conv_max(const fftconv_bank* bank, const float* data, int data_on_device, int H, int W,
+                          fftconv_peak* peaks, int peaks_on_device, void* stream);
+
 /* modulateAndNormalize — src/convolutionFFTkernel.cu:84-100: in place a = a*b/dataN. */
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
                                    long long n, int device, void* stream);

@@ -122,3 +122,31 @@ def test_prepared_bank_device_path_and_errors(fc, oracle):
     with pytest.raises(fc.FFTConvError):
         fc.Bank([np.zeros((40, 8, F), np.float32)])                     # beyond 32 x 32: not a prepared-bank shape
     bank.close()
+
+
+def test_fused_peak_reduction_matches_planes(fc, oracle):
+    """fftconv_bank_conv_max: maximum + position of every template's full convolution, fused into the inverse store."""
+    rng = np.random.default_rng(71)
+    F, K, H, W = 5, 140, 83, 61
+    ks = []
+    for k in range(K):
+        a, b = (int(rng.integers(2, 17)), int(rng.integers(2, 13)))
+        ks.append((rng.standard_normal((a, b, F))).astype(np.float32))
+    data = rng.standard_normal((H, W, F)).astype(np.float32)
+    bank = fc.Bank(ks)
+    planes = bank.conv(data)
+    before = fc.launch_count()
+    val, ys, xs = bank.conv_max(data)
+    assert fc.launch_count() > before
+    for k in range(K):
+        kh, kw, _ = ks[k].shape
+        blk = planes[k][:H + kh - 1, :W + kw - 1]
+        x, y = np.unravel_index(np.argmax(blk.T), blk.T.shape)             # first maximum, smallest x then y
+        assert val[k] == blk.max(), k                                       # same arithmetic as the plane: bit-equal
+        assert (ys[k], xs[k]) == (y, x), k
+    # and against the float64 direct convolution
+    for k in (0, 70, K - 1):
+        kh, kw, _ = ks[k].shape
+        ref = oracle.direct_conv64_c(data, ks[k], *bank.plane(H, W))[:H + kh - 1, :W + kw - 1]
+        assert abs(val[k] - ref.max()) <= 1e-5 * np.abs(ref).max() * 10
+    bank.close()
