@@ -534,6 +534,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
     if (!bankA) {
         OsKArgs a{};
         a.descs = d_descs; a.nk = nk; a.F = g.F; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
+        a.flip = opt.correlate ? 1 : 0;
         dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
         ProfScope ps(PK_OS_KERN, st);
         if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);
@@ -563,6 +564,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.NT = g.NT; a.NTimg = g.NTimg; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
         a.peak_keys = peak_keys; a.khw = khw; a.H = H; a.W = W;
+        a.corr = (opt.correlate && !peak_keys) ? 1 : 0;
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
@@ -605,7 +607,7 @@ enum ConvPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TILE16 = 2, PATH_OSGEMM = 
 // 128-row MMA blocks; small banks stay on the SIMT pipelines.
 static int choose_path(const fftconv_options& opt, int F, int FH, int FW, int maxkh, int maxkw, int K) {
     OsCfg g;
-    const bool os_ok = !opt.correlate && os_config(F, FH, FW, maxkh, maxkw, g);
+    const bool os_ok = os_config(F, FH, FW, maxkh, maxkw, g);
     const bool t16_ok = tile16_supported(FH, FW, maxkh, maxkw);
     if (opt.force_generic || opt.path == PATH_GENERIC) return PATH_GENERIC;
     if (opt.path == PATH_OSGEMM) return os_ok ? PATH_OSGEMM : (t16_ok ? PATH_TILE16 : PATH_GENERIC);
@@ -709,7 +711,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     if (osg) {
         KC = std::min(K, os_max_chunk(og, a.out_on_device));
         if (int e = os_reserve_chunk(c, og, KC, a.bankA == nullptr)) return e;
-        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, a.opt.correlate, st)) return e;
+        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, 0, st)) return e;   // correlation = flipped templates + shifted store
     } else if (tile16) {
         // one CTA per SM: size the chunk so that NT * ceil(KC/KB) CTAs fill whole waves
         Tile16Cfg g;
@@ -736,7 +738,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (int e = dev_reserve(c.outstage, sizeof(float) * plane * KC * 2)) return e;
 
     // descriptors / kcols / out pointers for ALL kernels go through pinned staging once
-    const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int)) * (size_t)K + sizeof(float*) * NO + 64;
+    const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int2) + sizeof(int)) * (size_t)K + sizeof(float*) * NO + 64;
     size_t host_kernel_bytes = 0;
     for (int k = 0; k < K && !a.bankA; ++k)
         if (!a.kernels[k].on_device) host_kernel_bytes += sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
@@ -748,10 +750,12 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     CU(cudaEventSynchronize(c.pinned_free));
     SrcDesc* h_desc = reinterpret_cast<SrcDesc*>(c.pinned);
     float** h_outp = reinterpret_cast<float**>(h_desc + K);
-    int* h_kcols = reinterpret_cast<int*>(h_outp + NO);
+    int2* h_khw = reinterpret_cast<int2*>(h_outp + NO);
+    int* h_kcols = reinterpret_cast<int*>(h_khw + K);
     SrcDesc* d_desc = reinterpret_cast<SrcDesc*>(c.desc.p);
     float** d_outp = reinterpret_cast<float**>(d_desc + K);
-    int* d_kcols = reinterpret_cast<int*>(d_outp + NO);
+    int2* d_khw = reinterpret_cast<int2*>(d_outp + NO);
+    int* d_kcols = reinterpret_cast<int*>(d_khw + K);
 
     // chunk boundaries.  Host outputs: the D2H stream is the bottleneck (PCIe), so the first chunk is kept
     // small -- its results start flowing to the host while the rest of the bank is still being computed.
@@ -773,6 +777,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
                                                : reinterpret_cast<const float*>(reinterpret_cast<char*>(c.stage.p) + stage_off[k]);
         h_desc[k].rows = a.kernels[k].kh;
         h_desc[k].cols = a.kernels[k].kw;
+        h_khw[k] = make_int2(a.kernels[k].kh, a.kernels[k].kw);
         h_kcols[k] = a.kernels[k].kw;
     }
     for (size_t ch = 0; ch + 1 < bounds.size(); ++ch)
@@ -804,7 +809,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (osg)
             e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K,
                          a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr,
-                         a.peak_keys ? a.peak_keys + k0 : nullptr, a.bank_khw ? a.bank_khw + k0 : nullptr, a.rawH, a.rawW);
+                         a.peak_keys ? a.peak_keys + k0 : nullptr, (a.bank_khw ? a.bank_khw : d_khw) + k0, a.rawH, a.rawW);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
@@ -1134,7 +1139,7 @@ int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const
     }
     if (!e) {
         OsKArgs a{};
-        a.descs = (const SrcDesc*)c->desc.p; a.nk = K; a.F = F; a.img = b->A; a.NKS = g.NKS; a.KC = g.KC;
+        a.descs = (const SrcDesc*)c->desc.p; a.nk = K; a.F = F; a.img = b->A; a.NKS = g.NKS; a.KC = g.KC; a.flip = 0;
         dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
         ProfScope ps(PK_OS_KERN, st);
         if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);

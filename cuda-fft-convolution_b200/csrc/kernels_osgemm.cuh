@@ -183,6 +183,7 @@ struct OsKArgs {
     int nk, F;
     float* img;
     int NKS, KC;
+    int flip;               // correlation mode: the template is read flipped in h and w (its own extent)
 };
 constexpr int OS_KSL = 16;            // templates per CTA
 
@@ -212,16 +213,18 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
             if (item < a.nk && f < a.F) {
                 const SrcDesc d = a.descs[item];
                 const int xa = 2 * cp, xb = xa + 1;
-                const float* pa = d.ptr + ((size_t)f * d.cols + xa) * d.rows;
-                const float* pb = pa + d.rows;
                 const bool va = xa < d.cols, vb = xb < d.cols;
                 const int rows = d.rows;
+                // flipped read: sample (j, x) of the sequence is element (rows-1-j, cols-1-x) of the template
+                const float* pa = d.ptr + ((size_t)f * d.cols + (a.flip ? d.cols - 1 - xa : xa)) * d.rows + (a.flip ? rows - 1 : 0);
+                const float* pb = d.ptr + ((size_t)f * d.cols + (a.flip ? d.cols - 1 - xb : xb)) * d.rows + (a.flip ? rows - 1 : 0);
+                const int sj = a.flip ? -1 : 1;
                 auto ld = [&](int j) {
                     float4 v;
-                    v.x = (va && j < rows) ? __ldg(pa + j) : 0.f;
-                    v.y = (vb && j < rows) ? __ldg(pb + j) : 0.f;
-                    v.z = (va && j + 1 < rows) ? __ldg(pa + j + 1) : 0.f;
-                    v.w = (vb && j + 1 < rows) ? __ldg(pb + j + 1) : 0.f;
+                    v.x = (va && j < rows) ? __ldg(pa + sj * j) : 0.f;
+                    v.y = (vb && j < rows) ? __ldg(pb + sj * j) : 0.f;
+                    v.z = (va && j + 1 < rows) ? __ldg(pa + sj * (j + 1)) : 0.f;
+                    v.w = (vb && j + 1 < rows) ? __ldg(pb + sj * (j + 1)) : 0.f;
                     return v;
                 };
                 float pr[16], pi[16], qr[16], qi[16];
@@ -740,8 +743,10 @@ struct OsInvArgs {
     // fused reduction (fftconv_bank_conv_max): when peak_keys != nullptr no plane is written; every template keeps the
     // maximum of its full linear convolution (H + kh - 1) x (W + kw - 1) as a packed (ordered value, position) key
     unsigned long long* peak_keys;
-    const int2* khw;        // (kh, kw) per template of the chunk
+    const int2* khw;        // (kh, kw) per template of the chunk (peak and correlation modes)
     int H, W;
+    int corr;               // correlation mode: plane position (Y, X) of the flipped-template convolution is stored at
+                            // ((Y - kh + 1) mod FH, (X - kw + 1) mod FW)
 };
 
 // order-preserving map float -> uint32 (larger float <=> larger uint)
@@ -789,6 +794,10 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
                 const int2 k = a.khw[t];
                 ny = min(a.Sh, a.H + k.x - 1 - Y0); nx = min(a.Sw, a.W + k.y - 1 - X0);
                 tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+            } else if (a.corr) {
+                ny = min(a.Sh, a.FH - Y0); nx = min(a.Sw, a.FW - X0);
+                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+                d = a.outs[(size_t)img * a.out_img_stride + t];
             } else {
                 ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
                 d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
@@ -895,6 +904,30 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
                 key = other > key ? other : key;
             }
             if (lane == 0 && key) atomicMax(a.peak_keys + t, key);
+            return;
+        }
+        if (a.corr) {
+            const int2 k = a.khw[t];
+            float* base = tile_dst[gq];
+            int ydl = tile_y0[gq] + ylo - (k.x - 1), ydh = tile_y0[gq] + yhi - (k.x - 1);
+            if (ydl < 0) ydl += a.FH;
+            if (ydh < 0) ydh += a.FH;
+            const bool slo = wlo && ydl < a.crop_h, shi = whi && ydh < a.crop_h;
+            const int xs = tile_x0[gq] - (k.y - 1);
+            auto put = [&](int xr, float vlo, float vhi) {
+                if (xr < 0 || xr >= nx) return;
+                int xd = xs + xr;
+                if (xd < 0) xd += a.FW;
+                if (xd >= a.crop_w) return;
+                float* d = base + (size_t)xd * a.out_ld;
+                if (slo) d[ydl] = vlo;
+                if (shi) d[ydh] = vhi;
+            };
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                put(4 * j1 + par - a.ox0, reA[j1], imA[j1]);
+                put(4 * j1 + par + 2 - a.ox0, reB[j1], imB[j1]);
+            }
             return;
         }
         float* dst = tile_dst[gq] + ylo;

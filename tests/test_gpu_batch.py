@@ -150,3 +150,21 @@ def test_fused_peak_reduction_matches_planes(fc, oracle):
         ref = oracle.direct_conv64_c(data, ks[k], *bank.plane(H, W))[:H + kh - 1, :W + kw - 1]
         assert abs(val[k] - ref.max()) <= 1e-5 * np.abs(ref).max() * 10
     bank.close()
+
+
+@pytest.mark.parametrize("path", [2, 3])
+def test_correlation_mode_per_template_sizes(fc, oracle, path):
+    """correlate = 1 (complexConjMulAndScale, src/cudaConvFFTData.cuh:42-45,63): circular cross-correlation on the
+    plane = convolution with the flipped template, shifted by (kh-1, kw-1) per template."""
+    rng = np.random.default_rng(81)
+    H, W, F, K = 75, 58, 4, 70
+    data = rng.random((H, W, F), dtype=np.float32)
+    ks = [rng.standard_normal((int(rng.integers(1, 15)), int(rng.integers(1, 13)), F)).astype(np.float32) for _ in range(K)]
+    ks[0] = rng.standard_normal((14, 12, F)).astype(np.float32)
+    corr = fc.cudaConvolutionFFT(data, 14, 12, ks, options=fc.Options(correlate=1, path=path))
+    FH, FW = fc.computeFFTsize16(H + 13), fc.computeFFTsize16(W + 11)
+    for k in (0, 1, 35, K - 1):
+        kh, kw, _ = ks[k].shape
+        flip = oracle.direct_conv64_c(data, np.ascontiguousarray(ks[k][::-1, ::-1, :]), FH, FW)
+        want = np.roll(flip, (-(kh - 1), -(kw - 1)), axis=(0, 1))
+        assert oracle.rel_l2(corr[k], want) < TOL, (path, k)
