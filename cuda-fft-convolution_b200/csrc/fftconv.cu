@@ -116,6 +116,8 @@ struct Ctx {
     cudaEvent_t pinned_free = nullptr;   // recorded after the last async copy out of `pinned`
     cudaStream_t side = nullptr;         // copy stream for the chunk pipeline
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t side2 = nullptr;        // data-side transforms of the overlap-save path run here, next to os_kern_fft
+    cudaEvent_t evf[2] = {nullptr, nullptr};
     int sm_count = 148;
 };
 
@@ -174,6 +176,8 @@ static int ctx_get(int device, Ctx** out) {
         CU(cudaEventCreateWithFlags(&c.pinned_free, cudaEventDisableTiming));
         for (auto& e : c.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c.side2, cudaStreamNonBlocking));
+        for (auto& e : c.evf) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         if (opt_in_smem(fwd_h_pass<PAD_ZERO>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(fwd_h_pass<PAD_CLAMP>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(fwd_w_pass)) return FFTCONV_ERR_CUDA;
@@ -506,7 +510,9 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
     return 0;
 }
 
-static size_t os_kern_smem(int NF) { return (size_t)32 * (17 * 16 * NF + 2) * sizeof(cpx); }
+static size_t os_kern_smem(int NF) {
+    return (size_t)32 * (17 * 16 * NF + 2) * sizeof(cpx) + (NF == 1 ? (size_t)32 * (16 * 18 + 2) * sizeof(float) : 0);   // + staged raw planes
+}
 
 // Templates per chunk.  Device outputs: as large as the scratch budget allows (fewer launch tails, the B images are
 // streamed once per chunk).  Host outputs: small chunks, so that the D2H of one chunk overlaps the next one's compute.
@@ -529,7 +535,8 @@ static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates, bool need_
 
 static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
                     const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0, const float* bankA = nullptr,
-                    unsigned long long* peak_keys = nullptr, const int2* khw = nullptr, int H = 0, int W = 0) {
+                    unsigned long long* peak_keys = nullptr, const int2* khw = nullptr, int H = 0, int W = 0,
+                    cudaEvent_t data_ready = nullptr) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
     if (!bankA) {
         OsKArgs a{};
@@ -541,6 +548,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         else os_kern_fft<2><<<grid, 256, os_kern_smem(2), st>>>(a);
         LAUNCH_CHECK();
     }
+    if (data_ready) CU(cudaStreamWaitEvent(st, data_ready, 0));      // B images of this call are complete
     {
         OsGemmArgs a{};
         a.Aimg = bankA ? bankA : (const float*)c.osA.p; a.Bimg = (const float*)c.osB.p; a.P = (float*)c.osP.p;
@@ -711,7 +719,13 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     if (osg) {
         KC = std::min(K, os_max_chunk(og, a.out_on_device));
         if (int e = os_reserve_chunk(c, og, KC, a.bankA == nullptr)) return e;
-        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, 0, st)) return e;   // correlation = flipped templates + shifted store
+        // The data-side transforms (spectrum -> plane -> tile spectra: small, latency-bound grids) do not depend on the
+        // bank: they run on a side stream in the shadow of the first os_kern_fft and join before the first GEMM.
+        CU(cudaEventRecord(c.evf[0], st));
+        CU(cudaStreamWaitEvent(c.side2, c.evf[0], 0));
+        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, 0, c.side2)) return e;   // correlation = flipped templates + shifted store
+        CU(cudaEventRecord(c.evf[1], c.side2));
+        if (a.bankA) CU(cudaStreamWaitEvent(st, c.evf[1], 0));      // prepared bank: nothing to overlap with
     } else if (tile16) {
         // one CTA per SM: size the chunk so that NT * ceil(KC/KB) CTAs fill whole waves
         Tile16Cfg g;
@@ -809,7 +823,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (osg)
             e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K,
                          a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr,
-                         a.peak_keys ? a.peak_keys + k0 : nullptr, (a.bank_khw ? a.bank_khw : d_khw) + k0, a.rawH, a.rawW);
+                         a.peak_keys ? a.peak_keys + k0 : nullptr, (a.bank_khw ? a.bank_khw : d_khw) + k0, a.rawH, a.rawW,
+                         (chunk == 0 && !a.bankA) ? c.evf[1] : nullptr);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else
@@ -1344,6 +1359,8 @@ void fftconv_release(void) {
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);
         for (auto& e : c.ev) if (e) cudaEventDestroy(e);
         if (c.side) cudaStreamDestroy(c.side);
+        if (c.side2) cudaStreamDestroy(c.side2);
+        for (auto& e : c.evf) if (e) cudaEventDestroy(e);
     }
     g_ctx.clear();
     if (prev >= 0) cudaSetDevice(prev);

@@ -202,6 +202,33 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
     const size_t stage_floats = (size_t)a.KC * OS_TM * 4;           // one K-stage of one bin
     const size_t bin_stride = (size_t)a.NKS * stage_floats;
 
+    // NF = 1: the 32 zero-padded (and, in correlation mode, flipped) 16 x 16 template planes of this CTA are staged in
+    // shared memory once, by asynchronous 4-byte copies (all 32 of a thread in flight); both phases read them from there
+    constexpr bool STAGED = NF == 1;
+    constexpr int RCOL = 18, RPL = 16 * RCOL + 2;      // raw column / plane stride (floats): conflict-free 64-bit reads
+    float* raw = reinterpret_cast<float*>(os_smem_raw + (size_t)32 * PS * sizeof(cpx));   // [32 planes][RPL]
+    if (STAGED) {
+        const int y = threadIdx.x & 15, x = threadIdx.x >> 4;
+#pragma unroll 4
+        for (int pl = 0; pl < 32; ++pl) {
+            const int item = slot0 + (pl & 15), f = 2 * fp + (pl >> 4);
+            float* dst = raw + pl * RPL + x * RCOL + y;
+            bool issued = false;
+            if (item < a.nk && f < a.F) {
+                const SrcDesc d = a.descs[item];
+                if (x < d.cols && y < d.rows) {
+                    const int sx = a.flip ? d.cols - 1 - x : x, sy = a.flip ? d.rows - 1 - y : y;
+                    const float* src = d.ptr + ((size_t)f * d.cols + sx) * d.rows + sy;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+                    issued = true;
+                }
+            }
+            if (!issued) *dst = 0.f;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+    }
+
 #pragma unroll 1
     for (int ph = 0; ph < 2; ++ph) {
         // ---- h step
@@ -211,20 +238,27 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
             const int item = slot0 + slot, f = 2 * fp + ch;
             float4* hrow = reinterpret_cast<float4*>(Hs + (size_t)pl * PS) + cp;      // + ro * (XC/2)
             if (item < a.nk && f < a.F) {
-                const SrcDesc d = a.descs[item];
+                // direct loads (NF = 2): flipped read = element (rows-1-j, cols-1-x) of the template
+                SrcDesc d{};
+                if (!STAGED) d = a.descs[item];
                 const int xa = 2 * cp, xb = xa + 1;
                 const bool va = xa < d.cols, vb = xb < d.cols;
                 const int rows = d.rows;
-                // flipped read: sample (j, x) of the sequence is element (rows-1-j, cols-1-x) of the template
-                const float* pa = d.ptr + ((size_t)f * d.cols + (a.flip ? d.cols - 1 - xa : xa)) * d.rows + (a.flip ? rows - 1 : 0);
-                const float* pb = d.ptr + ((size_t)f * d.cols + (a.flip ? d.cols - 1 - xb : xb)) * d.rows + (a.flip ? rows - 1 : 0);
+                const float* pa = STAGED ? nullptr : d.ptr + ((size_t)f * d.cols + (a.flip ? d.cols - 1 - xa : xa)) * d.rows + (a.flip ? rows - 1 : 0);
+                const float* pb = STAGED ? nullptr : d.ptr + ((size_t)f * d.cols + (a.flip ? d.cols - 1 - xb : xb)) * d.rows + (a.flip ? rows - 1 : 0);
                 const int sj = a.flip ? -1 : 1;
+                const float* ca = raw + pl * RPL + xa * RCOL;          // staged (NF = 1): two 64-bit reads per sample pair
                 auto ld = [&](int j) {
                     float4 v;
-                    v.x = (va && j < rows) ? __ldg(pa + sj * j) : 0.f;
-                    v.y = (vb && j < rows) ? __ldg(pb + sj * j) : 0.f;
-                    v.z = (va && j + 1 < rows) ? __ldg(pa + sj * (j + 1)) : 0.f;
-                    v.w = (vb && j + 1 < rows) ? __ldg(pb + sj * (j + 1)) : 0.f;
+                    if (STAGED) {
+                        const float2 p = *reinterpret_cast<const float2*>(ca + j), q = *reinterpret_cast<const float2*>(ca + RCOL + j);
+                        v = make_float4(p.x, q.x, p.y, q.y);
+                    } else {
+                        v.x = (va && j < rows) ? __ldg(pa + sj * j) : 0.f;
+                        v.y = (vb && j < rows) ? __ldg(pb + sj * j) : 0.f;
+                        v.z = (va && j + 1 < rows) ? __ldg(pa + sj * (j + 1)) : 0.f;
+                        v.w = (vb && j + 1 < rows) ? __ldg(pb + sj * (j + 1)) : 0.f;
+                    }
                     return v;
                 };
                 float pr[16], pi[16], qr[16], qi[16];
