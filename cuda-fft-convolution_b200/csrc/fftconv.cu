@@ -17,6 +17,7 @@
 #include "kernels_generic.cuh"
 #include "kernels_tile16.cuh"
 #include "kernels_osgemm.cuh"
+#include "kernels_bigplane.cuh"
 
 namespace fftconv {
 
@@ -51,12 +52,13 @@ static int fail(int code, const char* fmt, ...) {
 // Optional per-kernel timing (bench.py roofline leg): every launch of a profiled kind is
 // bracketed by CUDA events on the stream it is launched on.
 enum ProfKind { PK_RELAYOUT = 0, PK_KERN_H, PK_CONV, PK_C2R, PK_DATA_H, PK_DATA_W, PK_GEN_H, PK_GEN_W, PK_GEN_C2R,
-                PK_OS_PLANE, PK_OS_DATA, PK_OS_KERN, PK_OS_GEMM, PK_OS_INV, PK_COUNT };
+                PK_OS_PLANE, PK_OS_DATA, PK_OS_KERN, PK_OS_GEMM, PK_OS_INV, PK_BP_REPAD, PK_BP_KERN_H, PK_BP_CONV_W, PK_BP_INV_H, PK_COUNT };
 static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass", "tile16_conv", "tile16_c2r",
                                            "fwd_h_pass(data)", "fwd_w_pass(data)", "fwd_h_pass(kernels)",
                                            "conv_w_pass_generic", "inv_h_pass",
                                            "os_spectrum_to_plane", "os_data_fft(tiles)",
-                                           "os_kern_fft(templates)", "os_gemm", "os_inverse"};
+                                           "os_kern_fft(templates)", "os_gemm", "os_inverse",
+                                           "bp_repad_spec", "bp_kern_h", "bp_conv_w", "bp_inv_h"};
 static bool g_prof_on = false;
 struct ProfRec { int kind; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
@@ -109,6 +111,8 @@ struct Ctx {
     int dev = -1;
     bool inited = false;
     std::map<int, cpx*> tw;          // n -> device twiddle table e^{-2 pi i j / n}
+    std::map<int, unsigned short*> ipmap;   // n -> digit-reversal tables of the in-place plan: pos_of[n], nat_of[n]
+    DevBuf bpS;                      // large-plane path: re-padded, pre-scaled data spectrum
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
     DevBuf osA, osB, osP, osPlane, osZ, osPeaks;     // overlap-save / tcgen05 path scratch
     void* pinned = nullptr;          // host staging (descriptors, packed kernels)
@@ -193,6 +197,23 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_kern_h<1>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_inv_h<1>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_kern_h<2>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_inv_h<2>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_inv_h<3>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<false, false, 256>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, false, 256>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<false, true, 256>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, true, 256>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<false, false, 512>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<false, false, 1024>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, false, 512>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, false, 1024>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<false, true, 512>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<false, true, 1024>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, true, 512>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, true, 1024>)) return FFTCONV_ERR_CUDA;
         c.inited = true;
     }
     *out = &c;
@@ -609,10 +630,11 @@ struct ConvArgs {
                                    // only); outs then holds nimg*K device planes, image-major
 };
 
-enum ConvPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TILE16 = 2, PATH_OSGEMM = 3 };
+enum ConvPath { PATH_AUTO = 0, PATH_GENERIC = 1, PATH_TILE16 = 2, PATH_OSGEMM = 3, PATH_BIGPLANE = 4 };
 
 // Which pipeline serves this call.  The overlap-save / tensor-core path needs a bank large enough to fill
 // 128-row MMA blocks; small banks stay on the SIMT pipelines.
+static bool bigplane_supported(int FH, int FW, int F);
 static int choose_path(const fftconv_options& opt, int F, int FH, int FW, int maxkh, int maxkw, int K) {
     OsCfg g;
     const bool os_ok = os_config(F, FH, FW, maxkh, maxkw, g);
@@ -620,8 +642,12 @@ static int choose_path(const fftconv_options& opt, int F, int FH, int FW, int ma
     if (opt.force_generic || opt.path == PATH_GENERIC) return PATH_GENERIC;
     if (opt.path == PATH_OSGEMM) return os_ok ? PATH_OSGEMM : (t16_ok ? PATH_TILE16 : PATH_GENERIC);
     if (opt.path == PATH_TILE16) return t16_ok ? PATH_TILE16 : PATH_GENERIC;
+    const bool bp_ok = bigplane_supported(FH, FW, F);
+    if (opt.path == PATH_BIGPLANE) return bp_ok ? PATH_BIGPLANE : PATH_GENERIC;
     if (os_ok && K >= os_env_int("FFTCONV_OS_MIN_K", 64)) return PATH_OSGEMM;
-    return t16_ok ? PATH_TILE16 : PATH_GENERIC;
+    if (t16_ok) return PATH_TILE16;
+    // long lines: the in-place pipeline touches whole sectors in the strided pass (kernels_bigplane.cuh)
+    return (bp_ok && FH >= 1024 && FW >= 1024) ? PATH_BIGPLANE : PATH_GENERIC;
 }
 
 static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* d_descs, const int* d_kcols,
@@ -675,6 +701,145 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
     return 0;
 }
 
+
+// ------------------------------------------------------------------ large-plane path (kernels_bigplane.cuh), host side
+// In-place plan: odd radices first (their stride is the longest, so a zero-padded template prunes the first stage),
+// then the power of two split into radices 8 / 16 / 32.
+static bool make_ip_plan(int n, IpPlan& p) {
+    p = IpPlan{};
+    p.n = n;
+    if (n < 16 || n % 16 || n >= 65536) return false;
+    int L = n;
+    auto push = [&](int r) -> bool {
+        if (p.ns >= BP_MAX_STAGES) return false;
+        p.R[p.ns] = r; p.L[p.ns] = L; ++p.ns; L /= r;
+        return true;
+    };
+    int o = n, e = 0;
+    while ((o & 1) == 0) { o >>= 1; ++e; }        // n = o * 2^e, e >= 4
+    const int odd[] = {9, 17, 13, 11, 7, 5, 3};
+    for (int r : odd)
+        while (o % r == 0) { if (!push(r)) return false; o /= r; }
+    if (o != 1) return false;                     // a prime factor above 17: stay on the generic path
+    const int maxr = os_env_int("FFTCONV_BP_MAXR", 32);
+    const int maxbits = maxr >= 32 ? 5 : (maxr >= 16 ? 4 : 3);
+    const int nst = (e + maxbits - 1) / maxbits;  // radices 4 / 8 / 16 (/ 32)
+    for (int i = 0; i < nst; ++i) {
+        const int bits = e / nst + (i < e % nst ? 1 : 0);
+        if (!push(1 << bits)) return false;
+    }
+    return L == 1;
+}
+
+static inline int bp_ldl(int n) { return ((n + n / 16 + 15) / 16) * 16 + 4; }   // == 4 (mod 16): the 4 lines of a tile hit disjoint banks
+
+static bool bigplane_supported(int FH, int FW, int F) {
+    IpPlan a, b;
+    if (!make_ip_plan(FH, a) || !make_ip_plan(FW, b)) return false;
+    const size_t conv_smem = 4 * (size_t)bp_ldl(FW) * sizeof(cpx);
+    const size_t h_smem = 2 * (size_t)bp_ldl(FH) * sizeof(cpx);
+    (void)F;
+    return conv_smem <= kMaxSmem && h_smem <= kMaxSmem;
+}
+
+// pos_of[v]: position of natural index v in the digit-reversed order the forward stages leave; nat_of = its inverse
+static int get_ip_tables(Ctx& c, int n, const IpPlan& P, const unsigned short** pos_of, const unsigned short** nat_of) {
+    auto it = c.ipmap.find(n);
+    if (it == c.ipmap.end()) {
+        std::vector<unsigned short> h(2 * (size_t)n);
+        for (int pos = 0; pos < n; ++pos) {
+            int rem = pos, v = 0, mul = 1;
+            for (int s = 0; s < P.ns; ++s) {
+                const int m = P.L[s] / P.R[s];
+                const int q = rem / m;
+                rem -= q * m;
+                v += q * mul;
+                mul *= P.R[s];
+            }
+            h[(size_t)v] = (unsigned short)pos;
+            h[(size_t)n + pos] = (unsigned short)v;
+        }
+        unsigned short* d = nullptr;
+        CU(cudaMalloc(&d, sizeof(unsigned short) * 2 * (size_t)n));
+        CU(cudaMemcpy(d, h.data(), sizeof(unsigned short) * 2 * (size_t)n, cudaMemcpyHostToDevice));
+        it = c.ipmap.emplace(n, d).first;
+    }
+    *pos_of = it->second;
+    *nat_of = it->second + n;
+    return 0;
+}
+
+static inline int bp_chp(int CH) { return (CH + 3) & ~3; }
+
+// once per call: compat spectrum -> re-padded, pre-scaled private copy
+static int bigplane_prepare(Ctx& c, const cpx* d_spec, int CH, int FW, int F, int FH, cudaStream_t st) {
+    const int CHp = bp_chp(CH);
+    IpPlan pW;
+    make_ip_plan(FW, pW);
+    const unsigned short *posW, *natW;
+    if (int e = get_ip_tables(c, FW, pW, &posW, &natW)) return e;
+    if (int e = dev_reserve(c.bpS, sizeof(cpx) * (size_t)F * FW * CHp)) return e;
+    const long long rows = (long long)F * FW;
+    ProfScope ps(PK_BP_REPAD, st);
+    bp_repad_spec<<<c.sm_count * 8, 256, 0, st>>>(d_spec, CH, CHp, FW, rows, 1.0f / ((float)FW * (float)FH), natW, (cpx*)c.bpS.p);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* d_descs, const int* d_kcols,
+                               int nk, int maxcols, float* const* d_outptrs, cudaStream_t st) {
+    const int CH = a.CH, FW = a.FW, F = a.F, CHp = bp_chp(CH);
+    const int maxcols4 = (maxcols + 3) & ~3;
+    IpPlan pH, pW;
+    make_ip_plan(FH, pH); make_ip_plan(FW, pW);
+    const cpx *twH, *twW;
+    const unsigned short *posH, *natH, *posW, *natW;
+    if (int e = get_twiddles(c, FH, st, &twH)) return e;
+    if (int e = get_twiddles(c, FW, st, &twW)) return e;
+    if (int e = get_ip_tables(c, FH, pH, &posH, &natH)) return e;
+    if (int e = get_ip_tables(c, FW, pW, &posW, &natW)) return e;
+    const int ldH = bp_ldl(FH), ldW = bp_ldl(FW);
+    const size_t smemH = 2 * (size_t)ldH * sizeof(cpx), smemW = 4 * (size_t)ldW * sizeof(cpx);
+    {
+        dim3 grid(maxcols4 / 4, nk * F);
+        ProfScope ps(PK_BP_KERN_H, st);
+        if (os_env_int("FFTCONV_BP_HOCC", 1) >= 2)
+            bp_kern_h<2><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
+        else
+            bp_kern_h<1><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
+        LAUNCH_CHECK();
+    }
+    {
+        const bool multi = F > 1;
+        dim3 grid(nk, CHp / (multi ? 2 : 4));
+        const int threads = os_env_int("FFTCONV_BP_THREADS", 512);
+        ProfScope ps(PK_BP_CONV_W, st);
+        const cpx* T = (const cpx*)c.T.p; const cpx* Sp = (const cpx*)c.bpS.p; cpx* Z = (cpx*)c.Z.p;
+#define BP_LAUNCH(CONJ, MULTI, NT) bp_conv_w<CONJ, MULTI, NT><<<grid, NT, smemW, st>>>(T, d_kcols, maxcols4, Sp, F, FW, CHp, pW, twW, Z, ldW)
+#define BP_PICK(NT) do { if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, NT); else BP_LAUNCH(false, true, NT); } \
+                         else { if (a.opt.correlate) BP_LAUNCH(true, false, NT); else BP_LAUNCH(false, false, NT); } } while (0)
+        if (threads >= 1024) BP_PICK(1024); else if (threads >= 512) BP_PICK(512); else BP_PICK(256);
+#undef BP_PICK
+#undef BP_LAUNCH
+        LAUNCH_CHECK();
+    }
+    {
+        const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
+        const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : FW;
+        const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
+        dim3 grid(FW / 4, nk);
+        ProfScope ps(PK_BP_INV_H, st);
+        if (os_env_int("FFTCONV_BP_HOCC", 1) >= 3)
+            bp_inv_h<3><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
+        else if (os_env_int("FFTCONV_BP_HOCC", 1) >= 2)
+            bp_inv_h<2><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
+        else
+            bp_inv_h<1><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 static size_t plane_floats(const ConvArgs& a, int FH) {
     const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
     const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : a.FW;
@@ -702,6 +867,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     const int path = (a.nimg > 1 || a.bankA) ? PATH_OSGEMM : choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
     const bool tile16 = path == PATH_TILE16;
     const bool osg = path == PATH_OSGEMM;
+    const bool bigp = path == PATH_BIGPLANE;
     OsCfg og;
     if (osg && !os_config(F, FH, FW, maxkh, maxkw, og, a.nimg))
         return fail(FFTCONV_ERR_UNSUPPORTED, "batch outside the range of the overlap-save path");
@@ -712,9 +878,12 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     size_t per_kernel = 0;
     if (tile16) per_kernel = tile16_scratch_per_kernel(FH, FW, F, maxkh, maxkw);
     else if (osg) per_kernel = 0;
+    else if (bigp) per_kernel = sizeof(cpx) * ((size_t)F * ((maxkw + 3) & ~3) * bp_chp(CH) + (size_t)FW * bp_chp(CH));
     else per_kernel = sizeof(cpx) * ((size_t)F * maxkw * CH + (size_t)FW * CH);
     if (!a.out_on_device) per_kernel += plane * sizeof(float);
-    const size_t budget = (size_t)96 << 20;    // keep a chunk's intermediates L2-resident (126 MB L2)
+    // keep a chunk's intermediates L2-resident (126 MB L2); a large plane does not fit L2 anyway: there the chunk is
+    // as large as memory comfortably allows, so that the CTAs of many templates share each data-spectrum tile
+    const size_t budget = bigp ? (size_t)8 << 30 : (size_t)96 << 20;
     int KC = (int)std::max<size_t>(1, std::min<size_t>((size_t)K, budget / std::max<size_t>(per_kernel, 1)));
     if (osg) {
         KC = std::min(K, os_max_chunk(og, a.out_on_device));
@@ -744,6 +913,10 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         }
         KC = best_kc;
         if (int e = tile16_prepare(c, a.d_spec, FH, FW, F, maxkh, maxkw, KC, st)) return e;
+    } else if (bigp) {
+        if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)KC * F * ((maxkw + 3) & ~3) * bp_chp(CH))) return e;
+        if (int e = dev_reserve(c.Z, sizeof(cpx) * (size_t)KC * FW * bp_chp(CH))) return e;
+        if (int e = bigplane_prepare(c, a.d_spec, CH, FW, F, FH, st)) return e;
     } else {
         if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)KC * F * maxkw * CH)) return e;
         if (int e = dev_reserve(c.Z, sizeof(cpx) * (size_t)KC * FW * CH)) return e;
@@ -827,6 +1000,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
                          (chunk == 0 && !a.bankA) ? c.evf[1] : nullptr);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
+        else if (bigp)
+            e = conv_bigplane_chunk(c, a, FH, d_desc + k0, d_kcols + k0, nk, maxkw, d_outp + k0, st);
         else
             e = conv_generic_chunk(c, a, FH, d_desc + k0, d_kcols + k0, nk, maxkw, d_outp + k0, st);
         if (e) return e;
@@ -1352,8 +1527,9 @@ void fftconv_release(void) {
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
         for (auto& t : c.tw) cudaFree(t.second);
+        for (auto& t : c.ipmap) cudaFree(t.second);
         for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg,
-                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks})
+                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks, &c.bpS})
             if (b->p) cudaFree(b->p);
         if (c.pinned) cudaFreeHost(c.pinned);
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);

@@ -55,7 +55,9 @@ typedef struct fftconv_options {
     int force_generic; /* 1: bypass the fast paths (testing); same as path = 1               */
     int path;        /* 0: automatic; 1: generic line-FFT pipeline; 2: 16-point-tiled SIMT
                         pipeline; 3: overlap-save tiles + per-bin complex GEMM on tcgen05
-                        (falls back to 2 / 1 when the shape is outside that path's range)     */
+                        (falls back to 2 / 1 when the shape is outside that path's range);
+                        4: large-plane pipeline, in-place line transforms (automatic for planes
+                        >= 1024 x 1024 that paths 2 / 3 do not serve, e.g. BASELINE config 3)    */
     int reserved[2];
 } fftconv_options;
 

@@ -201,3 +201,81 @@ def test_large_plane_c3_scaled(fc, oracle):
         ref = sfft.irfft2(sfft.rfft2(data[:, :, 0].astype(np.float64), s=(FH, FH)) *
                           sfft.rfft2(k[:, :, 0].astype(np.float64), s=(FH, FH)), s=(FH, FH))
         assert oracle.rel_l2(o, ref) < TOL
+
+
+# ------------------------------------------------------------------ path 4: large-plane in-place pipeline
+# (kernels_bigplane.cuh).  Forced with Options(path=4) at small sizes so every radix of the in-place plan
+# (odd 3..17, 8 / 16 / 32) runs; sizes whose odd part has a prime factor above 17 must fall back to the generic path.
+@pytest.mark.parametrize("m", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 16, 17, 18, 19, 20, 26, 27, 32, 34, 36, 40, 45, 64, 68])
+def test_bigplane_every_radix(fc, oracle, m):
+    n = 16 * m
+    kh, kw = 5, 7
+    H, W = n - kh + 1, max(1, 48 - kw + 1 - (m % 3))
+    rng = np.random.default_rng(100 + m)
+    data = rng.random((H, W, 1), dtype=np.float32)
+    kernels = [rng.standard_normal((kh, kw, 1)).astype(np.float32), rng.standard_normal((3, 2, 1)).astype(np.float32)]
+    outs = fc.cudaConvolutionFFT(data, kh, kw, kernels, options=fc.Options(path=4))
+    _check(oracle, outs, data, kernels, n, fc.computeFFTsize16(W + kw - 1))
+    # and with the long axis along w (the strided pass)
+    data_t = np.ascontiguousarray(data.transpose(1, 0, 2))
+    kernels_t = [np.ascontiguousarray(k.transpose(1, 0, 2)) for k in kernels]
+    outs_t = fc.cudaConvolutionFFT(data_t, kw, kh, kernels_t, options=fc.Options(path=4))
+    _check(oracle, outs_t, data_t, kernels_t, fc.computeFFTsize16(W + kw - 1), n)
+
+
+@pytest.mark.parametrize("H,W,F,kh,kw", [(200, 120, 3, 40, 33), (130, 250, 2, 70, 9), (90, 90, 5, 90, 90), (64, 300, 4, 1, 1)])
+def test_bigplane_multichannel_unpruned(fc, oracle, H, W, F, kh, kw):
+    """Channel sum in the frequency domain (2 lines + 2 accumulator lines per CTA); templates longer than the
+    first-stage stride take the unpruned forward stage."""
+    rng = np.random.default_rng(H + W + F)
+    data = rng.random((H, W, F), dtype=np.float32)
+    kernels = [rng.standard_normal((kh, kw, F)).astype(np.float32),
+               rng.standard_normal((max(1, kh // 2), max(1, kw - 3), F)).astype(np.float32)]
+    outs = fc.cudaConvolutionFFT(data, kh, kw, kernels, options=fc.Options(path=4))
+    FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+    _check(oracle, outs, data, kernels, FH, FW)
+    outs_g = fc.cudaConvolutionFFT(data, kh, kw, kernels, options=fc.Options(path=1))
+    for a, b in zip(outs, outs_g):
+        assert oracle.rel_l2(a, b) < TOL
+
+
+def test_bigplane_options_match_generic(fc, oracle):
+    """correlate / crop / oversize (circular wrap) behave exactly as on the generic path."""
+    rng = np.random.default_rng(77)
+    data = rng.random((100, 70, 2), dtype=np.float32)
+    ks = [rng.standard_normal((9, 6, 2)).astype(np.float32), rng.standard_normal((30, 20, 2)).astype(np.float32)]
+    for kw_ in (dict(correlate=1), dict(crop_h=60, crop_w=33), dict(crop_h=50, crop_w=40, out_ld=64), dict()):
+        a = fc.cudaConvolutionFFT(data, 9, 6, ks, options=fc.Options(path=4, **kw_))      # 2nd kernel exceeds maxK: wraps
+        b = fc.cudaConvolutionFFT(data, 9, 6, ks, options=fc.Options(path=1, **kw_))
+        for x, y in zip(a, b):
+            assert x.shape == y.shape
+            if "crop_h" in kw_:          # cropped planes are stored packed ([crop_w][out_ld]) at the start of the buffer
+                ch, cw = kw_["crop_h"], kw_["crop_w"]
+                ld = kw_.get("out_ld", ch)
+                x = x.T.reshape(-1)[: cw * ld].reshape(cw, ld)[:, :ch]
+                y = y.T.reshape(-1)[: cw * ld].reshape(cw, ld)[:, :ch]
+            assert oracle.rel_l2(x, y) < TOL
+
+
+def test_bigplane_c3_scaled_auto_and_device_outputs(fc, oracle):
+    """BASELINE config 3 structure at 1/4 scale: plane 1152 = 9 * 128 picks path 4 automatically; checked against
+    the float64 FFT convolution and against the generic path."""
+    import scipy.fft as sfft
+    rng = np.random.default_rng(33)
+    H = W = 1024
+    kh = kw = 128
+    data = rng.random((H, W, 1), dtype=np.float32)
+    ks = [(rng.standard_normal((kh, kw, 1)) / kh).astype(np.float32) for _ in range(3)]
+    ks.append((rng.standard_normal((100, 37, 1)) / 64).astype(np.float32))
+    before = fc.launch_count()
+    outs = fc.cudaConvolutionFFT(data, kh, kw, ks)
+    assert fc.launch_count() > before
+    outs_g = fc.cudaConvolutionFFT(data, kh, kw, ks, options=fc.Options(path=1))
+    FH = fc.computeFFTsize16(H + kh - 1)
+    assert FH == 1152
+    for k, o, g in zip(ks, outs, outs_g):
+        ref = sfft.irfft2(sfft.rfft2(data[:, :, 0].astype(np.float64), s=(FH, FH)) *
+                          sfft.rfft2(k[:, :, 0].astype(np.float64), s=(FH, FH)), s=(FH, FH))
+        assert oracle.rel_l2(o, ref) < TOL
+        assert oracle.rel_l2(o, g) < TOL
+        assert not np.array_equal(o, g)          # really a different pipeline
