@@ -197,23 +197,18 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
+#define BP_OPTIN(NT, TU, MINB) \
+        if (opt_in_smem(bp_conv_w<false, false, NT, TU, MINB>)) return FFTCONV_ERR_CUDA; \
+        if (opt_in_smem(bp_conv_w<true, false, NT, TU, MINB>)) return FFTCONV_ERR_CUDA;
+        BP_OPTIN(256, 2, 2) BP_OPTIN(512, 4, 1) BP_OPTIN(256, 4, 1)
+#undef BP_OPTIN
+        if (opt_in_smem(bp_conv_w<false, true, 512, 2, 1>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, true, 512, 2, 1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_kern_h<1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_inv_h<1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_kern_h<2>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_inv_h<2>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_inv_h<3>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<false, false, 256>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<true, false, 256>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<false, true, 256>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<true, true, 256>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<false, false, 512>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<false, false, 1024>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<true, false, 512>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<true, false, 1024>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<false, true, 512>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<false, true, 1024>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<true, true, 512>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_conv_w<true, true, 1024>)) return FFTCONV_ERR_CUDA;
         c.inited = true;
     }
     *out = &c;
@@ -728,16 +723,19 @@ static bool make_ip_plan(int n, IpPlan& p) {
         const int bits = e / nst + (i < e % nst ? 1 : 0);
         if (!push(1 << bits)) return false;
     }
+    const int m0 = n / p.R[0];
+    p.magic = m0 >= 32 ? (unsigned)((0x100000000ull + m0 - 1) / m0) : 0u;
     return L == 1;
 }
 
-static inline int bp_ldl(int n) { return ((n + n / 16 + 15) / 16) * 16 + 4; }   // == 4 (mod 16): the 4 lines of a tile hit disjoint banks
+static inline int bp_ldl(int n) { return ((n + n / 16 + 40 + 15) / 16) * 16 + 4; }
+static const size_t kBpTwBytes = BP_TW_SMEM_MAX * sizeof(cpx);   // shared twiddle table behind the lines   // == 4 (mod 16): the 4 lines of a tile hit disjoint banks
 
 static bool bigplane_supported(int FH, int FW, int F) {
     IpPlan a, b;
     if (!make_ip_plan(FH, a) || !make_ip_plan(FW, b)) return false;
-    const size_t conv_smem = 4 * (size_t)bp_ldl(FW) * sizeof(cpx);
-    const size_t h_smem = 2 * (size_t)bp_ldl(FH) * sizeof(cpx);
+    const size_t conv_smem = 4 * (size_t)bp_ldl(FW) * sizeof(cpx) + kBpTwBytes;
+    const size_t h_smem = 2 * (size_t)bp_ldl(FH) * sizeof(cpx) + kBpTwBytes;
     (void)F;
     return conv_smem <= kMaxSmem && h_smem <= kMaxSmem;
 }
@@ -792,6 +790,7 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
     const int maxcols4 = (maxcols + 3) & ~3;
     IpPlan pH, pW;
     make_ip_plan(FH, pH); make_ip_plan(FW, pW);
+    pH.tws = os_env_int("FFTCONV_BP_TWS_H", 0); pW.tws = os_env_int("FFTCONV_BP_TWS_W", 1);
     const cpx *twH, *twW;
     const unsigned short *posH, *natH, *posW, *natW;
     if (int e = get_twiddles(c, FH, st, &twH)) return e;
@@ -799,11 +798,11 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
     if (int e = get_ip_tables(c, FH, pH, &posH, &natH)) return e;
     if (int e = get_ip_tables(c, FW, pW, &posW, &natW)) return e;
     const int ldH = bp_ldl(FH), ldW = bp_ldl(FW);
-    const size_t smemH = 2 * (size_t)ldH * sizeof(cpx), smemW = 4 * (size_t)ldW * sizeof(cpx);
+    const size_t smemH = 2 * (size_t)ldH * sizeof(cpx) + kBpTwBytes;
     {
         dim3 grid(maxcols4 / 4, nk * F);
         ProfScope ps(PK_BP_KERN_H, st);
-        if (os_env_int("FFTCONV_BP_HOCC", 1) >= 2)
+        if (os_env_int("FFTCONV_BP_HOCC", 2) >= 2)
             bp_kern_h<2><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
         else
             bp_kern_h<1><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
@@ -811,15 +810,17 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
     }
     {
         const bool multi = F > 1;
-        dim3 grid(nk, CHp / (multi ? 2 : 4));
+        const int tu = multi ? 2 : (os_env_int("FFTCONV_BP_TU", 4) >= 4 ? 4 : 2);
         const int threads = os_env_int("FFTCONV_BP_THREADS", 512);
+        dim3 grid(tu == 4 ? nk : 2 * nk, CHp / 4);
+        const size_t smem = (multi ? 4 : tu) * (size_t)ldW * sizeof(cpx) + kBpTwBytes;
         ProfScope ps(PK_BP_CONV_W, st);
         const cpx* T = (const cpx*)c.T.p; const cpx* Sp = (const cpx*)c.bpS.p; cpx* Z = (cpx*)c.Z.p;
-#define BP_LAUNCH(CONJ, MULTI, NT) bp_conv_w<CONJ, MULTI, NT><<<grid, NT, smemW, st>>>(T, d_kcols, maxcols4, Sp, F, FW, CHp, pW, twW, Z, ldW)
-#define BP_PICK(NT) do { if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, NT); else BP_LAUNCH(false, true, NT); } \
-                         else { if (a.opt.correlate) BP_LAUNCH(true, false, NT); else BP_LAUNCH(false, false, NT); } } while (0)
-        if (threads >= 1024) BP_PICK(1024); else if (threads >= 512) BP_PICK(512); else BP_PICK(256);
-#undef BP_PICK
+#define BP_LAUNCH(CONJ, MULTI, NT, TU, MINB) bp_conv_w<CONJ, MULTI, NT, TU, MINB><<<grid, NT, smem, st>>>(T, d_kcols, maxcols4, Sp, F, FW, CHp, pW, twW, Z, ldW)
+        if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, 512, 2, 1); else BP_LAUNCH(false, true, 512, 2, 1); }
+        else if (tu == 2) { if (a.opt.correlate) BP_LAUNCH(true, false, 256, 2, 2); else BP_LAUNCH(false, false, 256, 2, 2); }
+        else if (threads >= 512) { if (a.opt.correlate) BP_LAUNCH(true, false, 512, 4, 1); else BP_LAUNCH(false, false, 512, 4, 1); }
+        else { if (a.opt.correlate) BP_LAUNCH(true, false, 256, 4, 1); else BP_LAUNCH(false, false, 256, 4, 1); }
 #undef BP_LAUNCH
         LAUNCH_CHECK();
     }
@@ -829,9 +830,9 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
         const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
         dim3 grid(FW / 4, nk);
         ProfScope ps(PK_BP_INV_H, st);
-        if (os_env_int("FFTCONV_BP_HOCC", 1) >= 3)
+        if (os_env_int("FFTCONV_BP_HOCC", 2) >= 3)
             bp_inv_h<3><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
-        else if (os_env_int("FFTCONV_BP_HOCC", 1) >= 2)
+        else if (os_env_int("FFTCONV_BP_HOCC", 2) >= 2)
             bp_inv_h<2><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
         else
             bp_inv_h<1><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);

@@ -31,10 +31,14 @@ struct IpPlan {
     int n, ns;
     int R[BP_MAX_STAGES];    // radix of stage s
     int L[BP_MAX_STAGES];    // sub-transform length entering stage s (L[0] = n, L[s+1] = L[s] / R[s])
+    unsigned magic;          // ceil(2^32 / m0), m0 = n / R[0]  (0: no third pad term)
+    int tws;                 // 1: later stages read their twiddles from the shared-memory table
 };
 
-// one pad slot per 16 points keeps the short-stride stages (stride 1, 2, ... points between lanes) off a single bank
-__device__ __forceinline__ int bp_pidx(int i) { return i + (i >> 4); }
+// Padded position of point i of a line.  One pad slot per 16 points keeps the short-stride stages off a single bank;
+// one more per m0 = n/R[0] points does the same for the stride of the first stage, which is also the stride between
+// CONSECUTIVE natural indices after digit reversal (the scatter of bp_inv_h, the gather of bp_kern_h).
+__device__ __forceinline__ int bp_pidx(int i, unsigned magic) { return i + (i >> 4) + (int)__umulhi((unsigned)i, magic); }
 
 // ------------------------------------------------------------------------------- radix 32
 template <> struct Dft<32> {
@@ -65,104 +69,161 @@ template <> struct Dft<32> {
     }
 };
 
+// ------------------------------------------------------------------------------- stage twiddles
+// Stage 0 reads the global table tw[t] = w_n^t (t = j*q, coalesced enough, L1-resident).  Every later stage has a
+// sub-length L_s dividing L1 = n / R[0], so all of them share ONE small table  w_L1^t, t < L1  (4 KB at n = 4608) kept in
+// shared memory: those stages gather twiddles with large strides, which from global memory cost one L1 line per lane
+// and were the main long-scoreboard stall of the first version.
+struct TwSrc {
+    const cpx* g;        // global table w_n^t
+    unsigned sh;         // shared-memory byte address of the w_L1^t table (0: none)
+    int gstep;           // index scale for the global table
+    int sstep;           // index scale for the shared table
+};
+__device__ __forceinline__ cpx tw_fetch(const TwSrc& t, int jq) {
+    if (t.sh) {
+        cpx v;
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(t.sh + (unsigned)(jq * t.sstep) * 8u));
+        return v;
+    }
+    return __ldg(&t.g[jq * t.gstep]);
+}
+#define BP_TW_SMEM_MAX 1024
+// w_L1^t = w_n^(t * R0) for t < L1, filled by the whole CTA (followed by the caller's __syncthreads)
+__device__ __forceinline__ void bp_fill_tw(cpx* tab, const IpPlan& P, const cpx* __restrict__ tw) {
+    if (P.ns < 2 || P.L[1] > BP_TW_SMEM_MAX || P.tws == 0) return;
+    for (int t = threadIdx.x; t < P.L[1]; t += blockDim.x) tab[t] = __ldg(&tw[t * P.R[0]]);
+}
+__device__ __forceinline__ unsigned bp_tw_addr(const cpx* tab, const IpPlan& P) {
+    return (P.ns < 2 || P.L[1] > BP_TW_SMEM_MAX || P.tws == 0) ? 0u : (unsigned)__cvta_generic_to_shared(tab);
+}
+
 // ------------------------------------------------------------------------------- in-place stages
 // One work item = one radix-R butterfly of one line.  DIF (forward): DFT_R over the R samples  base + r*m, then the
 // output q is rotated by w_L^(j q).  DIT (inverse): the exact inverse — rotate input q by conj(w_L^(j q)), then the
-// inverse DFT_R.  Twiddles for R >= 16 come from a two-level split q = 4a + b (R/4 + 2 table reads instead of R - 1).
-template <int R, bool INV>
-__device__ __forceinline__ void ip_stage(cpx* __restrict__ lines, int nl, int ldl, int n, int L,
-                                         const cpx* __restrict__ tw) {
-    const int m = L / R, nb = n / R, step = n / L;
-    const int items = nb * nl;
+// inverse DFT_R.  Twiddles for R = 16 / 32 come from a two-level split q = 4a + b (R/4 + 2 table reads instead of R - 1).
+// LIN: the padded positions of the R samples are  A + r*S (+ r>>4 for a 32-point last stage): m is a multiple of 16,
+// or 1 — true for every stage of every plan except strides 2, 4, 8.
+template <int R, bool INV, bool LIN>
+__device__ __forceinline__ void ip_bfly(cpx* __restrict__ ln, int base, int m, int js, bool rot, bool first,
+                                        unsigned magic, const TwSrc& tw) {
     constexpr int G = (R >= 16 && R % 4 == 0) ? 4 : 1;
+    cpx w1[G], wg[R / G];
+    if (rot) {
+#pragma unroll
+        for (int q = 1; q < G; ++q) w1[q] = twd<INV>(tw_fetch(tw, js * q));
+#pragma unroll
+        for (int a = 1; a < R / G; ++a) wg[a] = twd<INV>(tw_fetch(tw, js * G * a));
+    }
+    const int A = bp_pidx(base, magic);
+    const int S = m == 1 ? 1 : m + (m >> 4) + ((first && magic) ? 1 : 0);
+    float re[R], im[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int o = LIN ? A + r * S + ((R == 32) ? ((m == 1) ? (r >> 4) : 0) : 0) : bp_pidx(base + r * m, magic);
+        cpx v = ln[o];
+        if (INV && rot && r > 0) {
+            const int a = r / G, q = r % G;
+            v = (G == 1 || q == 0) ? cmul(v, wg[a]) : (a == 0 ? cmul(v, w1[q]) : cmul(v, cmul(wg[a], w1[q])));
+        }
+        re[r] = v.x; im[r] = v.y;
+    }
+    dft_regs<R, INV>(re, im);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int o = LIN ? A + r * S + ((R == 32) ? ((m == 1) ? (r >> 4) : 0) : 0) : bp_pidx(base + r * m, magic);
+        cpx v = make_float2(re[r], im[r]);
+        if (!INV && rot && r > 0) {
+            const int a = r / G, q = r % G;
+            v = (G == 1 || q == 0) ? cmul(v, wg[a]) : (a == 0 ? cmul(v, w1[q]) : cmul(v, cmul(wg[a], w1[q])));
+        }
+        ln[o] = v;
+    }
+}
+
+// __noinline__: every radix gets its own register allocation (a 32-point butterfly needs ~100 registers, a 9-point one
+// 40); inlined into one kernel body the allocator spilled kilobytes per thread.
+template <int R, bool INV>
+__device__ __noinline__ void ip_stage(cpx* __restrict__ lines, int nl, int ldl, int n, int L, unsigned magic,
+                                      const cpx* __restrict__ twg, unsigned twsh, int L1) {
+    const int m = L / R, nb = n / R;
+    TwSrc tw;
+    tw.g = twg; tw.gstep = n / L;
+    tw.sh = L == n ? 0u : twsh;                       // stage 0 walks the global table
+    tw.sstep = L == n ? 0 : L1 / L;
+    const int items = nb * nl;
+    const bool lin = (m & 15) == 0 || m == 1;
+    const bool rot = m > 1;                           // last stage: j = 0, every rotation is 1
+    const bool first = L == n;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
         const int l = it / nb, b = it - l * nb;
         const int blk = b / m, j = b - blk * m;
-        cpx* ln = lines + (size_t)l * ldl;
+        cpx* ln = lines + l * ldl;
         const int base = blk * L + j;
-        cpx w1[G], wg[R / G];
-        const bool rot = m > 1;                       // last stage: j = 0, every rotation is 1
-        if (rot) {
-            const int js = j * step;
-#pragma unroll
-            for (int q = 1; q < G; ++q) w1[q] = twd<INV>(__ldg(&tw[js * q]));
-#pragma unroll
-            for (int a = 1; a < R / G; ++a) wg[a] = twd<INV>(__ldg(&tw[js * G * a]));
-        }
-        float re[R], im[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            cpx v = ln[bp_pidx(base + r * m)];
-            if (INV && rot && r > 0) {
-                const int a = r / G, q = r % G;
-                v = (G == 1 || q == 0) ? cmul(v, wg[a]) : (a == 0 ? cmul(v, w1[q]) : cmul(v, cmul(wg[a], w1[q])));
-            }
-            re[r] = v.x; im[r] = v.y;
-        }
-        dft_regs<R, INV>(re, im);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            cpx v = make_float2(re[r], im[r]);
-            if (!INV && rot && r > 0) {
-                const int a = r / G, q = r % G;
-                v = (G == 1 || q == 0) ? cmul(v, wg[a]) : (a == 0 ? cmul(v, w1[q]) : cmul(v, cmul(wg[a], w1[q])));
-            }
-            ln[bp_pidx(base + r * m)] = v;
-        }
+        // (a 32-point stage is always followed by 16- or 32-point stages: its stride is a multiple of 16, or 1)
+        if (lin || R == 32) ip_bfly<R, INV, true>(ln, base, m, j, rot, first, magic, tw);
+        else ip_bfly<R, INV, false>(ln, base, m, j, rot, first, magic, tw);
     }
 }
 
 template <bool INV>
-__device__ __forceinline__ void ip_run_stage(int R, cpx* lines, int nl, int ldl, int n, int L, const cpx* __restrict__ tw) {
+__device__ __forceinline__ void ip_run_stage(int R, cpx* lines, int nl, int ldl, int n, int L, unsigned magic,
+                                             const cpx* __restrict__ tw, unsigned twsh, int L1) {
     switch (R) {
-        case 2:  ip_stage<2, INV>(lines, nl, ldl, n, L, tw); break;
-        case 3:  ip_stage<3, INV>(lines, nl, ldl, n, L, tw); break;
-        case 4:  ip_stage<4, INV>(lines, nl, ldl, n, L, tw); break;
-        case 5:  ip_stage<5, INV>(lines, nl, ldl, n, L, tw); break;
-        case 7:  ip_stage<7, INV>(lines, nl, ldl, n, L, tw); break;
-        case 8:  ip_stage<8, INV>(lines, nl, ldl, n, L, tw); break;
-        case 9:  ip_stage<9, INV>(lines, nl, ldl, n, L, tw); break;
-        case 11: ip_stage<11, INV>(lines, nl, ldl, n, L, tw); break;
-        case 13: ip_stage<13, INV>(lines, nl, ldl, n, L, tw); break;
-        case 16: ip_stage<16, INV>(lines, nl, ldl, n, L, tw); break;
-        case 17: ip_stage<17, INV>(lines, nl, ldl, n, L, tw); break;
-        default: ip_stage<32, INV>(lines, nl, ldl, n, L, tw); break;
+        case 2:  ip_stage<2, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 3:  ip_stage<3, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 4:  ip_stage<4, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 5:  ip_stage<5, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 7:  ip_stage<7, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 8:  ip_stage<8, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 9:  ip_stage<9, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 11: ip_stage<11, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 13: ip_stage<13, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 16: ip_stage<16, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        case 17: ip_stage<17, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
+        default: ip_stage<32, INV>(lines, nl, ldl, n, L, magic, tw, twsh, L1); break;
     }
 }
 
 // forward first stage when only the first nz <= n/R samples of a line are non-zero (a zero-padded template):
 // the DFT_R collapses to a broadcast,  Y_q[j] = x[j] * w_n^(j q).
-__device__ __forceinline__ void ip_stage_pruned_fwd(cpx* __restrict__ lines, int nl, int ldl, int n, int R,
+__device__ __noinline__ void ip_stage_pruned_fwd(cpx* __restrict__ lines, int nl, int ldl, int n, int R, unsigned magic,
                                                     const cpx* __restrict__ tw) {
     const int m = n / R;
-    const int items = m * nl;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        const int l = it / m, j = it - l * m;
-        cpx* ln = lines + (size_t)l * ldl;
-        const cpx x = ln[bp_pidx(j)];
-        for (int q = 1; q < R; ++q) ln[bp_pidx(j + q * m)] = cmul(x, __ldg(&tw[j * q]));
+    const int S = m + (m >> 4) + (magic ? 1 : 0);     // m is a multiple of 16 (the last radix alone is >= 4 ... see make_ip_plan)
+    const bool lin = (m & 15) == 0;
+    for (int l = 0; l < nl; ++l) {
+        cpx* ln = lines + l * ldl;
+        for (int j = threadIdx.x; j < m; j += blockDim.x) {
+            const int A = bp_pidx(j, magic);
+            const cpx x = ln[A];
+            for (int q = 1; q < R; ++q)
+                ln[lin ? A + q * S : bp_pidx(j + q * m, magic)] = cmul(x, __ldg(&tw[j * q]));
+        }
     }
 }
 
 // natural order in (first nz samples non-zero, the caller zero-filled up to bp_fill_to) -> digit-reversed out
-__device__ __forceinline__ void ip_forward(cpx* lines, int nl, int ldl, const IpPlan& P, const cpx* __restrict__ tw, int nz) {
+__device__ __forceinline__ void ip_forward(cpx* lines, int nl, int ldl, const IpPlan& P, const cpx* __restrict__ tw,
+                                           unsigned twsh, int nz) {
     int s = 0;
     if (nz <= P.L[0] / P.R[0]) {
-        ip_stage_pruned_fwd(lines, nl, ldl, P.n, P.R[0], tw);
+        ip_stage_pruned_fwd(lines, nl, ldl, P.n, P.R[0], P.magic, tw);
         __syncthreads();
         s = 1;
     }
     for (; s < P.ns; ++s) {
-        ip_run_stage<false>(P.R[s], lines, nl, ldl, P.n, P.L[s], tw);
+        ip_run_stage<false>(P.R[s], lines, nl, ldl, P.n, P.L[s], P.magic, tw, twsh, P.L[1]);
         __syncthreads();
     }
 }
 __device__ __forceinline__ int bp_fill_to(const IpPlan& P, int nz) { return nz <= P.L[0] / P.R[0] ? P.L[0] / P.R[0] : P.n; }
 
 // digit-reversed in -> natural order out (unnormalised)
-__device__ __forceinline__ void ip_inverse(cpx* lines, int nl, int ldl, const IpPlan& P, const cpx* __restrict__ tw) {
+__device__ __forceinline__ void ip_inverse(cpx* lines, int nl, int ldl, const IpPlan& P, const cpx* __restrict__ tw,
+                                           unsigned twsh) {
     for (int s = P.ns - 1; s >= 0; --s) {
-        ip_run_stage<true>(P.R[s], lines, nl, ldl, P.n, P.L[s], tw);
+        ip_run_stage<true>(P.R[s], lines, nl, ldl, P.n, P.L[s], P.magic, tw, twsh, P.L[1]);
         __syncthreads();
     }
 }
@@ -188,11 +249,15 @@ __global__ void bp_repad_spec(const cpx* __restrict__ S, int CH, int CHp, int FW
 // T: [nk * F][maxcols4][CHp]
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) bp_kern_h(const SrcDesc* __restrict__ srcs, int F, int maxcols4, int FH, int CH, int CHp,
-                                                 const __grid_constant__ IpPlan plan, const cpx* __restrict__ tw,
-                                                 const unsigned short* __restrict__ pos_of, cpx* __restrict__ T, int ldl)
+                                                       const __grid_constant__ IpPlan plan, const cpx* __restrict__ tw,
+                                                       const unsigned short* __restrict__ pos_of, cpx* __restrict__ T, int ldl)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* lines = reinterpret_cast<cpx*>(smem_raw);
+    const unsigned magic = plan.magic;
+    cpx* twtab = lines + 2 * ldl;
+    bp_fill_tw(twtab, plan, tw);
+    const unsigned twsh = bp_tw_addr(twtab, plan);
     const int pf = blockIdx.y, s = pf / F, f = pf - s * F;
     const SrcDesc d = srcs[s];
     const int x0 = blockIdx.x * 4;
@@ -200,157 +265,176 @@ __global__ void __launch_bounds__(256, MINB) bp_kern_h(const SrcDesc* __restrict
     const int rows = min(d.rows, FH);
     const float* base = d.ptr + (size_t)f * d.rows * d.cols;
     const int fill = bp_fill_to(plan, rows);
-    for (int idx = threadIdx.x; idx < 2 * fill; idx += blockDim.x) {
-        const int l = idx / fill, y = idx - l * fill;
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
         const int xa = x0 + 2 * l, xb = xa + 1;
-        cpx v = make_float2(0.f, 0.f);
-        if (y < rows) {
-            if (xa < d.cols) v.x = base[(size_t)xa * d.rows + y];
-            if (xb < d.cols) v.y = base[(size_t)xb * d.rows + y];
+        const float* ca = base + (size_t)xa * d.rows;
+        const float* cb = base + (size_t)xb * d.rows;
+        for (int y = threadIdx.x; y < fill; y += 256) {
+            cpx v = make_float2(0.f, 0.f);
+            if (y < rows) {
+                if (xa < d.cols) v.x = ca[y];
+                if (xb < d.cols) v.y = cb[y];
+            }
+            lines[l * ldl + bp_pidx(y, magic)] = v;
         }
-        lines[(size_t)l * ldl + bp_pidx(y)] = v;
     }
     __syncthreads();
-    ip_forward(lines, 2, ldl, plan, tw, rows);
-    for (int idx = threadIdx.x; idx < 2 * CHp; idx += blockDim.x) {
-        const int l = idx / CHp, u = idx - l * CHp;
-        cpx a = make_float2(0.f, 0.f), b = a;
-        if (u < CH) {
-            const cpx* ln = lines + (size_t)l * ldl;
-            const cpx zu = ln[bp_pidx(pos_of[u])];
-            const cpx zn = cconj(ln[bp_pidx(pos_of[u == 0 ? 0 : FH - u])]);
-            a = make_float2(0.5f * (zu.x + zn.x), 0.5f * (zu.y + zn.y));
-            const cpx dd = make_float2(0.5f * (zu.x - zn.x), 0.5f * (zu.y - zn.y));
-            b = make_float2(dd.y, -dd.x);                                   // -i * dd
+    ip_forward(lines, 2, ldl, plan, tw, twsh, rows);
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const cpx* ln = lines + l * ldl;
+        cpx* o = T + ((size_t)pf * maxcols4 + x0 + 2 * l) * CHp;
+        for (int u = threadIdx.x; u < CHp; u += 256) {
+            cpx a = make_float2(0.f, 0.f), b = a;
+            if (u < CH) {
+                const cpx zu = ln[bp_pidx(pos_of[u], magic)];
+                const cpx zn = cconj(ln[bp_pidx(pos_of[u == 0 ? 0 : FH - u], magic)]);
+                a = make_float2(0.5f * (zu.x + zn.x), 0.5f * (zu.y + zn.y));
+                const cpx dd = make_float2(0.5f * (zu.x - zn.x), 0.5f * (zu.y - zn.y));
+                b = make_float2(dd.y, -dd.x);                                   // -i * dd
+            }
+            o[u] = a;
+            o[CHp + u] = b;
         }
-        cpx* o = T + ((size_t)pf * maxcols4 + x0 + 2 * l) * CHp + u;
-        o[0] = a;
-        o[CHp] = b;
     }
 }
 
 // ------------------------------------------------------------------------------- bp_conv_w
-// grid (nk, CHp / TU) x 512, template index fastest: the CTAs resident at any moment share a handful of h-bin tiles,
-// so the data spectrum is read from HBM once per call, not once per template.
-// TU = 4 lines (single channel, product in place) or 2 lines + 2 accumulator lines (MULTI: channel sum).
-template <bool CONJ, bool MULTI, int NT>
-__global__ void __launch_bounds__(NT, 1) bp_conv_w(const cpx* __restrict__ T, const int* __restrict__ kcols, int maxcols4,
+// Template index fastest in the grid: the CTAs resident at any moment share a handful of h-bin tiles, so the data
+// spectrum is read from HBM once per call, not once per template.
+// TU = 4: grid (nk, CHp / 4), one CTA per SM owns whole 32-byte sectors (4 h-bins of every column).
+// TU = 2: grid (2 nk, CHp / 4), TWO CTAs per SM (single channel) — the two halves of a sector belong to CTAs that are
+//         neighbours in launch order, so they meet in L2; the load / transform / product / store phases of the two
+//         CTAs overlap.  MULTI adds TU accumulator lines (channel sum in the frequency domain).
+template <bool CONJ, bool MULTI, int NT, int TU, int MINB>
+__global__ void __launch_bounds__(NT, MINB) bp_conv_w(const cpx* __restrict__ T, const int* __restrict__ kcols, int maxcols4,
                                                     const cpx* __restrict__ Sp, int F, int FW, int CHp,
                                                     const __grid_constant__ IpPlan plan, const cpx* __restrict__ tw,
                                                     cpx* __restrict__ Z, int ldl)
 {
-    constexpr int TU = MULTI ? 2 : 4;
+    constexpr int PS = NT / TU;                           // points advanced per pass of the CTA
+    constexpr int MB = 6;                                 // global loads in flight per thread
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* lines = reinterpret_cast<cpx*>(smem_raw);
-    cpx* acc = lines + (size_t)TU * ldl;                  // MULTI only
-    const int k = blockIdx.x, u0 = blockIdx.y * TU;
+    const unsigned magic = plan.magic;
+    cpx* twtab = lines + (MULTI ? 2 * TU : TU) * ldl;
+    bp_fill_tw(twtab, plan, tw);
+    const unsigned twsh = bp_tw_addr(twtab, plan);
+    const int k = TU == 4 ? blockIdx.x : blockIdx.x >> 1;
+    const int u0 = TU == 4 ? blockIdx.y * 4 : blockIdx.y * 4 + (blockIdx.x & 1) * 2;
     const int ncols = min(kcols[k], FW);
     const int fill = bp_fill_to(plan, ncols);
+    const int l = threadIdx.x % TU, p0 = threadIdx.x / TU;
+    cpx* ln = lines + l * ldl;
+    cpx* an = ln + TU * ldl;                              // MULTI only: accumulator line
 
-    constexpr int MB = 6;                                   // global loads in flight per thread
     for (int f = 0; f < F; ++f) {
-        const cpx* Tp = T + ((size_t)(k * F + f) * maxcols4) * CHp + u0;
-        for (int i0 = threadIdx.x; i0 < fill * TU; i0 += NT * MB) {
-            cpx v[MB];
+        const cpx* Tp = T + ((size_t)(k * F + f) * maxcols4) * CHp + u0 + l;
+        for (int xb = p0; xb < fill; xb += PS * 4) {        // 4 loads in flight (unconditional, clamped: they stay in registers)
+            cpx v[4];
 #pragma unroll
-            for (int b = 0; b < MB; ++b) {
-                const int idx = i0 + b * NT, x = idx / TU, l = idx - x * TU;
-                v[b] = make_float2(0.f, 0.f);
-                if (x < ncols) v[b] = Tp[(size_t)x * CHp + l];
-            }
+            for (int b = 0; b < 4; ++b) v[b] = __ldcs(&Tp[(size_t)min(xb + b * PS, ncols - 1) * CHp]);
 #pragma unroll
-            for (int b = 0; b < MB; ++b) {
-                const int idx = i0 + b * NT, x = idx / TU, l = idx - x * TU;
-                if (idx < fill * TU) lines[(size_t)l * ldl + bp_pidx(x)] = v[b];
+            for (int b = 0; b < 4; ++b) {
+                const int x = xb + b * PS;
+                if (x < fill) ln[bp_pidx(x, magic)] = x < ncols ? v[b] : make_float2(0.f, 0.f);
             }
         }
         __syncthreads();
-        ip_forward(lines, TU, ldl, plan, tw, ncols);
-        const cpx* Sf = Sp + (size_t)f * FW * CHp + u0;     // rows already in digit-reversed order
-        for (int i0 = threadIdx.x; i0 < FW * TU; i0 += NT * MB) {
+        ip_forward(lines, TU, ldl, plan, tw, twsh, ncols);
+        const cpx* Sf = Sp + (size_t)f * FW * CHp + u0 + l;     // rows already in digit-reversed order
+        for (int pb = p0; pb < FW; pb += PS * MB) {
             cpx dsp[MB];
 #pragma unroll
             for (int b = 0; b < MB; ++b) {
-                const int idx = i0 + b * NT, p = idx / TU, l = idx - p * TU;
-                if (idx < FW * TU) dsp[b] = __ldg(&Sf[(size_t)p * CHp + l]);
+                dsp[b] = __ldcs(&Sf[(size_t)min(pb + b * PS, FW - 1) * CHp]);
             }
 #pragma unroll
             for (int b = 0; b < MB; ++b) {
-                const int idx = i0 + b * NT, p = idx / TU, l = idx - p * TU;
-                if (idx < FW * TU) {
-                    const size_t o = (size_t)l * ldl + bp_pidx(p);
-                    const cpx kx = lines[o];
+                const int p = pb + b * PS;
+                if (p < FW) {
+                    const int o = bp_pidx(p, magic);
+                    const cpx kx = ln[o];
                     cpx pr = CONJ ? cmulc(dsp[b], kx) : cmul(dsp[b], kx);
                     if (MULTI) {
-                        if (f > 0) { const cpx a = acc[o]; pr.x += a.x; pr.y += a.y; }
-                        acc[o] = pr;
+                        if (f > 0) { const cpx a = an[o]; pr.x += a.x; pr.y += a.y; }
+                        an[o] = pr;
                     } else {
-                        lines[o] = pr;
+                        ln[o] = pr;
                     }
                 }
             }
         }
         __syncthreads();
     }
-    cpx* res = MULTI ? acc : lines;
-    ip_inverse(res, TU, ldl, plan, tw);
-    cpx* Zk = Z + (size_t)k * FW * CHp + u0;
-    for (int idx = threadIdx.x; idx < FW * TU; idx += blockDim.x) {
-        const int x = idx / TU, l = idx - x * TU;
-        Zk[(size_t)x * CHp + l] = res[(size_t)l * ldl + bp_pidx(x)];
-    }
+    ip_inverse(MULTI ? lines + TU * ldl : lines, TU, ldl, plan, tw, twsh);
+    const cpx* rn = MULTI ? an : ln;
+    cpx* Zk = Z + (size_t)k * FW * CHp + u0 + l;
+    for (int x = p0; x < FW; x += PS) __stcs(&Zk[(size_t)x * CHp], rn[bp_pidx(x, magic)]);
 }
 
 // ------------------------------------------------------------------------------- bp_inv_h
 // grid (FW / 4, nk) x 256; Z [k][FW][CHp] (already scaled) -> 4 real columns of plane k
 template <int MINB>
 __global__ void __launch_bounds__(256, MINB) bp_inv_h(const cpx* __restrict__ Z, int FH, int FW, int CH, int CHp,
-                                                const __grid_constant__ IpPlan plan, const cpx* __restrict__ tw,
-                                                const unsigned short* __restrict__ pos_of,
-                                                float* const* __restrict__ outs, int crop_h, int crop_w, int out_ld, int ldl)
+                                                      const __grid_constant__ IpPlan plan, const cpx* __restrict__ tw,
+                                                      const unsigned short* __restrict__ pos_of,
+                                                      float* const* __restrict__ outs, int crop_h, int crop_w, int out_ld, int ldl)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cpx* lines = reinterpret_cast<cpx*>(smem_raw);
+    const unsigned magic = plan.magic;
     const int k = blockIdx.y, x0 = blockIdx.x * 4;
     if (x0 >= crop_w) return;
+    cpx* twtab = lines + 2 * ldl;
+    bp_fill_tw(twtab, plan, tw);
+    const unsigned twsh = bp_tw_addr(twtab, plan);
     const cpx* Zk = Z + ((size_t)k * FW + x0) * CHp;
     const int half = FH / 2;
     constexpr int MB = 5;                                   // 2 * MB global loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < 2 * CH; i0 += 256 * MB) {
-        cpx za[MB], zb[MB];
 #pragma unroll
-        for (int b = 0; b < MB; ++b) {
-            const int idx = i0 + b * 256;
-            if (idx < 2 * CH) {
-                const int l = idx / CH, u = idx - l * CH;
-                za[b] = Zk[(size_t)(2 * l) * CHp + u];
-                zb[b] = Zk[(size_t)(2 * l + 1) * CHp + u];
+    for (int l = 0; l < 2; ++l) {
+        cpx* ln = lines + l * ldl;
+        const cpx* Za = Zk + (size_t)(2 * l) * CHp;
+        const cpx* Zb = Za + CHp;
+        for (int ub = threadIdx.x; ub < CH; ub += 256 * MB) {
+            cpx za[MB], zb[MB];
+            int pa[MB], pb[MB];
+#pragma unroll
+            for (int b = 0; b < MB; ++b) {
+                const int u = ub + b * 256;
+                const int uc = min(u, CH - 1);
+                za[b] = Za[uc]; zb[b] = Zb[uc]; pa[b] = pos_of[uc]; pb[b] = pos_of[uc == 0 ? 0 : FH - uc];
             }
-        }
 #pragma unroll
-        for (int b = 0; b < MB; ++b) {
-            const int idx = i0 + b * 256;
-            if (idx < 2 * CH) {
-                const int l = idx / CH, u = idx - l * CH;
-                cpx* ln = lines + (size_t)l * ldl;
-                if (u == 0 || u == half) {                          // C2R ignores Im of DC / Nyquist
-                    ln[bp_pidx(pos_of[u])] = make_float2(za[b].x, zb[b].x);
-                } else {
-                    ln[bp_pidx(pos_of[u])] = make_float2(za[b].x - zb[b].y, za[b].y + zb[b].x);           // za + i zb
-                    ln[bp_pidx(pos_of[FH - u])] = make_float2(za[b].x + zb[b].y, zb[b].x - za[b].y);      // conj(za) + i conj(zb)
+            for (int b = 0; b < MB; ++b) {
+                const int u = ub + b * 256;
+                if (u < CH) {
+                    if (u == 0 || u == half) {                          // C2R ignores Im of DC / Nyquist
+                        ln[bp_pidx(pa[b], magic)] = make_float2(za[b].x, zb[b].x);
+                    } else {
+                        ln[bp_pidx(pa[b], magic)] = make_float2(za[b].x - zb[b].y, za[b].y + zb[b].x);     // za + i zb
+                        ln[bp_pidx(pb[b], magic)] = make_float2(za[b].x + zb[b].y, zb[b].x - za[b].y);     // conj(za) + i conj(zb)
+                    }
                 }
             }
         }
     }
     __syncthreads();
-    ip_inverse(lines, 2, ldl, plan, tw);
+    ip_inverse(lines, 2, ldl, plan, tw, twsh);
     float* o = outs[k];
-    for (int idx = threadIdx.x; idx < 2 * crop_h; idx += blockDim.x) {
-        const int l = idx / crop_h, y = idx - l * crop_h;
-        const cpx r = lines[(size_t)l * ldl + bp_pidx(y)];
+#pragma unroll
+    for (int l = 0; l < 2; ++l) {
+        const cpx* ln = lines + l * ldl;
         const int xa = x0 + 2 * l, xb = xa + 1;
-        if (xa < crop_w) o[(size_t)xa * out_ld + y] = r.x;
-        if (xb < crop_w) o[(size_t)xb * out_ld + y] = r.y;
+        float* oa = o + (size_t)xa * out_ld;
+        float* ob = o + (size_t)xb * out_ld;
+        for (int y = threadIdx.x; y < crop_h; y += 256) {
+            const cpx r = ln[bp_pidx(y, magic)];
+            if (xa < crop_w) oa[y] = r.x;
+            if (xb < crop_w) ob[y] = r.y;
+        }
     }
 }
 

@@ -16,8 +16,8 @@ out = torch.empty((K, FW, FH), device="cuda")
 ref = torch.fft.irfft2(torch.fft.rfft2(data.double(), s=(FW, FH)) * torch.fft.rfft2(bank[:1].double(), s=(FW, FH)), s=(FW, FH)).sum(1)
 variants = []
 for spec_ in (sys.argv[2:] or ["512,32,2"]):
-    t, r, h = spec_.split(",")
-    variants.append(dict(FFTCONV_BP_THREADS=t, FFTCONV_BP_MAXR=r, FFTCONV_BP_HOCC=h))
+    t, r, h, tu, twh, tww = (spec_.split(",") + ["4", "0", "1"])[:6]
+    variants.append(dict(FFTCONV_BP_THREADS=t, FFTCONV_BP_MAXR=r, FFTCONV_BP_HOCC=h, FFTCONV_BP_TU=tu, FFTCONV_BP_TWS_H=twh, FFTCONV_BP_TWS_W=tww))
 for v in variants:
     os.environ.update(v)
     fc.lib().fftconv_release()
