@@ -179,7 +179,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import fftconv_b200 as fc
-    from fftconv_b200.sharding import broadcast_spectrum
+    from fftconv_b200.sharding import broadcast_spectrum, broadcast_spectrum_async, bind_host_to_gpu
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,9 +189,15 @@ def run_ours(args):
         import torch.distributed as dist_mod
         dist = dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        opts = None
+        try:                                         # the broadcast must not queue behind the template transforms
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            pass
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"), pg_options=opts)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
+    numa_cpus = bind_host_to_gpu(local) if world > 1 else None     # before any pinned allocation
     H, W, F, kh, kw, K, desc = WORKLOADS[args.workload]
     FH, FW = fft16(H + kh - 1), fft16(W + kw - 1)
     CH = FH // 2 + 1
@@ -211,6 +217,13 @@ def run_ours(args):
         """data FFT (rank 0) -> [NCCL broadcast of the spectrum] -> bank convolution on every rank"""
         if rank == 0:
             fc.fft_data_device(data, H, W, F, kh, kw, spec_t=spec)
+        if os.environ.get("FFTCONV_BENCH_BCAST", "sync") == "async":
+            # A/B switch: NCCL broadcast on a side stream, only the data-side transforms wait for it
+            # (fftconv_spectrum_ready_event).  Measured SLOWER on 2 x B200 (1.22 vs 1.12 ms per step, profiles/
+            # r01e_n2_bcast_ab.txt): the NCCL kernel and the template transforms fight for SMs; kept off.
+            ready = broadcast_spectrum_async(spec, 0)
+            fc.conv_bank(spec, bank, kh, kw, out, spectrum_ready=ready)
+            return
         broadcast_spectrum(spec, 0)
         fc.conv_bank(spec, bank, kh, kw, out)
 
@@ -400,6 +413,7 @@ def run_ours(args):
                              f"{4 * K * FH * FW / 1e6:.0f} MB of outputs (> 126 MB L2)",
                        "parallelism": f"template bank sharded over {world} GPU(s), data spectrum "
                                       + ("broadcast by NCCL inside the step" if world > 1 else "local"),
+                       "host_affinity": (f"{len(numa_cpus)} cores local to the GPU (NVML)" if numa_cpus else "unchanged"),
                        "timing": "CUDA events per step on the launch stream, max over ranks",
                        "rel_l2_vs_fp64": rel_l2},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

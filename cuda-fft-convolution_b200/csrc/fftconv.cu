@@ -123,6 +123,7 @@ struct Ctx {
     cudaStream_t side2 = nullptr;        // data-side transforms of the overlap-save path run here, next to os_kern_fft
     cudaEvent_t evf[2] = {nullptr, nullptr};
     int sm_count = 148;
+    cudaEvent_t spec_ready = nullptr;    // fftconv_spectrum_ready_event: one-shot dependency of the data-side work
 };
 
 static std::mutex g_mu;
@@ -180,7 +181,11 @@ static int ctx_get(int device, Ctx** out) {
         CU(cudaEventCreateWithFlags(&c.pinned_free, cudaEventDisableTiming));
         for (auto& e : c.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&c.side2, cudaStreamNonBlocking));
+        {   // data-side transforms are the critical path of a call: they outrank the template transforms they overlap
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi));
+        }
         for (auto& e : c.evf) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         if (opt_in_smem(fwd_h_pass<PAD_ZERO>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(fwd_h_pass<PAD_CLAMP>)) return FFTCONV_ERR_CUDA;
@@ -873,6 +878,9 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     if (osg && !os_config(F, FH, FW, maxkh, maxkw, og, a.nimg))
         return fail(FFTCONV_ERR_UNSUPPORTED, "batch outside the range of the overlap-save path");
     const size_t NO = (size_t)K * a.nimg;                          // output planes
+    cudaEvent_t spec_ready = c.spec_ready;
+    c.spec_ready = nullptr;
+    if (spec_ready && !osg) CU(cudaStreamWaitEvent(st, spec_ready, 0));   // only the overlap-save path has image-independent work to run ahead
 
     // ---- chunking: bound the scratch held per chunk
     const size_t plane = plane_floats(a, FH);
@@ -893,6 +901,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         // bank: they run on a side stream in the shadow of the first os_kern_fft and join before the first GEMM.
         CU(cudaEventRecord(c.evf[0], st));
         CU(cudaStreamWaitEvent(c.side2, c.evf[0], 0));
+        if (spec_ready) CU(cudaStreamWaitEvent(c.side2, spec_ready, 0));
         if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, 0, c.side2)) return e;   // correlation = flipped templates + shifted store
         CU(cudaEventRecord(c.evf[1], c.side2));
         if (a.bankA) CU(cudaStreamWaitEvent(st, c.evf[1], 0));      // prepared bank: nothing to overlap with
@@ -1541,6 +1550,16 @@ void fftconv_release(void) {
     }
     g_ctx.clear();
     if (prev >= 0) cudaSetDevice(prev);
+}
+
+int fftconv_spectrum_ready_event(int device, void* cuda_event) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    DeviceGuard dg(device);
+    if (!dg.ok) return fail(FFTCONV_ERR_CUDA, "cannot select device %d", device);
+    Ctx* c;
+    if (int e = ctx_get(device, &c)) return e;
+    c->spec_ready = reinterpret_cast<cudaEvent_t>(cuda_event);
+    return 0;
 }
 
 const char* fftconv_last_error(void) { return g_err.c_str(); }

@@ -42,6 +42,7 @@ EXPORTED_SYMBOLS = [
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
+    "fftconv_spectrum_ready_event",
 ]
 
 # error ids / messages of the reference
@@ -89,6 +90,7 @@ def lib() -> ctypes.CDLL:
         L = ctypes.CDLL(LIB_PATH)
         c_int, c_vp, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong
         L.fftconv_fft_size16.argtypes = [c_int]
+        L.fftconv_spectrum_ready_event.argtypes = [c_int, c_vp]
         L.fftconv_fft_size_pow2.argtypes = [c_int]
         L.fftconv_fft_data.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
         L.fftconv_fft_data_clamp.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
@@ -408,9 +410,12 @@ def cudaConvolutionFFT(*args, options: Optional[Options] = None) -> List[np.ndar
 
 
 # ------------------------------------------------------------------------------ extensions
-def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Options] = None, stream=None):
+def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Options] = None, stream=None,
+              spectrum_ready=None):
     """Device-resident bank: spec_t complex64 [F][FW][CH], bank_t float32 [K][F][kw][kh] (torch, cuda).
-    Writes K planes [FW][FH] (or the crop) into out_t; stream-ordered, no host sync."""
+    Writes K planes [FW][FH] (or the crop) into out_t; stream-ordered, no host sync.
+    spectrum_ready: torch.cuda.Event recorded behind a collective that is still filling spec_t on another stream
+    (fftconv_spectrum_ready_event): only the data-side work waits for it, the template transforms start at once."""
     torch = _torch()
     F, FW, CH = spec_t.shape
     FH = (CH - 1) * 2
@@ -423,6 +428,8 @@ def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Op
         out_t = torch.empty((K, cw, ld), dtype=torch.float32, device=spec_t.device)
     st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
     op = ctypes.byref(options) if options is not None else None
+    if spectrum_ready is not None:
+        _check(lib().fftconv_spectrum_ready_event(dev, ctypes.c_void_p(spectrum_ready.cuda_event)), ERRID_CONV)
     rc = lib().fftconv_conv_bank(spec_t.data_ptr(), CH, FW, F, K, bank_t.data_ptr(), kh, kw, out_t.data_ptr(), op, dev, st)
     _check(rc, ERRID_CONV)
     return out_t

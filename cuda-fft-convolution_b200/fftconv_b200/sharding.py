@@ -44,6 +44,66 @@ def broadcast_spectrum(spec, src: int = 0, group=None):
     return spec
 
 
+_bcast_streams = {}
+
+
+def broadcast_spectrum_async(spec, src: int = 0, group=None):
+    """Broadcast on a side stream; returns a torch.cuda.Event to hand to conv_bank(spectrum_ready=...) (None when
+    there is nothing to wait for).  The side stream first waits for the caller's current stream (rank `src` has just
+    queued the transform that fills `spec`; on every rank the previous consumer of `spec` is ordered before), then the
+    NCCL broadcast runs there, so the caller's stream is free to run the image-independent template transforms while
+    the spectrum crosses NVLink."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return None
+    if not spec.is_cuda:                       # gloo / CPU tests: nothing to overlap
+        dist.broadcast(torch.view_as_real(spec), src=src, group=group)
+        return None
+    dev = spec.device
+    side = _bcast_streams.get(dev.index)
+    if side is None:
+        side = _bcast_streams[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        dist.broadcast(torch.view_as_real(spec), src=src, group=group)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    spec.record_stream(side)
+    return ev
+
+
+def bind_host_to_gpu(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPU cores NVML reports as local to the GPU (same NUMA node / PCIe root), BEFORE
+    pinned host buffers are allocated: first touch then places them next to the GPU's PCIe link.  With one process per
+    GPU this keeps the ranks' host<->device streams off the inter-socket link.  Best effort: returns the core list, or
+    None when NVML / the affinity call is unavailable."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        if not uuid.startswith("GPU-"):
+            uuid = "GPU-" + uuid
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 def sharded_convolution(data, max_kh: int, max_kw: int, kernels: Sequence, fft_fn: Callable, conv_fn: Callable,
                         alloc_spec: Callable, gather: bool = False, group=None):
     """cudaConvolutionFFT over a process group.

@@ -158,6 +158,13 @@ int fftconv_bank_conv_max(const fftconv_bank* bank, const float* data, int data_
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
                                    long long n, int device, void* stream);
 
+/* Multi-GPU schedule (the N_GPU plans of src/cudaConvFFTDataStreams.cu:273-289, where the spectrum reaches GPU i by
+ * cudaMemcpyPeerAsync): when the spectrum is being delivered by a collective on ANOTHER stream (an NCCL broadcast),
+ * hand its completion event (cudaEvent_t) to the library.  The next convolution call on `device` then makes only its
+ * data-side work wait for the event; the template transforms, which do not depend on the image, start at once on the
+ * call stream, so the broadcast travels over NVLink in their shadow.  One-shot: consumed by that call. */
+int fftconv_spectrum_ready_event(int device, void* cuda_event);
+
 /* Number of kernel launches issued by this library since load (bench accounting). */
 long long fftconv_launch_count(void);
 /* Per-kernel device timing for the roofline leg of bench.py: while enabled, every kernel launch is
