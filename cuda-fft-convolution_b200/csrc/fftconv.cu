@@ -113,6 +113,7 @@ struct Ctx {
     std::map<int, cpx*> tw;          // n -> device twiddle table e^{-2 pi i j / n}
     std::map<int, unsigned short*> ipmap;   // n -> digit-reversal tables of the in-place plan: pos_of[n], nat_of[n]
     DevBuf bpS;                      // large-plane path: re-padded, pre-scaled data spectrum
+    DevBuf batchA;                   // fftconv_conv_batch: template spectra shared by the image groups of one call
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
     DevBuf osA, osB, osP, osPlane, osZ, osPeaks;     // overlap-save / tcgen05 path scratch
     void* pinned = nullptr;          // host staging (descriptors, packed kernels)
@@ -1220,6 +1221,20 @@ int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W,
                      out_on_device, threads, nthreads, opt, device, stream, false);
 }
 
+struct fftconv_bank {
+    int device, K, F, maxkh, maxkw, NKS, KC;
+    float* A;             // [ceil(K/128)][bin][ks][kc][128][4] fp32
+    size_t bytes;
+    int2* khw;            // (kh, kw) per template, device
+    bool owns;            // false: A lives in the cached workspace (the per-call bank of fftconv_conv_batch)
+};
+
+static int bank_conv_images(const fftconv_bank* b, const float* d_data, int nimg, int H, int W, float* const* outs,
+                            int out_on_device, const fftconv_options& o, cudaStream_t st);
+static int bank_create_impl(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                            const unsigned char* kernel_on_device, int F, int device, void* stream, fftconv_bank** out,
+                            bool in_workspace);
+
 int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int W, int F, int maxKH, int maxKW, int K,
                        const float* const* kernels, const int* kh, const int* kw, const int* kf,
                        const unsigned char* kernel_on_device, float* const* outs, int out_on_device,
@@ -1251,6 +1266,14 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
     // the images of a group only add tiles to the N dimension of the per-bin GEMM; the group is sized so that
     // the product spectra of one template chunk stay within a few GB
     const int G = std::max(1, std::min(N, 1280 / g1.NTimg));
+    // several groups: the template spectra (A operand images) do not depend on the images -- transform the bank ONCE
+    // (a prepared bank that lives for this call) instead of once per group
+    fftconv_bank* tmp_bank = nullptr;
+    if (N > G && fftconv_fft_size16(H + maxkh - 1) == FH && fftconv_fft_size16(W + maxkw - 1) == FW) {
+        if (int e = bank_create_impl(K, kernels, kh, kw, kf, kernel_on_device, F, device, stream, &tmp_bank, true)) return e;
+        if (tmp_bank->maxkh != maxkh || tmp_bank->maxkw != maxkw) { fftconv_bank_destroy(tmp_bank); tmp_bank = nullptr; }
+    }
+    struct BankGuard { fftconv_bank* b; ~BankGuard() { if (b) fftconv_bank_destroy(b); } } bank_guard{tmp_bank};
     for (int n0 = 0; n0 < N; n0 += G) {
         const int nimg = std::min(G, N - n0);
         const float* d_data = data + (size_t)n0 * img;
@@ -1264,6 +1287,13 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
             CU(cudaMemcpyAsync(c->ddata.p, d_data, sizeof(float) * img * nimg, cudaMemcpyHostToDevice, (cudaStream_t)stream));
             d_data = (const float*)c->ddata.p;
         }
+        if (tmp_bank) {
+            std::lock_guard<std::mutex> lk(g_mu);
+            DeviceGuard guard(device);
+            if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+            if (int e = bank_conv_images(tmp_bank, d_data, nimg, H, W, outs + (size_t)n0 * K, 1, o, (cudaStream_t)stream)) return e;
+            continue;
+        }
         ConvRaw raw{d_data, H, W, nimg};
         if (int e = conv_impl(nullptr, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs + (size_t)n0 * K, 1,
                               nullptr, 0, opt, device, stream, false, &raw))
@@ -1274,15 +1304,13 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
 
 // ---- prepared banks: the template spectra (tcgen05 A operand images) are independent of the image size on the
 // overlap-save path (64 x 64 tiles), so they are computed once and stay resident in HBM.
-struct fftconv_bank {
-    int device, K, F, maxkh, maxkw, NKS, KC;
-    float* A;             // [ceil(K/128)][bin][ks][kc][128][4] fp32
-    size_t bytes;
-    int2* khw;            // (kh, kw) per template, device
-};
 
-int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
-                        const unsigned char* kernel_on_device, int F, int device, void* stream, fftconv_bank** out) {
+// in_workspace: the A images go to the cached workspace and the call stays stream-ordered (no allocation, no host
+// synchronisation): the per-call bank of fftconv_conv_batch.  Otherwise the bank owns its memory and the call returns
+// when the transform is done.
+static int bank_create_impl(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                            const unsigned char* kernel_on_device, int F, int device, void* stream, fftconv_bank** out,
+                            bool in_workspace) {
     g_err.clear();
     if (!out || K <= 0 || F <= 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
     *out = nullptr;
@@ -1300,10 +1328,15 @@ int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const
     if (int e = ctx_get(device, &c)) return e;
     cudaStream_t st = (cudaStream_t)stream;
     const int ntblk = (K + OS_TM - 1) / OS_TM;
-    std::unique_ptr<fftconv_bank> b(new fftconv_bank{device, K, F, maxkh, maxkw, g.NKS, g.KC, nullptr, 0, nullptr});
+    std::unique_ptr<fftconv_bank> b(new fftconv_bank{device, K, F, maxkh, maxkw, g.NKS, g.KC, nullptr, 0, nullptr, !in_workspace});
     b->bytes = (size_t)ntblk * OS_NBIN * g.NKS * (g.a_stage / 2);
-    CU(cudaMalloc(&b->A, b->bytes));
-    {
+    if (in_workspace) {
+        if (int e = dev_reserve(c->batchA, b->bytes)) return e;
+        b->A = (float*)c->batchA.p;
+    } else {
+        CU(cudaMalloc(&b->A, b->bytes));
+    }
+    if (!in_workspace) {
         std::vector<int2> khw(K);
         for (int k = 0; k < K; ++k) khw[k] = make_int2(refs[k].kh, refs[k].kw);
         if (cudaMalloc(&b->khw, sizeof(int2) * (size_t)K) != cudaSuccess ||
@@ -1345,12 +1378,21 @@ int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const
         if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);
         else os_kern_fft<2><<<grid, 256, os_kern_smem(2), st>>>(a);
         g_launches.fetch_add(1, std::memory_order_relaxed);
-        if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+        if (cudaGetLastError() != cudaSuccess) e = fail(FFTCONV_ERR_CUDA, "bank transform failed");
+        if (!e && in_workspace) {
+            if (cudaEventRecord(c->pinned_free, st) != cudaSuccess) e = fail(FFTCONV_ERR_CUDA, "event record failed");
+        } else if (!e && cudaStreamSynchronize(st) != cudaSuccess) {
             e = fail(FFTCONV_ERR_CUDA, "bank transform failed");
+        }
     }
-    if (e) { cudaFree(b->A); cudaFree(b->khw); return e; }
+    if (e) { if (b->owns) { cudaFree(b->A); cudaFree(b->khw); } return e; }
     *out = b.release();
     return 0;
+}
+
+int fftconv_bank_create(int K, const float* const* kernels, const int* kh, const int* kw, const int* kf,
+                        const unsigned char* kernel_on_device, int F, int device, void* stream, fftconv_bank** out) {
+    return bank_create_impl(K, kernels, kh, kw, kf, kernel_on_device, F, device, stream, out, false);
 }
 
 int fftconv_bank_info(const fftconv_bank* b, int* K, int* F, int* maxKH, int* maxKW, long long* bytes) {
@@ -1361,6 +1403,22 @@ int fftconv_bank_info(const fftconv_bank* b, int* K, int* F, int* maxKH, int* ma
     if (maxKW) *maxKW = b->maxkw;
     if (bytes) *bytes = (long long)b->bytes;
     return 0;
+}
+
+// nimg device-resident images [nimg][F][W][H] against a prepared bank (caller holds g_mu and has selected the device);
+// outs: nimg * K planes, image-major.
+static int bank_conv_images(const fftconv_bank* b, const float* d_data, int nimg, int H, int W, float* const* outs,
+                            int out_on_device, const fftconv_options& o, cudaStream_t st) {
+    Ctx* c;
+    if (int e = ctx_get(b->device, &c)) return e;
+    const int FH = fftconv_fft_size16(H + b->maxkh - 1), FW = fftconv_fft_size16(W + b->maxkw - 1);
+    ConvArgs a;
+    a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = b->F; a.K = b->K;
+    a.kernels = nullptr; a.outs = outs; a.out_on_device = out_on_device != 0;
+    a.opt = o; a.pipelined = false;
+    a.d_raw = d_data; a.rawH = H; a.rawW = W; a.nimg = nimg;
+    a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw;
+    return run_conv(*c, a, st);
 }
 
 int fftconv_bank_conv(const fftconv_bank* b, const float* data, int data_on_device, int H, int W,
@@ -1386,13 +1444,7 @@ int fftconv_bank_conv(const fftconv_bank* b, const float* data, int data_on_devi
         CU(cudaMemcpyAsync(c->ddata.p, data, bytes, cudaMemcpyHostToDevice, st));
         d_data = (const float*)c->ddata.p;
     }
-    ConvArgs a;
-    a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = F; a.K = K;
-    a.kernels = nullptr; a.outs = outs; a.out_on_device = out_on_device != 0;
-    a.opt = o; a.pipelined = false;
-    a.d_raw = d_data; a.rawH = H; a.rawW = W;
-    a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw;
-    return run_conv(*c, a, st);
+    return bank_conv_images(b, d_data, 1, H, W, outs, out_on_device, o, st);
 }
 
 int fftconv_bank_conv_max(const fftconv_bank* b, const float* data, int data_on_device, int H, int W,
@@ -1441,8 +1493,10 @@ void fftconv_bank_destroy(fftconv_bank* b) {
     if (!b) return;
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceGuard guard(b->device);
-    cudaFree(b->A);
-    cudaFree(b->khw);
+    if (b->owns) {
+        cudaFree(b->A);
+        cudaFree(b->khw);
+    }
     delete b;
 }
 
@@ -1539,7 +1593,7 @@ void fftconv_release(void) {
         for (auto& t : c.tw) cudaFree(t.second);
         for (auto& t : c.ipmap) cudaFree(t.second);
         for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg,
-                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks, &c.bpS})
+                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks, &c.bpS, &c.batchA})
             if (b->p) cudaFree(b->p);
         if (c.pinned) cudaFreeHost(c.pinned);
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);

@@ -51,6 +51,25 @@ def test_batch_many_tile_blocks(fc, oracle):
     _case(fc, oracle, N=4, H=200, W=150, F=3, kh=5, kw=6, K=9, seed=44)
 
 
+def test_batch_several_groups_share_one_bank_transform(fc, oracle):
+    """More images than one group holds (1280 tiles): the bank is transformed once for the whole call and every
+    group runs against the resident template spectra."""
+    import torch
+    N, H, W, F, kh, kw, K = 11, 300, 300, 2, 32, 32, 130
+    rng = np.random.default_rng(46)
+    data = rng.random((N, H, W, F), dtype=np.float32)
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.05).astype(np.float32)
+    FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+    d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(0, 3, 2, 1))).cuda()
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    out = fc.conv_batch(d_t, b_t)
+    torch.cuda.synchronize()
+    for n in (0, 9, 10):                       # first group, last image of it, second group
+        for k in (0, 127, 129):
+            got = out[n, k].cpu().numpy().T
+            assert oracle.rel_l2(got, oracle.direct_conv64_c(data[n], bank[k], FH, FW)) < TOL, (n, k)
+
+
 def test_batch_falls_back_for_large_kernels(fc, oracle):
     """kernels beyond 32x32 are outside the overlap-save path: the call loops over the images."""
     _case(fc, oracle, N=2, H=80, W=70, F=2, kh=40, kw=33, K=3, seed=45)
