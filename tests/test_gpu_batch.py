@@ -187,3 +187,30 @@ def test_correlation_mode_per_template_sizes(fc, oracle, path):
         flip = oracle.direct_conv64_c(data, np.ascontiguousarray(ks[k][::-1, ::-1, :]), FH, FW)
         want = np.roll(flip, (-(kh - 1), -(kw - 1)), axis=(0, 1))
         assert oracle.rel_l2(corr[k], want) < TOL, (path, k)
+
+
+def test_spectrum_ready_event_orders_only_the_data_side(fc, oracle):
+    """fftconv_spectrum_ready_event: the spectrum is filled on ANOTHER stream (a copy standing in for the NCCL broadcast);
+    the call stream never waits for it explicitly — only the event handed to the library orders the data-side work."""
+    import torch
+    rng = np.random.default_rng(48)
+    H = W = 128; F = 4; kh = kw = 9; K = 70
+    data = rng.random((H, W, F), dtype=np.float32)
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.1).astype(np.float32)
+    spec_src = fc.cudaFFTData(data, kh, kw).tensor.clone()
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    for path in (0, 1, 3):
+        spec = torch.zeros_like(spec_src)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            torch.cuda._sleep(20_000_000)                  # the "collective" is late
+            spec.copy_(spec_src, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        out = fc.conv_bank(spec, b_t, kh, kw, options=fc.Options(path=path), spectrum_ready=ev)
+        torch.cuda.synchronize()
+        FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+        for k in (0, K - 1):
+            assert oracle.rel_l2(out[k].cpu().numpy().T, oracle.direct_conv64_c(data, bank[k], FH, FW)) < TOL, (path, k)

@@ -56,6 +56,12 @@ def _worker(rank, world, port, q):
         ref = oracle.convolution_fft(data, 8, 8, kernels)
         ok = len(full) == len(ref) and all(np.array_equal(a, r) for a, r in zip(full, ref))
         ok = ok and all(np.array_equal(p, ref[b + i]) for i, p in enumerate(planes))
+        # the side-stream broadcast helper degrades to an in-order broadcast on CPU tensors and returns no event
+        from fftconv_b200.sharding import broadcast_spectrum_async, bind_host_to_gpu
+        sp = fft_fn(data, 8, 8) if rank == 0 else torch.zeros(shape, dtype=torch.complex64)
+        ok = ok and broadcast_spectrum_async(sp, 0) is None
+        ok = ok and np.array_equal(sp.numpy(), oracle.fft_data(data, 8, 8))
+        ok = ok and bind_host_to_gpu(0) is None            # no GPU / NVML here: best effort, must not raise
         q.put((rank, b, e, bool(ok)))
     finally:
         dist.destroy_process_group()
