@@ -179,7 +179,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import fftconv_b200 as fc
-    from fftconv_b200.sharding import broadcast_spectrum, broadcast_spectrum_async, bind_host_to_gpu
+    from fftconv_b200.sharding import broadcast_spectrum, broadcast_spectrum_async, bind_host_to_gpu, PeerSpectrum
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -211,13 +211,30 @@ def run_ours(args):
     spec = torch.empty((F, FW, CH), dtype=torch.complex64, device=dev)
     out = torch.empty((K, FW, FH), dtype=torch.float32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    # spectrum delivery at N > 1: "peer" = CUDA IPC + NVLink pull ordered by device flags (fftconv_peer_*),
+    # "sync" = NCCL broadcast on the step's stream, "async" = NCCL broadcast on a side stream (A/B switches)
+    bcast_mode = os.environ.get("FFTCONV_BENCH_BCAST", "peer") if world > 1 else "local"
+    peer = None
+    if bcast_mode == "peer":
+        peer = PeerSpectrum((F, FW, CH))
+        if peer.enabled:
+            spec = peer.spec
+        else:
+            peer, bcast_mode = None, "sync"
     stream = torch.cuda.current_stream()
 
     def step():
         """data FFT (rank 0) -> [NCCL broadcast of the spectrum] -> bank convolution on every rank"""
+        if peer is not None:
+            peer.begin_fill()
+            if rank == 0:
+                fc.fft_data_device(data, H, W, F, kh, kw, spec_t=spec)
+            peer.publish_and_fetch()
+            fc.conv_bank(spec, bank, kh, kw, out)
+            return
         if rank == 0:
             fc.fft_data_device(data, H, W, F, kh, kw, spec_t=spec)
-        if os.environ.get("FFTCONV_BENCH_BCAST", "sync") == "async":
+        if bcast_mode == "async":
             # A/B switch: NCCL broadcast on a side stream, only the data-side transforms wait for it
             # (fftconv_spectrum_ready_event).  Measured SLOWER on 2 x B200 (1.22 vs 1.12 ms per step, profiles/
             # r01e_n2_bcast_ab.txt): the NCCL kernel and the template transforms fight for SMs; kept off.
@@ -325,9 +342,14 @@ def run_ours(args):
                                            op, 0, None, 0, None, local, st)
         else:
             rc = 0
+            if peer is not None:
+                peer.begin_fill()
             if rank == 0:
                 rc = L.fftconv_fft_data(h_data.data_ptr(), 0, H, W, F, kh, kw, spec.data_ptr(), local, st)
-            broadcast_spectrum(spec, 0)
+            if peer is not None:
+                peer.publish_and_fetch()
+            else:
+                broadcast_spectrum(spec, 0)
             rc = rc or L.fftconv_conv_fft_data(spec.data_ptr(), CH, FW, F, K, kp, khs, kws, None, None, op, 0,
                                                None, 0, None, local, st)
         if rc != 0:
@@ -352,7 +374,7 @@ def run_ours(args):
            "h2d_bytes_per_step": int(4 * H * W * F + world * 4 * K * F * kh * kw),
            "d2h_bytes_per_step": int(world * 4 * K * FH * FW),
            "api": "fftconv_convolution_fft (cudaConvolutionFFT) host->host" if world == 1 else
-                  "fftconv_fft_data + NCCL broadcast + fftconv_conv_fft_data, host->host",
+                  f"fftconv_fft_data + spectrum delivery ({bcast_mode}) + fftconv_conv_fft_data, host->host",
            "bound": "PCIe D2H of the output planes"}
 
     # ---- extensions beyond the reference surface (informational, N = 1): prepared bank + fused per-template maximum
@@ -412,7 +434,9 @@ def run_ours(args):
                        "l2": "flushed between steps by an untimed 256 MiB memset; each step also writes "
                              f"{4 * K * FH * FW / 1e6:.0f} MB of outputs (> 126 MB L2)",
                        "parallelism": f"template bank sharded over {world} GPU(s), data spectrum "
-                                      + ("broadcast by NCCL inside the step" if world > 1 else "local"),
+                                      + ({"peer": "pulled from rank 0 over CUDA IPC + NVLink inside the step (device flags, no collective kernel)",
+                                          "sync": "broadcast by NCCL inside the step", "async": "broadcast by NCCL on a side stream inside the step",
+                                          "local": "local"}[bcast_mode]),
                        "host_affinity": (f"{len(numa_cpus)} cores local to the GPU (NVML)" if numa_cpus else "unchanged"),
                        "timing": "CUDA events per step on the launch stream, max over ranks",
                        "rel_l2_vs_fp64": rel_l2},
@@ -420,6 +444,10 @@ def run_ours(args):
             "cpu_baseline": cpu_baseline, "extras": extras, "wall_s_timed_region": t_wall,
         }
         print(json.dumps(line))
+    if peer is not None:
+        if peer.status() != 0:
+            raise SystemExit("peer spectrum wait timed out: " + fc.last_error())
+        peer.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -847,6 +848,37 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
     return 0;
 }
 
+
+// ------------------------------------------------------------------ peer spectrum (CUDA IPC + NVLink)
+__device__ unsigned int g_peer_timeouts = 0;
+
+__global__ void peer_signal_kernel(unsigned long long* flag, unsigned long long value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+
+// one thread per flag; gives up after ~2 s so that a lost peer cannot wedge the device
+__global__ void peer_wait_kernel(const unsigned long long* flags, int n, unsigned long long value) {
+    const int i = threadIdx.x;
+    if (i >= n) return;
+    const long long t0 = clock64();
+    unsigned long long v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + i) : "memory");
+        if (v >= value) break;
+        if (clock64() - t0 > 4000000000ll) { atomicAdd(&g_peer_timeouts, 1u); break; }
+        __nanosleep(100);
+    }
+    __threadfence_system();
+}
+
+// grid-stride 16-byte copy out of the mapped peer buffer (NVLink reads), tail in bytes
+__global__ void peer_pull_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16,
+                                 unsigned char* __restrict__ dtail, const unsigned char* __restrict__ stail, int ntail) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+    if (blockIdx.x == 0 && (int)threadIdx.x < ntail) dtail[threadIdx.x] = stail[threadIdx.x];
+}
+
 static size_t plane_floats(const ConvArgs& a, int FH) {
     const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
     const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : a.FW;
@@ -1613,6 +1645,92 @@ int fftconv_spectrum_ready_event(int device, void* cuda_event) {
     Ctx* c;
     if (int e = ctx_get(device, &c)) return e;
     c->spec_ready = reinterpret_cast<cudaEvent_t>(cuda_event);
+    return 0;
+}
+
+// ---- peer spectrum
+int fftconv_peer_alloc(size_t bytes, int device, void** ptr, unsigned char handle[64]) {
+    g_err.clear();
+    if (!ptr || !handle || bytes == 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    void* p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    if (cudaMemset(p, 0, bytes) != cudaSuccess || cudaIpcGetMemHandle(&h, p) != cudaSuccess) {
+        const cudaError_t e = cudaGetLastError();
+        cudaFree(p);
+        return fail(FFTCONV_ERR_CUDA, "CUDA IPC export failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaDeviceSynchronize());
+    memcpy(handle, &h, 64);
+    *ptr = p;
+    return 0;
+}
+int fftconv_peer_open(const unsigned char handle[64], int device, void** ptr) {
+    g_err.clear();
+    if (!ptr || !handle) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int fftconv_peer_close(void* mapped_ptr, int device) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    CU(cudaIpcCloseMemHandle(mapped_ptr));
+    return 0;
+}
+int fftconv_peer_free(void* ptr, int device) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    CU(cudaFree(ptr));
+    return 0;
+}
+int fftconv_peer_signal(unsigned long long* flag, unsigned long long value, int device, void* stream) {
+    DeviceGuard guard(device);
+    if (!guard.ok || !flag) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(flag, value);
+    LAUNCH_CHECK();
+    return 0;
+}
+int fftconv_peer_wait_all(const unsigned long long* flags, int n, unsigned long long value, int device, void* stream) {
+    DeviceGuard guard(device);
+    if (!guard.ok || !flags || n <= 0 || n > 1024) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    peer_wait_kernel<<<1, ((n + 31) / 32) * 32, 0, (cudaStream_t)stream>>>(flags, n, value);
+    LAUNCH_CHECK();
+    return 0;
+}
+int fftconv_peer_wait(const unsigned long long* flag, unsigned long long value, int device, void* stream) {
+    return fftconv_peer_wait_all(flag, 1, value, device, stream);
+}
+int fftconv_peer_pull(void* dst, const void* src_mapped, size_t bytes, int device, void* stream) {
+    DeviceGuard guard(device);
+    if (!guard.ok || !dst || !src_mapped) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    if (((uintptr_t)dst | (uintptr_t)src_mapped) & 15) {
+        CU(cudaMemcpyAsync(dst, src_mapped, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return 0;
+    }
+    const size_t n16 = bytes / 16;
+    const int ntail = (int)(bytes - n16 * 16);
+    Ctx* c;
+    { std::lock_guard<std::mutex> lk(g_mu); if (int e = ctx_get(device, &c)) return e; }
+    peer_pull_kernel<<<c->sm_count * 2, 512, 0, (cudaStream_t)stream>>>((uint4*)dst, (const uint4*)src_mapped, n16,
+                                                                      (unsigned char*)dst + n16 * 16,
+                                                                      (const unsigned char*)src_mapped + n16 * 16, ntail);
+    LAUNCH_CHECK();
+    return 0;
+}
+int fftconv_peer_status(int device) {
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    CU(cudaDeviceSynchronize());
+    unsigned int n = 0;
+    CU(cudaMemcpyFromSymbol(&n, g_peer_timeouts, sizeof n));
+    if (n) return fail(FFTCONV_ERR_CUDA, "%u peer wait(s) timed out on device %d", n, device);
     return 0;
 }
 

@@ -43,6 +43,8 @@ EXPORTED_SYMBOLS = [
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
     "fftconv_spectrum_ready_event",
+    "fftconv_peer_alloc", "fftconv_peer_open", "fftconv_peer_close", "fftconv_peer_free", "fftconv_peer_signal",
+    "fftconv_peer_wait", "fftconv_peer_wait_all", "fftconv_peer_pull", "fftconv_peer_status",
 ]
 
 # error ids / messages of the reference
@@ -91,6 +93,15 @@ def lib() -> ctypes.CDLL:
         c_int, c_vp, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong
         L.fftconv_fft_size16.argtypes = [c_int]
         L.fftconv_spectrum_ready_event.argtypes = [c_int, c_vp]
+        L.fftconv_peer_alloc.argtypes = [ctypes.c_size_t, c_int, ctypes.POINTER(c_vp), c_vp]
+        L.fftconv_peer_open.argtypes = [c_vp, c_int, ctypes.POINTER(c_vp)]
+        L.fftconv_peer_close.argtypes = [c_vp, c_int]
+        L.fftconv_peer_free.argtypes = [c_vp, c_int]
+        L.fftconv_peer_signal.argtypes = [c_vp, ctypes.c_ulonglong, c_int, c_vp]
+        L.fftconv_peer_wait.argtypes = [c_vp, ctypes.c_ulonglong, c_int, c_vp]
+        L.fftconv_peer_wait_all.argtypes = [c_vp, c_int, ctypes.c_ulonglong, c_int, c_vp]
+        L.fftconv_peer_pull.argtypes = [c_vp, c_vp, ctypes.c_size_t, c_int, c_vp]
+        L.fftconv_peer_status.argtypes = [c_int]
         L.fftconv_fft_size_pow2.argtypes = [c_int]
         L.fftconv_fft_data.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
         L.fftconv_fft_data_clamp.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]

@@ -34,11 +34,29 @@ def shard_bank(costs: Sequence[float], world: int) -> List[Tuple[int, int]]:
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 
-def broadcast_spectrum(spec, src: int = 0, group=None):
-    """Broadcast a complex64 spectrum tensor [F][FW][CH] from `src` (in place on the other ranks)."""
+def broadcast_spectrum(spec, src: int = 0, group=None, two_phase: Optional[bool] = None):
+    """Broadcast a complex64 spectrum tensor [F][FW][CH] from `src` (in place on the other ranks).
+
+    NCCL's broadcast is a ring: the spectrum crawls through all the GPUs one after the other (170 us for 9.24 MB on
+    8 x B200).  With 4 or more ranks the copy is therefore done in two phases that use every NVSwitch port at once —
+    `src` scatters one slice to every rank, then the ranks all-gather the slices (in place) — when the spectrum splits
+    evenly; otherwise (or with two_phase=False / on CPU tensors) the plain broadcast runs."""
+    import os
     import torch
     import torch.distributed as dist
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return spec
+    world = dist.get_world_size(group)
+    flat = torch.view_as_real(spec).reshape(-1)
+    if two_phase is None:
+        two_phase = world >= 4 and os.environ.get("FFTCONV_BCAST", "two_phase") != "ring"
+    if two_phase and spec.is_cuda and spec.is_contiguous() and flat.numel() % world == 0:
+        rank = dist.get_rank(group)
+        n = flat.numel() // world
+        mine = flat[rank * n:(rank + 1) * n]
+        parts = [flat[r * n:(r + 1) * n] for r in range(world)] if rank == src else None
+        dist.scatter(mine, scatter_list=parts, src=src, group=group)
+        dist.all_gather_into_tensor(flat, mine, group=group)
         return spec
     dist.broadcast(torch.view_as_real(spec), src=src, group=group)
     return spec
@@ -71,6 +89,130 @@ def broadcast_spectrum_async(spec, src: int = 0, group=None):
         ev.record(side)
     spec.record_stream(side)
     return ev
+
+
+class _RawCuda:
+    """Zero-copy view of device memory owned by libfftconv (torch.as_tensor reads __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class PeerSpectrum:
+    """The spectrum of rank `src`, delivered to every rank over CUDA IPC + NVLink without a collective kernel and
+    without host synchronisation (fftconv_peer_* in include/fftconv.h; the B200 form of the cudaMemcpyPeerAsync in
+    src/cudaConvFFTDataStreams.cu:279-289).
+
+        ps = PeerSpectrum((F, FW, CH))              # collective: every rank of the group constructs it
+        each step:   ps.begin_fill()                # src: wait until every rank has pulled the previous spectrum
+                     if rank == src: fill ps.spec   # e.g. fc.fft_data_device(..., spec_t=ps.spec)
+                     ps.publish_and_fetch()         # src: raise the flag; others: wait for it, pull, acknowledge
+                     use ps.spec                    # local complex64 tensor [F][FW][CH] on every rank
+
+    Everything is stream-ordered on the current stream.  When CUDA IPC is unavailable (`enabled` False on every rank)
+    the same calls fall back to the NCCL broadcast."""
+
+    def __init__(self, shape, src: int = 0, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import lib
+        self.group, self.src = group, src
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.dev = torch.cuda.current_device()
+        self.shape = tuple(int(x) for x in shape)
+        F, FW, CH = self.shape
+        self.nbytes = 8 * F * FW * CH
+        self.flag_off = (self.nbytes + 255) // 256 * 256
+        total = self.flag_off + 8 * (1 + self.world)
+        self.step = 0
+        self._L = L = lib()
+        self._owned = self._mapped = None
+        ok, handle = 1, b""
+        if self.rank == src:
+            p, h = ctypes.c_void_p(0), (ctypes.c_ubyte * 64)()
+            if L.fftconv_peer_alloc(total, self.dev, ctypes.byref(p), h) == 0:
+                self._owned, handle = p.value, bytes(h)
+            else:
+                ok = 0
+        if self.world > 1:
+            got = [None] * self.world
+            dist.all_gather_object(got, (ok, handle), group=group)
+            ok, handle = got[src]
+            if ok and self.rank != src:
+                p = ctypes.c_void_p(0)
+                hb = (ctypes.c_ubyte * 64)(*handle)
+                if L.fftconv_peer_open(hb, self.dev, ctypes.byref(p)) == 0:
+                    self._mapped = p.value
+                else:
+                    ok = 0
+            oks = [None] * self.world
+            dist.all_gather_object(oks, int(ok), group=group)
+            ok = min(oks)
+        self.enabled = bool(ok)
+        if self.enabled and self.rank == src:
+            raw = torch.as_tensor(_RawCuda(self._owned, self.nbytes), device=f"cuda:{self.dev}")
+            self.spec = torch.view_as_complex(raw.view(torch.float32).view(F, FW, CH, 2))
+            self._base = self._owned
+        else:
+            self.spec = torch.empty(self.shape, dtype=torch.complex64, device=f"cuda:{self.dev}")
+            self._base = self._mapped
+        if not self.enabled:
+            self.close()
+            self._closed = False          # nothing left to release; later close() calls stay collective no-ops
+            self.world = 1
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _chk(self, rc):
+        if rc != 0:
+            from . import last_error
+            raise RuntimeError("peer spectrum: " + last_error())
+
+    def begin_fill(self):
+        if self.enabled and self.rank == self.src and self.step > 0:
+            self._chk(self._L.fftconv_peer_wait_all(self._base + self.flag_off + 8, self.world, self.step, self.dev, self._stream()))
+
+    def publish_and_fetch(self):
+        if not self.enabled:
+            broadcast_spectrum(self.spec, self.src, self.group, two_phase=False)
+            return self.spec
+        self.step += 1
+        L, st = self._L, self._stream()
+        ready = self._base + self.flag_off
+        ack = ready + 8 * (1 + self.rank)
+        if self.rank == self.src:
+            self._chk(L.fftconv_peer_signal(ready, self.step, self.dev, st))
+        else:
+            self._chk(L.fftconv_peer_wait(ready, self.step, self.dev, st))
+            self._chk(L.fftconv_peer_pull(self.spec.data_ptr(), self._base, self.nbytes, self.dev, st))
+        self._chk(L.fftconv_peer_signal(ack, self.step, self.dev, st))
+        return self.spec
+
+    def status(self) -> int:
+        """0 when no wait has timed out (synchronises the device)."""
+        return self._L.fftconv_peer_status(self.dev) if self.enabled else 0
+
+    def close(self):
+        """Collective: every rank of the group calls it (the owner frees only after every peer has unmapped)."""
+        import torch
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.dev)
+        if self._mapped is not None:
+            self._L.fftconv_peer_close(self._mapped, self.dev)
+            self._mapped = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        if self._owned is not None:
+            self._L.fftconv_peer_free(self._owned, self.dev)
+            self._owned = None
+        self.enabled = False
 
 
 def bind_host_to_gpu(device_index: int) -> Optional[List[int]]:

@@ -29,6 +29,8 @@
 #ifndef FFTCONV_H_
 #define FFTCONV_H_
 
+#include <stddef.h>
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -164,6 +166,26 @@ int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_
  * data-side work wait for the event; the template transforms, which do not depend on the image, start at once on the
  * call stream, so the broadcast travels over NVLink in their shadow.  One-shot: consumed by that call. */
 int fftconv_spectrum_ready_event(int device, void* cuda_event);
+
+/* PEER SPECTRUM — the multi-GPU plans of src/cudaConvFFTDataStreams.cu:279-289 copy the spectrum GPU 0 -> GPU i with
+ * cudaMemcpyPeerAsync.  One process per GPU cannot call that; the same copy is done here over CUDA IPC + NVLink, ordered
+ * entirely on the device (no host synchronisation, no collective kernel):
+ *   owner:  fftconv_peer_alloc (cudaMalloc + IPC handle; zero-filled), other ranks: fftconv_peer_open(handle);
+ *   owner:  ... kernels that fill the buffer ...; fftconv_peer_signal(flag, step)          (release, system scope)
+ *   peer:   fftconv_peer_wait(flag, step); fftconv_peer_pull(local, mapped, bytes); fftconv_peer_signal(ack_r, step)
+ *   owner, before refilling: fftconv_peer_wait_all(acks, n, step)  — every peer has pulled the previous contents.
+ * Flags are 64-bit counters living in the owner's allocation; every call is stream-ordered.  A wait gives up after
+ * about two seconds of device time and records the failure (next fftconv_peer_status call returns non-zero), so a
+ * lost peer can never wedge the GPU. */
+int fftconv_peer_alloc(size_t bytes, int device, void** ptr, unsigned char handle[64]);
+int fftconv_peer_open(const unsigned char handle[64], int device, void** ptr);
+int fftconv_peer_close(void* mapped_ptr, int device);
+int fftconv_peer_free(void* ptr, int device);
+int fftconv_peer_signal(unsigned long long* flag, unsigned long long value, int device, void* stream);
+int fftconv_peer_wait(const unsigned long long* flag, unsigned long long value, int device, void* stream);
+int fftconv_peer_wait_all(const unsigned long long* flags, int n, unsigned long long value, int device, void* stream);
+int fftconv_peer_pull(void* dst, const void* src_mapped, size_t bytes, int device, void* stream);
+int fftconv_peer_status(int device);        /* 0: no wait has timed out on this device (synchronises the device) */
 
 /* Number of kernel launches issued by this library since load (bench accounting). */
 long long fftconv_launch_count(void);
