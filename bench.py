@@ -70,12 +70,17 @@ class ClockSampler:
         self.proc = None
 
     def __enter__(self):
+        if self.index is None:               # only rank 0 samples (8 concurrent nvidia-smi start-ups outlast the timed region)
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t0 = time.perf_counter()         # nvidia-smi needs a moment to start: wait for its first sample
+            while not self.rows and time.perf_counter() - t0 < 5.0:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
         return self
@@ -256,7 +261,7 @@ def run_ours(args):
     # ---- timed region: K steps, each bracketed by CUDA events; L2 flushed (untimed) between steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = fc.launch_count()
-    with ClockSampler(local) as clk:
+    with ClockSampler(local if rank == 0 else None) as clk:
         barrier()
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
