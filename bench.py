@@ -384,7 +384,7 @@ def run_ours(args):
 
     # ---- extensions beyond the reference surface (informational, N = 1): prepared bank + fused per-template maximum
     extras = None
-    if world == 1:
+    if world == 1 and not args.no_extras:
         hb = ctypes.c_void_p(0)
         dk = (ctypes.c_void_p * K)(*[bank.data_ptr() + 4 * k * F * kw * kh for k in range(K)])
         ond = (ctypes.c_ubyte * K)(*([1] * K))
@@ -466,6 +466,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the informational prepared-bank / fused-max legs "
+                                                               "(profiling runs: keeps the launch list to the step's own kernels)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -476,7 +478,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--workload", args.workload] + (["--no-cpu"] if args.no_cpu else [])
+               "--workload", args.workload] + (["--no-cpu"] if args.no_cpu else []) + (["--no-extras"] if args.no_extras else [])
         raise SystemExit(subprocess.call(cmd))
     run_ours(args)
 

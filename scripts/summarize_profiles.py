@@ -17,7 +17,7 @@ for r in rows[1:]:
     a = agg.setdefault(name, [0, 0.0]); a[0] += 1; a[1] += v_us
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(P, f"{R}_launches_summary.md"), "w") as f:
-    f.write(f"# {R}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu`\n\n"
+    f.write(f"# {R}: ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu --no-extras`\n\n"
             "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES).\n"
             "Includes the warm-up, timed, profiling and e2e legs of bench.py.\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
