@@ -86,3 +86,18 @@ def test_no_product_import_of_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, fn
+
+
+def test_torch_ops_register_and_infer_shapes():
+    """torch.ops.fftconv.*: registered, shape inference on the meta device, and no CPU fallback."""
+    import torch
+    import fftconv_b200.torch_ops  # noqa: F401
+    d = torch.empty((31, 256, 256), device="meta")
+    spec = torch.ops.fftconv.fft_data(d, 16, 16)
+    assert tuple(spec.shape) == (31, 272, 137) and spec.dtype == torch.complex64
+    bank = torch.empty((1000, 31, 16, 16), device="meta")
+    assert tuple(torch.ops.fftconv.conv_fft_data(spec, bank).shape) == (1000, 272, 272)
+    imgs = torch.empty((64, 32, 512, 512), device="meta")
+    assert tuple(torch.ops.fftconv.convolution_fft(imgs, torch.empty((256, 32, 32, 32), device="meta")).shape) == (64, 256, 544, 544)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        torch.ops.fftconv.fft_data(torch.zeros((2, 8, 8)), 3, 3)          # CPU tensors: no fallback

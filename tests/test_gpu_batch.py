@@ -214,3 +214,23 @@ def test_spectrum_ready_event_orders_only_the_data_side(fc, oracle):
         FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
         for k in (0, K - 1):
             assert oracle.rel_l2(out[k].cpu().numpy().T, oracle.direct_conv64_c(data, bank[k], FH, FW)) < TOL, (path, k)
+
+
+def test_torch_ops_match_the_mirror(fc, oracle):
+    import torch
+    import fftconv_b200.torch_ops  # noqa: F401
+    rng = np.random.default_rng(49)
+    H, W, F, kh, kw, K = 70, 50, 3, 9, 7, 5
+    data = rng.random((H, W, F), dtype=np.float32)
+    bank = rng.standard_normal((K, kh, kw, F)).astype(np.float32)
+    d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(2, 1, 0))).cuda()
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    spec = torch.ops.fftconv.fft_data(d_t, kh, kw)
+    out = torch.ops.fftconv.conv_fft_data(spec, b_t)
+    out2 = torch.ops.fftconv.convolution_fft(d_t[None], b_t)
+    torch.cuda.synchronize()
+    FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+    for k in range(K):
+        ref = oracle.direct_conv64_c(data, bank[k], FH, FW)
+        assert oracle.rel_l2(out[k].cpu().numpy().T, ref) < TOL
+        assert oracle.rel_l2(out2[0, k].cpu().numpy().T, ref) < TOL
