@@ -1,6 +1,6 @@
 // fftconv_bench — stand-alone C++ driver of the C ABI (include/fftconv.h); no MATLAB, no Python.
 //
-//   fftconv_bench [--config c1|c2|c3|c3s] [--H h --W w --F f --kh a --kw b --K k] [--iters n]
+//   fftconv_bench [--config c1|c2|c3|c3s|c4|c4s] [--H h --W w --F f --kh a --kw b --K k --N n] [--iters n]
 //                 [--host] [--check n] [--device d]
 //
 // Builds the named synthetic workload, runs cudaConvolutionFFT-equivalent calls through
@@ -24,7 +24,7 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 2; } } while (0)
 #define FC(x) do { int r_ = (x); if (r_ != 0) { fprintf(stderr, "fftconv error %d: %s\n", r_, fftconv_last_error()); return 3; } } while (0)
 
-struct Cfg { int H, W, F, kh, kw, K; const char* name; };
+struct Cfg { int H, W, F, kh, kw, K; const char* name; int N = 1; };   // N > 1: batched images (fftconv_conv_batch)
 
 int main(int argc, char** argv) {
     Cfg c{256, 256, 31, 16, 16, 1000, "c2"};
@@ -39,16 +39,21 @@ int main(int argc, char** argv) {
             else if (n == "c2") c = Cfg{256, 256, 31, 16, 16, 1000, "c2"};
             else if (n == "c3") c = Cfg{4096, 4096, 1, 512, 512, 64, "c3"};
             else if (n == "c3s") c = Cfg{1024, 1024, 1, 128, 128, 16, "c3s"};
+            else if (n == "c4") c = Cfg{512, 512, 32, 32, 32, 256, "c4", 64};
+            else if (n == "c4s") c = Cfg{512, 512, 32, 32, 32, 256, "c4s", 8};
             else { fprintf(stderr, "unknown config %s\n", n.c_str()); return 1; }
         } else if (a == "--H") c.H = next(); else if (a == "--W") c.W = next(); else if (a == "--F") c.F = next();
         else if (a == "--kh") c.kh = next(); else if (a == "--kw") c.kw = next(); else if (a == "--K") c.K = next();
+        else if (a == "--N") c.N = next();
         else if (a == "--iters") iters = next(); else if (a == "--check") check = next();
         else if (a == "--device") device = next(); else if (a == "--host") host = true;
         else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 1; }
     }
     const int FH = fftconv_fft_size16(c.H + c.kh - 1), FW = fftconv_fft_size16(c.W + c.kw - 1), CH = FH / 2 + 1;
-    const size_t nd = (size_t)c.H * c.W * c.F, nk1 = (size_t)c.kh * c.kw * c.F, plane = (size_t)FH * FW;
-    printf("%s  %s: data %dx%dx%d, %d templates %dx%dx%d, plane %dx%d\n", fftconv_version(), c.name, c.H, c.W, c.F,
+    if (c.N < 1) c.N = 1;
+    if (c.N > 1 && (host || check > 0)) { fprintf(stderr, "--host / --check are single-image options\n"); return 1; }
+    const size_t nd = (size_t)c.H * c.W * c.F * c.N, nk1 = (size_t)c.kh * c.kw * c.F, plane = (size_t)FH * FW;
+    printf("%s  %s: %d x data %dx%dx%d, %d templates %dx%dx%d, plane %dx%d\n", fftconv_version(), c.name, c.N, c.H, c.W, c.F,
            c.K, c.kh, c.kw, c.F, FH, FW);
 
     std::mt19937 rng(2);
@@ -62,7 +67,7 @@ int main(int argc, char** argv) {
     float *d_data, *d_bank, *d_out;
     fftconv_float2* d_spec;
     CK(cudaMalloc(&d_data, nd * 4)); CK(cudaMalloc(&d_bank, nk1 * c.K * 4));
-    CK(cudaMalloc(&d_out, plane * c.K * 4)); CK(cudaMalloc(&d_spec, sizeof(fftconv_float2) * (size_t)CH * FW * c.F));
+    CK(cudaMalloc(&d_out, plane * c.K * c.N * 4)); CK(cudaMalloc(&d_spec, sizeof(fftconv_float2) * (size_t)CH * FW * c.F));
     CK(cudaMemcpy(d_data, h_data.data(), nd * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_bank, h_bank.data(), nk1 * c.K * 4, cudaMemcpyHostToDevice));
 
@@ -74,9 +79,17 @@ int main(int argc, char** argv) {
         CK(cudaMallocHost(&h_out, plane * c.K * 4));
         for (int k = 0; k < c.K; ++k) { kp[k] = h_bank.data() + nk1 * k; op[k] = h_out + plane * k; }
     }
+    std::vector<const float*> bkp(c.K);
+    std::vector<float*> bop((size_t)c.K * c.N);
+    std::vector<unsigned char> ond(c.K, 1);
+    for (int k = 0; k < c.K; ++k) bkp[k] = d_bank + nk1 * k;
+    for (size_t i = 0; i < bop.size(); ++i) bop[i] = d_out + plane * i;
     cudaStream_t st;
     CK(cudaStreamCreate(&st));
     auto step = [&]() -> int {
+        if (c.N > 1)       // batched images: the images add tiles to the per-bin tensor-core GEMM
+            return fftconv_conv_batch(d_data, 1, c.N, c.H, c.W, c.F, c.kh, c.kw, c.K, bkp.data(), khs.data(), kws.data(),
+                                      nullptr, ond.data(), bop.data(), 1, nullptr, device, st);
         if (host)
             return fftconv_convolution_fft(h_data.data(), 0, c.H, c.W, c.F, c.kh, c.kw, c.K, kp.data(), khs.data(),
                                            kws.data(), nullptr, nullptr, op.data(), 0, nullptr, 0, nullptr, device, st);
@@ -98,7 +111,11 @@ int main(int argc, char** argv) {
     CK(cudaEventElapsedTime(&ev_ms, e0, e1));
     const double ms = host ? wall_ms : ev_ms / iters;
     printf("%s path: %.3f ms per call, %.3e conv outputs/s, %lld kernel launches so far\n", host ? "host->host" : "device-resident",
-           ms, (double)c.K * plane / (ms * 1e-3), fftconv_launch_count());
+           ms, (double)c.N * c.K * plane / (ms * 1e-3), fftconv_launch_count());
+    // compulsory bytes: every input read once, every output written once
+    const double a_bytes = 4.0 * nd + 4.0 * nk1 * c.K + 4.0 * c.N * c.K * plane;
+    printf("algorithmic bytes %.1f MB -> %.1f GB/s = %.1f %% of the 6.55 TB/s measured HBM copy bandwidth\n", a_bytes / 1e6,
+           a_bytes / (ms * 1e-3) / 1e9, 100.0 * a_bytes / (ms * 1e-3) / 6.55e12);
 
     if (check > 0) {
         std::vector<float> out(plane * c.K);
