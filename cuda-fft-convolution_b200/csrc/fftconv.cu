@@ -1,5 +1,6 @@
 // libfftconv.so — C ABI + host schedule of the B200-native FFT-convolution engine.
 // See include/fftconv.h for the contract and the reference lines each entry point replaces.
+#include <cuda.h>            // CUtensorMap types only: the driver entry point is fetched through the runtime
 #include <cuda_runtime.h>
 
 #include <atomic>
@@ -203,6 +204,7 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(os_data_fft)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_inverse_tma)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
 #define BP_OPTIN(NT, TU, MINB) \
         if (opt_in_smem(bp_conv_w<false, false, NT, TU, MINB>)) return FFTCONV_ERR_CUDA; \
@@ -477,6 +479,36 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
     return true;
 }
 
+static int os_env_int(const char* name, int dflt);
+// gather of the product spectra in the inverse: 1 = TMA tensor copies (os_inverse_tma), 0 = per-thread cp.async
+// (os_inverse); FFTCONV_OS_INV_TMA is an A/B switch
+static bool os_inv_tma() { return os_env_int("FFTCONV_OS_INV_TMA", 1) != 0; }
+
+// CUtensorMap of P seen as {RS floats, 64 columns, rows}, box {8, 64, 1}.  cuTensorMapEncodeTiled is fetched through the
+// runtime (cudaGetDriverEntryPoint): the library does not link libcuda.
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nrows, OsTensorMap* out) {
+    static PFN_tmapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = (PFN_tmapEncodeTiled)fn;
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(OsTensorMap), "tensor map size");
+    const cuuint64_t gdim[3] = {(cuuint64_t)RS, 64, (cuuint64_t)nrows};
+    const cuuint64_t gstride[2] = {(cuuint64_t)RS * 4, (cuuint64_t)RS * 4 * 64};
+    const cuuint32_t box[3] = {8, 64, 1}, estride[3] = {1, 1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P), gdim,
+                              gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
 static int os_env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
@@ -596,12 +628,21 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
         a.peak_keys = peak_keys; a.khw = khw; a.H = H; a.W = W;
         a.corr = (opt.correlate && !peak_keys) ? 1 : 0;
+        a.dbg_nogather = os_env_int("FFTCONV_OS_INV_NOGATHER", 0);
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
-        dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
         ProfScope ps(PK_OS_INV, st);
-        os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);
+        if (os_inv_tma()) {
+            OsTensorMap tm;
+            const int ntb = (nk + OS_TM - 1) / OS_TM;
+            if (int e = os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_CH * OS_TM, &tm)) return e;
+            dim3 grid(g.NNB * (g.RS / 8), nk);             // (tile block, group of 4 tiles) x template
+            os_inverse_tma<<<grid, 256, OS_ITMA_SMEM, st>>>(a, tm);
+        } else {
+            dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
+            os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);
+        }
         LAUNCH_CHECK();
     }
     return 0;

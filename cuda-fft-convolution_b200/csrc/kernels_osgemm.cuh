@@ -779,6 +779,7 @@ struct OsInvArgs {
     unsigned long long* peak_keys;
     const int2* khw;        // (kh, kw) per template of the chunk (peak and correlation modes)
     int H, W;
+    int dbg_nogather;       // timing experiments only (FFTCONV_OS_INV_NOGATHER): 1 = skip the gather of P, 2 = gather only
     int corr;               // correlation mode: plane position (Y, X) of the flipped-template convolution is stored at
                             // ((Y - kh + 1) mod FH, (X - kw + 1) mod FW)
 };
@@ -847,7 +848,7 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         const int v = threadIdx.x >> OS_IGB;
         const int m = m0 + gq;
         cpx* dst = buf + gq * OS_ITILE + os_icol(v);
-        if (m < a.NT) {
+        if (m < a.NT && a.dbg_nogather != 1) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
             const size_t ustride = (size_t)OS_TM * 32 * a.RS;              // cpx units; P[tblk][nblk][u][template][v][RS]
             const cpx* pp = reinterpret_cast<const cpx*>(
@@ -865,6 +866,7 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
+    if (a.dbg_nogather == 2) return;
     // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
     //     col0[u] := Z[u][0] + i Z[u][32],   col32[u] := Z[u][0] - i Z[u][32]
     if (threadIdx.x < OS_IG * 33) {
@@ -915,6 +917,197 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
             if (v < 32) { const cpx p = ty[os_icol(v)], q = ty[os_icol(64 - v)]; return make_float2(p.x - q.y, p.y + q.x); }
             const cpx p = ty[os_icol(64 - v)], q = ty[os_icol(v)];
             return make_float2(p.x + q.y, q.x - p.y);
+        };
+        auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
+        if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
+        else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
+        const int ny = tile_ny[gq], nx = tile_nx[gq];
+        const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
+        const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
+        if (a.peak_keys) {
+            float best = -INFINITY; int by = 0, bx = 0;
+            auto upd = [&](float v, int yy, int xx) { if (v > best) { best = v; by = yy; bx = xx; } };
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {                             // ascending x: the first maximum wins
+                const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+                if (xa >= 0 && xa < nx) { if (wlo) upd(reA[j1], ylo, xa); if (whi) upd(imA[j1], yhi, xa); }
+                if (xb >= 0 && xb < nx) { if (wlo) upd(reB[j1], ylo, xb); if (whi) upd(imB[j1], yhi, xb); }
+            }
+            unsigned long long key = best > -INFINITY ? os_peak_key(best, tile_y0[gq] + by, tile_x0[gq] + bx) : 0ull;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                key = other > key ? other : key;
+            }
+            if (lane == 0 && key) atomicMax(a.peak_keys + t, key);
+            return;
+        }
+        if (a.corr) {
+            const int2 k = a.khw[t];
+            float* base = tile_dst[gq];
+            int ydl = tile_y0[gq] + ylo - (k.x - 1), ydh = tile_y0[gq] + yhi - (k.x - 1);
+            if (ydl < 0) ydl += a.FH;
+            if (ydh < 0) ydh += a.FH;
+            const bool slo = wlo && ydl < a.crop_h, shi = whi && ydh < a.crop_h;
+            const int xs = tile_x0[gq] - (k.y - 1);
+            auto put = [&](int xr, float vlo, float vhi) {
+                if (xr < 0 || xr >= nx) return;
+                int xd = xs + xr;
+                if (xd < 0) xd += a.FW;
+                if (xd >= a.crop_w) return;
+                float* d = base + (size_t)xd * a.out_ld;
+                if (slo) d[ydl] = vlo;
+                if (shi) d[ydh] = vhi;
+            };
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                put(4 * j1 + par - a.ox0, reA[j1], imA[j1]);
+                put(4 * j1 + par + 2 - a.ox0, reB[j1], imB[j1]);
+            }
+            return;
+        }
+        float* dst = tile_dst[gq] + ylo;
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) {
+            const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+            if (xa >= 0 && xa < nx) {
+                float* d = dst + (size_t)xa * a.out_ld;
+                if (wlo) d[0] = reA[j1];
+                if (whi) d[32] = imA[j1];
+            }
+            if (xb >= 0 && xb < nx) {
+                float* d = dst + (size_t)xb * a.out_ld;
+                if (wlo) d[0] = reB[j1];
+                if (whi) d[32] = imB[j1];
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// os_inverse_tma: same transform as os_inverse; the gather is done by the TMA engine.
+// P keeps the bin-major layout os_gemm streams out (P[tblk][nblk][u][template][v][RS]); seen as a 3-D tensor
+// {RS floats, 64 columns v, rows (tblk, nblk, u, template)} the 4 tiles of a group are a box {8, 64, 1}: 64 pieces of 32
+// bytes, 320 bytes apart.  One thread issues 33 tensor copies (cp.async.bulk.tensor.3d, one mbarrier) instead of the CTA
+// issuing 8 448 eight-byte cp.async — that issue was os_inverse's top stall (mio_throttle) and on its own ran at 2.1 TB/s.
+// The box lands dense, [u][v][tile] (2 KB per row, 128-byte aligned as the tensor copy requires):
+//   pass 1   lane = (column within a block of 8, tile): every access of a warp is 256 contiguous bytes.  All inputs are in
+//            registers when the block barrier falls, so the results are written in os_inverse's per-tile layout
+//            (column stride 33) over the same buffer;
+//   pass 2   and the store are os_inverse's: lanes along h, one warp per tile, every store instruction writes one
+//            contiguous run of a plane column.
+constexpr int OS_TROW = 256;          // complex pitch of a landed row: 64 columns x 4 tiles
+constexpr int OS_ITMA_SMEM = (OS_IG * OS_ITILE > OS_CH * OS_TROW ? OS_IG * OS_ITILE : OS_CH * OS_TROW) * 8;
+
+__device__ __forceinline__ void os_tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
+struct alignas(64) OsTensorMap { unsigned long long opaque[16]; };       // CUtensorMap (128 bytes), built on the host
+
+__global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __grid_constant__ OsTensorMap tmap)
+{
+    extern __shared__ __align__(128) unsigned char os_smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float* tile_dst[OS_IG];
+    __shared__ int tile_ny[OS_IG], tile_nx[OS_IG], tile_y0[OS_IG], tile_x0[OS_IG], tile_ok[OS_IG];
+    const int t = blockIdx.y;
+    const int NG = a.RS >> 3;
+    const int nblk = blockIdx.x / NG, g = blockIdx.x - nblk * NG;
+    const int mbase = nblk * a.NTn + 4 * g;                                // first tile of the group
+    const int tblk = t / OS_TM, tl = t - tblk * OS_TM;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < OS_IG) {
+        const int m = mbase + threadIdx.x;
+        const bool ok = 4 * g + (int)threadIdx.x < a.NTn && m < a.NT;
+        float* d = nullptr; int ny = 0, nx = 0;
+        if (ok) {
+            const int img = m / a.NTimg, mt = m - img * a.NTimg;
+            const int tj = mt / a.nth, ti = mt - tj * a.nth;
+            const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
+            if (a.peak_keys) {                    // region of the full linear convolution of THIS template
+                const int2 k = a.khw[t];
+                ny = min(a.Sh, a.H + k.x - 1 - Y0); nx = min(a.Sw, a.W + k.y - 1 - X0);
+                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+            } else if (a.corr) {
+                ny = min(a.Sh, a.FH - Y0); nx = min(a.Sw, a.FW - X0);
+                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+                d = a.outs[(size_t)img * a.out_img_stride + t];
+            } else {
+                ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
+                d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
+            }
+        }
+        tile_dst[threadIdx.x] = d; tile_ny[threadIdx.x] = ny; tile_nx[threadIdx.x] = nx; tile_ok[threadIdx.x] = ok ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- gather: 33 boxes {4 tiles, 64 columns, 1 row}, one thread, all in flight at once
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, OS_CH * 2048u);
+        const int row0 = ((tblk * a.NNB + nblk) * OS_CH) * OS_TM + tl;     // row of u = 0; rows of one u are OS_TM apart
+#pragma unroll 1
+        for (int u = 0; u < OS_CH; ++u) os_tma_load_3d(buf + u * OS_TROW, &tmap, 8 * g, 0, row0 + u * OS_TM, &bar);
+    }
+    mbar_wait(&bar, 0);
+    // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
+    //     col0[u] := Z[u][0] + i Z[u][32],   col32[u] := Z[u][0] - i Z[u][32]
+    if (threadIdx.x < OS_IG * 33) {
+        const int q = threadIdx.x & 3, u = threadIdx.x >> 2;
+        cpx* c0 = buf + u * OS_TROW + q;
+        cpx* c32 = c0 + 4 * 32;
+        const cpx za = *c0, zb = *c32;
+        *c0 = make_float2(za.x - zb.y, za.y + zb.x);
+        *c32 = make_float2(za.x + zb.y, za.y - zb.x);
+    }
+    __syncthreads();
+    const int par = warp >> OS_IGB;                                        // warp-uniform: tasks (par, par + 2)
+    // ---- pass 1: inverse along h.  x[u] = col_v[u] (u <= 32), conj(col_mv[64-u]) (u > 32); landed layout in,
+    //      per-tile layout out (tile q at q * OS_ITILE, column v at os_icol(v))
+    {
+        const int q = lane & 3;
+        const int v = 8 * (warp & 3) + (lane >> 2), mv = v ? 64 - v : 32;
+        const cpx* cv = buf + q + 4 * v;                                   // element u: cv[u * OS_TROW]
+        const cpx* cm = buf + q + 4 * mv;
+        float reA[16], imA[16], reB[16], imB[16];
+        auto ld1 = [&](int u) -> cpx {
+            if (u <= 32) return cv[u * OS_TROW];
+            const cpx z = cm[(64 - u) * OS_TROW];
+            return make_float2(z.x, -z.y);
+        };
+        auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
+        if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
+        else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
+        __syncthreads();                                                   // every input of the CTA has been read
+        cpx* ov = buf + q * OS_ITILE + os_icol(v);
+        cpx* om = buf + q * OS_ITILE + os_icol(mv);
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) {                                  // Y[y]: y < 32 -> col v, y >= 32 -> col mv
+            const int ya = 4 * j1 + par, yb = ya + 2;                      // (compile-time split: j1 < 8 <=> y < 32)
+            if (j1 < 8) { ov[ya] = make_float2(reA[j1], imA[j1]); ov[yb] = make_float2(reB[j1], imB[j1]); }
+            else        { om[ya - 32] = make_float2(reA[j1], imA[j1]); om[yb - 32] = make_float2(reB[j1], imB[j1]); }
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: C2R along w.  W[v] = Y[y][v] + i Y[y+32][v]; outputs straight to the plane (as os_inverse)
+    {
+        const int gq = warp & (OS_IG - 1);                                 // one warp = the 32 lines of one tile
+        const cpx* tile = buf + gq * OS_ITILE;
+        const int y = lane;
+        if (!tile_ok[gq]) return;                                          // warp-uniform (no barrier below)
+        const cpx* ty = tile + y;
+        float reA[16], imA[16], reB[16], imB[16];
+        auto ld1 = [&](int v) -> cpx {
+            if (v == 0) { const cpx p0 = ty[os_icol(0)], p32 = ty[os_icol(32)]; return make_float2(p0.x, p32.x); }
+            if (v == 32) { const cpx p0 = ty[os_icol(0)], p32 = ty[os_icol(32)]; return make_float2(p0.y, p32.y); }
+            if (v < 32) { const cpx p = ty[os_icol(v)], z = ty[os_icol(64 - v)]; return make_float2(p.x - z.y, p.y + z.x); }
+            const cpx p = ty[os_icol(64 - v)], z = ty[os_icol(v)];
+            return make_float2(p.x + z.y, z.x - p.y);
         };
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
