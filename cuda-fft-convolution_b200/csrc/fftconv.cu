@@ -206,18 +206,12 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse_tma)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
-#define BP_OPTIN(NT, TU, MINB) \
-        if (opt_in_smem(bp_conv_w<false, false, NT, TU, MINB>)) return FFTCONV_ERR_CUDA; \
-        if (opt_in_smem(bp_conv_w<true, false, NT, TU, MINB>)) return FFTCONV_ERR_CUDA;
-        BP_OPTIN(256, 2, 2) BP_OPTIN(512, 4, 1) BP_OPTIN(256, 4, 1)
-#undef BP_OPTIN
+        if (opt_in_smem(bp_conv_w<false, false, 512, 4, 1>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(bp_conv_w<true, false, 512, 4, 1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_conv_w<false, true, 512, 2, 1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_conv_w<true, true, 512, 2, 1>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_kern_h<1>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_inv_h<1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_kern_h<2>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_inv_h<2>)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(bp_inv_h<3>)) return FFTCONV_ERR_CUDA;
         c.inited = true;
     }
     *out = &c;
@@ -628,15 +622,14 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
         a.peak_keys = peak_keys; a.khw = khw; a.H = H; a.W = W;
         a.corr = (opt.correlate && !peak_keys) ? 1 : 0;
-        a.dbg_nogather = os_env_int("FFTCONV_OS_INV_NOGATHER", 0);
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
         ProfScope ps(PK_OS_INV, st);
-        if (os_inv_tma()) {
-            OsTensorMap tm;
-            const int ntb = (nk + OS_TM - 1) / OS_TM;
-            if (int e = os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_CH * OS_TM, &tm)) return e;
+        OsTensorMap tm;
+        const int ntb = (nk + OS_TM - 1) / OS_TM;
+        // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
+        if (os_inv_tma() && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_CH * OS_TM, &tm) == 0) {
             dim3 grid(g.NNB * (g.RS / 8), nk);             // (tile block, group of 4 tiles) x template
             os_inverse_tma<<<grid, 256, OS_ITMA_SMEM, st>>>(a, tm);
         } else {
@@ -764,9 +757,8 @@ static bool make_ip_plan(int n, IpPlan& p) {
     for (int r : odd)
         while (o % r == 0) { if (!push(r)) return false; o /= r; }
     if (o != 1) return false;                     // a prime factor above 17: stay on the generic path
-    const int maxr = os_env_int("FFTCONV_BP_MAXR", 32);
-    const int maxbits = maxr >= 32 ? 5 : (maxr >= 16 ? 4 : 3);
-    const int nst = (e + maxbits - 1) / maxbits;  // radices 4 / 8 / 16 (/ 32)
+    const int nst = (e + 4) / 5;                  // as few power-of-two stages as radices <= 32 allow, evenly split
+                                                  // (measured at 4608 = 9 * 512: [9, 32, 16] 4.7 ms, [9, 8, 8, 8] 6.2 ms per 16 templates)
     for (int i = 0; i < nst; ++i) {
         const int bits = e / nst + (i < e % nst ? 1 : 0);
         if (!push(1 << bits)) return false;
@@ -838,7 +830,7 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
     const int maxcols4 = (maxcols + 3) & ~3;
     IpPlan pH, pW;
     make_ip_plan(FH, pH); make_ip_plan(FW, pW);
-    pH.tws = os_env_int("FFTCONV_BP_TWS_H", 0); pW.tws = os_env_int("FFTCONV_BP_TWS_W", 1);
+    pH.tws = 0; pW.tws = 1;      // shared-memory twiddle table for the later stages of the w pass (neutral for the h passes)
     const cpx *twH, *twW;
     const unsigned short *posH, *natH, *posW, *natW;
     if (int e = get_twiddles(c, FH, st, &twH)) return e;
@@ -850,25 +842,21 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
     {
         dim3 grid(maxcols4 / 4, nk * F);
         ProfScope ps(PK_BP_KERN_H, st);
-        if (os_env_int("FFTCONV_BP_HOCC", 2) >= 2)
-            bp_kern_h<2><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
-        else
-            bp_kern_h<1><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
+        bp_kern_h<2><<<grid, 256, smemH, st>>>(d_descs, F, maxcols4, FH, CH, CHp, pH, twH, posH, (cpx*)c.T.p, ldH);
         LAUNCH_CHECK();
     }
     {
+        // single channel: 4 lines (whole 32-byte sectors), product in place; several channels: 2 lines + 2 accumulator
+        // lines.  512 threads, one CTA per SM (measured alternatives at config 3, per 16 templates: 256 threads 3.8 ms,
+        // two 2-line CTAs per SM 3.5 ms, against 3.0 ms)
         const bool multi = F > 1;
-        const int tu = multi ? 2 : (os_env_int("FFTCONV_BP_TU", 4) >= 4 ? 4 : 2);
-        const int threads = os_env_int("FFTCONV_BP_THREADS", 512);
-        dim3 grid(tu == 4 ? nk : 2 * nk, CHp / 4);
-        const size_t smem = (multi ? 4 : tu) * (size_t)ldW * sizeof(cpx) + kBpTwBytes;
+        dim3 grid(multi ? 2 * nk : nk, CHp / 4);
+        const size_t smem = 4 * (size_t)ldW * sizeof(cpx) + kBpTwBytes;
         ProfScope ps(PK_BP_CONV_W, st);
         const cpx* T = (const cpx*)c.T.p; const cpx* Sp = (const cpx*)c.bpS.p; cpx* Z = (cpx*)c.Z.p;
-#define BP_LAUNCH(CONJ, MULTI, NT, TU, MINB) bp_conv_w<CONJ, MULTI, NT, TU, MINB><<<grid, NT, smem, st>>>(T, d_kcols, maxcols4, Sp, F, FW, CHp, pW, twW, Z, ldW)
-        if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, 512, 2, 1); else BP_LAUNCH(false, true, 512, 2, 1); }
-        else if (tu == 2) { if (a.opt.correlate) BP_LAUNCH(true, false, 256, 2, 2); else BP_LAUNCH(false, false, 256, 2, 2); }
-        else if (threads >= 512) { if (a.opt.correlate) BP_LAUNCH(true, false, 512, 4, 1); else BP_LAUNCH(false, false, 512, 4, 1); }
-        else { if (a.opt.correlate) BP_LAUNCH(true, false, 256, 4, 1); else BP_LAUNCH(false, false, 256, 4, 1); }
+#define BP_LAUNCH(CONJ, MULTI, TU) bp_conv_w<CONJ, MULTI, 512, TU, 1><<<grid, 512, smem, st>>>(T, d_kcols, maxcols4, Sp, F, FW, CHp, pW, twW, Z, ldW)
+        if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, 2); else BP_LAUNCH(false, true, 2); }
+        else { if (a.opt.correlate) BP_LAUNCH(true, false, 4); else BP_LAUNCH(false, false, 4); }
 #undef BP_LAUNCH
         LAUNCH_CHECK();
     }
@@ -878,12 +866,7 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
         const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
         dim3 grid(FW / 4, nk);
         ProfScope ps(PK_BP_INV_H, st);
-        if (os_env_int("FFTCONV_BP_HOCC", 2) >= 3)
-            bp_inv_h<3><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
-        else if (os_env_int("FFTCONV_BP_HOCC", 2) >= 2)
-            bp_inv_h<2><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
-        else
-            bp_inv_h<1><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
+        bp_inv_h<2><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
         LAUNCH_CHECK();
     }
     return 0;

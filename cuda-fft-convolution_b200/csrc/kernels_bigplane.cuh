@@ -303,10 +303,9 @@ __global__ void __launch_bounds__(256, MINB) bp_kern_h(const SrcDesc* __restrict
 // ------------------------------------------------------------------------------- bp_conv_w
 // Template index fastest in the grid: the CTAs resident at any moment share a handful of h-bin tiles, so the data
 // spectrum is read from HBM once per call, not once per template.
-// TU = 4: grid (nk, CHp / 4), one CTA per SM owns whole 32-byte sectors (4 h-bins of every column).
-// TU = 2: grid (2 nk, CHp / 4), TWO CTAs per SM (single channel) — the two halves of a sector belong to CTAs that are
-//         neighbours in launch order, so they meet in L2; the load / transform / product / store phases of the two
-//         CTAs overlap.  MULTI adds TU accumulator lines (channel sum in the frequency domain).
+// TU = 4: grid (nk, CHp / 4), single channel: one CTA per SM owns whole 32-byte sectors (4 h-bins of every column).
+// TU = 2: grid (2 nk, CHp / 4), MULTI: 2 lines + 2 accumulator lines (channel sum in the frequency domain); the two
+//         halves of a sector belong to CTAs that are neighbours in launch order, so they meet in L2.
 template <bool CONJ, bool MULTI, int NT, int TU, int MINB>
 __global__ void __launch_bounds__(NT, MINB) bp_conv_w(const cpx* __restrict__ T, const int* __restrict__ kcols, int maxcols4,
                                                     const cpx* __restrict__ Sp, int F, int FW, int CHp,

@@ -779,7 +779,6 @@ struct OsInvArgs {
     unsigned long long* peak_keys;
     const int2* khw;        // (kh, kw) per template of the chunk (peak and correlation modes)
     int H, W;
-    int dbg_nogather;       // timing experiments only (FFTCONV_OS_INV_NOGATHER): 1 = skip the gather of P, 2 = gather only
     int corr;               // correlation mode: plane position (Y, X) of the flipped-template convolution is stored at
                             // ((Y - kh + 1) mod FH, (X - kw + 1) mod FW)
 };
@@ -848,7 +847,7 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         const int v = threadIdx.x >> OS_IGB;
         const int m = m0 + gq;
         cpx* dst = buf + gq * OS_ITILE + os_icol(v);
-        if (m < a.NT && a.dbg_nogather != 1) {
+        if (m < a.NT) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
             const size_t ustride = (size_t)OS_TM * 32 * a.RS;              // cpx units; P[tblk][nblk][u][template][v][RS]
             const cpx* pp = reinterpret_cast<const cpx*>(
@@ -866,7 +865,6 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
-    if (a.dbg_nogather == 2) return;
     // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
     //     col0[u] := Z[u][0] + i Z[u][32],   col32[u] := Z[u][0] - i Z[u][32]
     if (threadIdx.x < OS_IG * 33) {

@@ -1,5 +1,5 @@
-"""Config 3 (4096^2 x K kernels 512^2) on the large-plane path under the tuning knobs of kernels_bigplane.cuh.
-python scripts/c3_variants.py [K]"""
+"""Config 3 (4096^2 x K kernels 512^2) on the large-plane path: device-resident time and per-kernel breakdown.
+python scripts/c3_time.py [K]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-fft-convolution_b200")]
@@ -14,10 +14,7 @@ FH = FW = 4608
 spec = fc.fft_data_device(data, H, W, F, kh, kw)
 out = torch.empty((K, FW, FH), device="cuda")
 ref = torch.fft.irfft2(torch.fft.rfft2(data.double(), s=(FW, FH)) * torch.fft.rfft2(bank[:1].double(), s=(FW, FH)), s=(FW, FH)).sum(1)
-variants = []
-for spec_ in (sys.argv[2:] or ["512,32,2"]):
-    t, r, h, tu, twh, tww = (spec_.split(",") + ["4", "0", "1"])[:6]
-    variants.append(dict(FFTCONV_BP_THREADS=t, FFTCONV_BP_MAXR=r, FFTCONV_BP_HOCC=h, FFTCONV_BP_TU=tu, FFTCONV_BP_TWS_H=twh, FFTCONV_BP_TWS_W=tww))
+variants = [dict()]
 for v in variants:
     os.environ.update(v)
     fc.lib().fftconv_release()
