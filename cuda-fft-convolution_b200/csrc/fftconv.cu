@@ -181,6 +181,13 @@ static int ctx_get(int device, Ctx** out) {
                 h_tw[r][j] = make_float2((float)cos(a), (float)sin(a));
             }
         CU(cudaMemcpyToSymbol(c_odd_tw, h_tw, sizeof h_tw));
+        {   // w64^(r0 c) for the run-time-residue transform task of os_kern_fft (same constexpr series as the compile-time twiddles)
+            static float2 h_w64[4][16];
+            for (int r0 = 0; r0 < 4; ++r0)
+                for (int cc = 0; cc < 16; ++cc)
+                    h_w64[r0][cc] = make_float2((float)os_cos64d((r0 * cc) & 63), (float)os_sin64d((r0 * cc) & 63));
+            CU(cudaMemcpyToSymbol(c_os_w64, h_w64, sizeof h_w64));
+        }
         CU(cudaEventCreateWithFlags(&c.pinned_free, cudaEventDisableTiming));
         for (auto& e : c.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));

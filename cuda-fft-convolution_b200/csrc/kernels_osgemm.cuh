@@ -115,6 +115,38 @@ __device__ __forceinline__ void os_fft64_task(Load&& ld, float* re, float* im) {
     });
     dft_regs<16, INV>(re, im);
 }
+// The same task with the residue r0 as a RUN-TIME, warp-uniform value: the twiddles w64^{r0 c} come from a constant-memory
+// table (one uniform constant load each) instead of being folded into the instruction stream.  os_kern_fft used to
+// inline 12 compile-time specialisations of the task (10 128 instructions = 162 KB of SASS, more than the instruction
+// cache holds: `no_instruction` was its top stall at 7 warps per issue cycle); with this form it inlines 3.
+// c_os_w64[r0][c] = (cos, sin)(2 pi r0 c / 64), filled by the host from the same constexpr series (os_cos64d / os_sin64d).
+__constant__ float2 c_os_w64[4][16];
+
+template <int NF, class Load>
+__device__ __forceinline__ void os_fft64_task_dyn(int r0, Load&& ld, float* re, float* im) {
+    const float2* tw = c_os_w64[r0];
+    os_static_for<0, 8>([&](auto c2c) {
+        constexpr int c2 = decltype(c2c)::value;
+        float sr0 = 0.f, si0 = 0.f, sr1 = 0.f, si1 = 0.f;
+        os_static_for<0, NF>([&](auto qc) {
+            constexpr int q = decltype(qc)::value;
+            const float4 v = ld(2 * c2 + 16 * q);
+            if (q == 0) { sr0 = v.x; si0 = v.y; sr1 = v.z; si1 = v.w; }
+            else {                                   // (x + i y) (-i)^(r0 q), q = 1: k = r0
+                const int k = (r0 * q) & 3;
+                const float ax = (k & 1) ? v.y : v.x, ay = (k & 1) ? -v.x : v.y;      // k odd: (y, -x)
+                const float bx = (k & 1) ? v.w : v.z, by = (k & 1) ? -v.z : v.w;
+                const float sg = (k & 2) ? -1.f : 1.f;                                    // k = 2: (-x, -y); k = 3: (-y, x) = -(y, -x)
+                sr0 += sg * ax; si0 += sg * ay; sr1 += sg * bx; si1 += sg * by;
+            }
+        });
+        const float2 w0 = tw[2 * c2], w1 = tw[2 * c2 + 1];                             // (sr + i si)(c - i s)
+        re[2 * c2] = fmaf(si0, w0.y, sr0 * w0.x);     im[2 * c2] = fmaf(-sr0, w0.y, si0 * w0.x);
+        re[2 * c2 + 1] = fmaf(si1, w1.y, sr1 * w1.x); im[2 * c2 + 1] = fmaf(-sr1, w1.y, si1 * w1.x);
+    });
+    dft_regs<16, false>(re, im);
+}
+
 // r0 is warp-uniform at every call site, so the switch does not diverge
 template <int NF, bool INV, class Load>
 __device__ __forceinline__ void os_fft64_task_rt(int r0, Load&& ld, float* re, float* im) {
@@ -266,17 +298,15 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
                 auto put = [&](int ro, float zr, float zi, float nr, float ni) {
                     hrow[ro * NCP] = make_float4(0.5f * (zr + nr), 0.5f * (zi - ni), 0.5f * (zi + ni), -0.5f * (zr - nr));
                 };
+                os_fft64_task_dyn<NF>(ph == 0 ? 1 : 0, ld, pr, pi);   // Z[4 j1 + 1]  |  Z[4 j1]
+                os_fft64_task_dyn<NF>(ph == 0 ? 3 : 2, ld, qr, qi);   // Z[4 j1 + 3]  |  Z[4 j1 + 2]
                 if (ph == 0) {
-                    os_fft64_task<1, NF, false>(ld, pr, pi);          // Z[4 j1 + 1]
-                    os_fft64_task<3, NF, false>(ld, qr, qi);          // Z[4 j1 + 3]
 #pragma unroll
                     for (int j1 = 0; j1 < 8; ++j1) {
                         put(2 * j1, pr[j1], pi[j1], qr[15 - j1], qi[15 - j1]);          // u = 4 j1 + 1
                         put(2 * j1 + 1, qr[j1], qi[j1], pr[15 - j1], pi[15 - j1]);      // u = 4 j1 + 3
                     }
                 } else {
-                    os_fft64_task<0, NF, false>(ld, pr, pi);          // Z[4 j1]
-                    os_fft64_task<2, NF, false>(ld, qr, qi);          // Z[4 j1 + 2]
 #pragma unroll
                     for (int j1 = 0; j1 < 9; ++j1) put(2 * j1, pr[j1], pi[j1], pr[(16 - j1) & 15], pi[(16 - j1) & 15]);   // u = 4 j1
 #pragma unroll
@@ -297,19 +327,19 @@ __global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
             const int slot = lane & 15;
             if (ro >= NR) continue;
             const int u = ph == 0 ? 2 * ro + 1 : 2 * ro;
+            float* base = a.img + ((size_t)tblk * OS_NBIN + (size_t)u * 64 + r0) * bin_stride + (size_t)ks * stage_floats +
+                          (size_t)kc * OS_TM * 4 + (size_t)(sl0 + slot) * 4;
             float re0[16], im0[16], re1[16], im1[16];
             {
                 const float4* row = reinterpret_cast<const float4*>(Hs + (size_t)slot * PS + ro * XC);
                 auto ld = [&](int j) { return row[j >> 1]; };
-                os_fft64_task_rt<NF, false>(r0, ld, re0, im0);
+                os_fft64_task_dyn<NF>(r0, ld, re0, im0);
             }
             {
                 const float4* row = reinterpret_cast<const float4*>(Hs + (size_t)(16 + slot) * PS + ro * XC);
                 auto ld = [&](int j) { return row[j >> 1]; };
-                os_fft64_task_rt<NF, false>(r0, ld, re1, im1);
+                os_fft64_task_dyn<NF>(r0, ld, re1, im1);
             }
-            float* base = a.img + ((size_t)tblk * OS_NBIN + (size_t)u * 64 + r0) * bin_stride + (size_t)ks * stage_floats +
-                          (size_t)kc * OS_TM * 4 + (size_t)(sl0 + slot) * 4;
 #pragma unroll
             for (int j1 = 0; j1 < 16; ++j1)
                 *reinterpret_cast<float4*>(base + (size_t)(4 * j1) * bin_stride) = make_float4(re0[j1], im0[j1], re1[j1], im1[j1]);
