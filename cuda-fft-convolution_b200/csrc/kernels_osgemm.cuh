@@ -220,7 +220,7 @@ struct OsKArgs {
 constexpr int OS_KSL = 16;            // templates per CTA
 
 template <int NF>
-__global__ void __launch_bounds__(256) os_kern_fft(OsKArgs a)
+__global__ void __launch_bounds__(256, 2) os_kern_fft(OsKArgs a)
 {
     constexpr int XC = 16 * NF, NCP = XC / 2;
     constexpr int PS = 17 * XC + 2;                    // plane stride in cpx (+16 B: conflict-free LDS.128 across templates)
