@@ -1639,7 +1639,7 @@ long long fftconv_workspace_bytes(int device) {
     const Ctx& c = it->second;
     size_t s = c.T.cap + c.Z.cap + c.stage.cap + c.desc.cap + c.outstage.cap + c.dspec.cap + c.ddata.cap +
                c.priv.cap + c.Ag.cap + c.Wg.cap + c.osA.cap + c.osB.cap + c.osP.cap +
-               c.osPlane.cap + c.osZ.cap;
+               c.osPlane.cap + c.osZ.cap + c.osPeaks.cap + c.bpS.cap + c.batchA.cap;
     for (auto& kv : c.tw) s += sizeof(cpx) * (size_t)kv.first;
     return (long long)s;
 }
