@@ -1669,6 +1669,24 @@ void fftconv_release(void) {
     if (prev >= 0) cudaSetDevice(prev);
 }
 
+int fftconv_query_path(int H, int W, int F, int maxKH, int maxKW, int K, const fftconv_options* opt,
+                       int* radices_h, int* radices_w) {
+    g_err.clear();
+    if (H <= 0 || W <= 0 || F <= 0 || maxKH <= 0 || maxKW <= 0 || K < 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
+    const int FH = fftconv_fft_size16(H + maxKH - 1), FW = fftconv_fft_size16(W + maxKW - 1);
+    const fftconv_options o = opt ? *opt : fftconv_options{};
+    const int path = choose_path(o, F, FH, FW, std::min(maxKH, FH), std::min(maxKW, FW), K);
+    for (int side = 0; side < 2; ++side) {
+        int* out = side ? radices_w : radices_h;
+        if (!out) continue;
+        for (int i = 0; i < 8; ++i) out[i] = 0;
+        IpPlan p;
+        if (path == PATH_BIGPLANE && make_ip_plan(side ? FW : FH, p))
+            for (int i = 0; i < p.ns && i < 8; ++i) out[i] = p.R[i];
+    }
+    return path;
+}
+
 int fftconv_spectrum_ready_event(int device, void* cuda_event) {
     std::lock_guard<std::mutex> lk(g_mu);
     DeviceGuard dg(device);

@@ -42,7 +42,7 @@ EXPORTED_SYMBOLS = [
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
-    "fftconv_spectrum_ready_event",
+    "fftconv_spectrum_ready_event", "fftconv_query_path",
     "fftconv_peer_alloc", "fftconv_peer_open", "fftconv_peer_close", "fftconv_peer_free", "fftconv_peer_signal",
     "fftconv_peer_wait", "fftconv_peer_wait_all", "fftconv_peer_pull", "fftconv_peer_status",
 ]
@@ -93,6 +93,7 @@ def lib() -> ctypes.CDLL:
         c_int, c_vp, c_ll = ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong
         L.fftconv_fft_size16.argtypes = [c_int]
         L.fftconv_spectrum_ready_event.argtypes = [c_int, c_vp]
+        L.fftconv_query_path.argtypes = [c_int] * 6 + [c_vp, c_vp, c_vp]
         L.fftconv_peer_alloc.argtypes = [ctypes.c_size_t, c_int, ctypes.POINTER(c_vp), c_vp]
         L.fftconv_peer_open.argtypes = [c_vp, c_int, ctypes.POINTER(c_vp)]
         L.fftconv_peer_close.argtypes = [c_vp, c_int]

@@ -187,6 +187,13 @@ int fftconv_peer_wait_all(const unsigned long long* flags, int n, unsigned long 
 int fftconv_peer_pull(void* dst, const void* src_mapped, size_t bytes, int device, void* stream);
 int fftconv_peer_status(int device);        /* 0: no wait has timed out on this device (synchronises the device) */
 
+/* Which pipeline would serve cudaConvolutionFFT(data H x W x F, declared maximum maxKH x maxKW, K kernels of that size)
+ * under `opt` (NULL = defaults): returns fftconv_options.path numbering (1 generic, 2 16-point-tiled, 3 overlap-save +
+ * tcgen05 GEMM, 4 large plane).  For path 4 the radices of the in-place line plans along h and w are written to
+ * radices_h / radices_w (up to 8 entries, 0-terminated; either may be NULL).  Pure host logic: needs no device. */
+int fftconv_query_path(int H, int W, int F, int maxKH, int maxKW, int K, const fftconv_options* opt,
+                       int* radices_h, int* radices_w);
+
 /* Number of kernel launches issued by this library since load (bench accounting). */
 long long fftconv_launch_count(void);
 /* Per-kernel device timing for the roofline leg of bench.py: while enabled, every kernel launch is

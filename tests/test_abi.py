@@ -101,3 +101,58 @@ def test_torch_ops_register_and_infer_shapes():
     assert tuple(torch.ops.fftconv.convolution_fft(imgs, torch.empty((256, 32, 32, 32), device="meta")).shape) == (64, 256, 544, 544)
     with pytest.raises((RuntimeError, NotImplementedError)):
         torch.ops.fftconv.fft_data(torch.zeros((2, 8, 8)), 3, 3)          # CPU tensors: no fallback
+
+
+def _query(fc, H, W, F, kh, kw, K, **opt):
+    L = fc.lib()
+    rh, rw = (ctypes.c_int * 8)(), (ctypes.c_int * 8)()
+    o = fc.Options(**opt) if opt else None
+    path = L.fftconv_query_path(H, W, F, kh, kw, K, ctypes.byref(o) if o is not None else None, rh, rw)
+    return path, [r for r in rh if r], [r for r in rw if r]
+
+
+def test_pipeline_selection_host_logic(fc):
+    """Which pipeline serves which BASELINE config (pure host logic, no device): the overlap-save / tcgen05 path needs a
+    bank that fills an MMA block, small banks take the 16-point-tiled path, planes of 1024 and more with large templates
+    the in-place large-plane path, sizes with a prime factor above 17 the generic one."""
+    assert _query(fc, 256, 256, 31, 16, 16, 1000)[0] == 3          # C2
+    assert _query(fc, 256, 256, 31, 16, 16, 10)[0] == 2            # same shapes, 10 templates
+    assert _query(fc, 64, 8, 5, 10, 4, 10)[0] == 2                 # C1
+    assert _query(fc, 512, 512, 32, 32, 32, 256)[0] == 3           # C4 (per image)
+    path, rh, rw = _query(fc, 4096, 4096, 1, 512, 512, 64)         # C3: plane 4608 = 9 * 512
+    assert path == 4 and rh == [9, 32, 16] and rw == [9, 32, 16]
+    path, rh, rw = _query(fc, 1024, 1024, 3, 128, 100, 4)          # plane 1152 x 1136 = (9 * 128) x (16 * 71): 71 is prime
+    assert path == 1 and rh == [] and rw == []
+    path, rh, rw = _query(fc, 1920, 1080, 3, 129, 65, 8)           # 2048 x 1152
+    assert path == 4 and int(np.prod(rh)) == 2048 and int(np.prod(rw)) == 1152 and rw[0] == 9
+    # forced paths fall back when the shape is outside the path's range
+    assert _query(fc, 256, 256, 31, 16, 16, 1000, path=1)[0] == 1
+    assert _query(fc, 256, 256, 31, 16, 16, 1000, force_generic=1)[0] == 1
+    assert _query(fc, 300, 300, 2, 40, 40, 100, path=3)[0] in (1, 2)       # templates above 32 x 32
+    assert _query(fc, 100, 100, 1, 8, 8, 1, path=4)[0] == 4                # any 16 m plane with factors <= 17
+    assert _query(fc, 290, 100, 1, 15, 8, 1, path=4)[0] == 1               # 304 = 16 * 19
+    assert fc.lib().fftconv_query_path(0, 8, 1, 3, 3, 1, None, None, None) < 0
+
+
+def test_in_place_plans_cover_every_supported_size(fc):
+    """Every plane side 16 m up to 8192 whose odd part factors over {3, 5, 7, 9, 11, 13, 17} gets a plan whose radices
+    multiply back to the side, odd radices first, at most 8 stages; nothing else is claimed."""
+    def smooth17(m):
+        for p in (2, 3, 5, 7, 11, 13, 17):
+            while m % p == 0:
+                m //= p
+        return m == 1
+    for m in range(1, 513):
+        n = 16 * m
+        path, rh, _ = _query(fc, n, 64, 1, 1, 1, 1, path=4)
+        if smooth17(m):
+            assert path == 4 and int(np.prod(rh)) == n, (n, rh)
+            odd_done = False
+            for r in rh:
+                if r % 2 == 0:
+                    odd_done = True
+                else:
+                    assert not odd_done, (n, rh)
+                assert r in (2, 3, 4, 5, 7, 8, 9, 11, 13, 16, 17, 32), (n, rh)
+        else:
+            assert path != 4, n
