@@ -11,11 +11,14 @@
 // form of the product runs as 3xTF32 (hi*hi + hi*lo + lo*hi) with fp32 accumulation in TMEM.
 //
 //   os_kern_fft                templates -> A operand images: zero pad fused into the load, pruned 2-D 64 x 64
-//                              half spectrum in shared memory, hi/lo TF32 split, operand-image store
+//                              half spectrum in shared memory (run-time residue task: one copy of the transform
+//                              code serves all four residues), operand-image store in plain fp32
 //   os_data_fft                overlap-save window gather (zero fill, circular wrap) -> 2-D spectrum -> B images
 //   os_gemm                    TMA bulk copies -> smem operand images -> tcgen05.mma (kind::tf32,
 //                              M=128 templates, N=2*tiles, K=2*F) -> TMEM -> bulk store of P
-//   os_inverse                 per (template, tile): 2-D C2R inverse, scale, valid-region store (crop fused)
+//   os_inverse_tma             per (template, 4 tiles): TMA tensor copies gather the product spectra (box = 4 tiles x
+//                              64 columns), 2-D C2R inverse, valid-region store (crop / peak / correlation shift fused)
+//   os_inverse                 the same with a per-thread cp.async gather (fallback when no tensor map can be built)
 //   inv_w_pass                 (spectrum -> plane, when the caller hands in a cudaFFTData spectrum)
 //
 // Replaces the same reference rows as kernels_tile16.cuh (padData, cufftExecR2C,
@@ -26,7 +29,8 @@
 //   Aimg [tblk][bin][ks][kc][128 templates][4]  plain fp32      (MMA A: rows = templates; hi/lo split on chip)
 //   Bimg [nblk][bin][ks][term hi/lo][kc][NMMA rows     ][4]      (MMA B: rows = (tile, re/im column))
 //   P    [tblk][nblk][u][128 templates][v][RS]  fp32, (re,im) per tile (bin = u*64 + v); a template's 64 bins of a
-//        spectrum row are one contiguous 64*RS*4-byte run, which is what os_inverse gathers
+//        spectrum row are one contiguous 64*RS*4-byte run: os_gemm writes it with bulk stores, os_inverse_tma reads
+//        boxes {8 floats, 64 columns, 1 row} of it through a 3-D tensor map
 // Core matrix = 8 rows x 16 B contiguous -> SBO = 128 B, LBO (next 16-byte k unit) = rows * 16 B.
 #pragma once
 #include <cstdint>
