@@ -1,6 +1,6 @@
 // fftconv_bench — stand-alone C++ driver of the C ABI (include/fftconv.h); no MATLAB, no Python.
 //
-//   fftconv_bench [--config c1|c2|c3|c3s|c4|c4s] [--H h --W w --F f --kh a --kw b --K k --N n] [--iters n]
+//   fftconv_bench [--config c1|c2|c3|c3s|c4|c4s|c5|c5s] [--H h --W w --F f --kh a --kw b --K k --N n] [--iters n]
 //                 [--host] [--check n] [--device d]
 //
 // Builds the named synthetic workload, runs cudaConvolutionFFT-equivalent calls through
@@ -29,7 +29,7 @@ struct Cfg { int H, W, F, kh, kw, K; const char* name; int N = 1; };   // N > 1:
 int main(int argc, char** argv) {
     Cfg c{256, 256, 31, 16, 16, 1000, "c2"};
     int iters = 10, check = 0, device = 0;
-    bool host = false;
+    bool host = false, pyramid = false;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() { return i + 1 < argc ? atoi(argv[++i]) : 0; };
@@ -41,6 +41,8 @@ int main(int argc, char** argv) {
             else if (n == "c3s") c = Cfg{1024, 1024, 1, 128, 128, 16, "c3s"};
             else if (n == "c4") c = Cfg{512, 512, 32, 32, 32, 256, "c4", 64};
             else if (n == "c4s") c = Cfg{512, 512, 32, 32, 32, 256, "c4s", 8};
+            else if (n == "c5") { c = Cfg{256, 256, 31, 16, 16, 20000, "c5"}; pyramid = true; }
+            else if (n == "c5s") { c = Cfg{256, 256, 31, 16, 16, 2000, "c5s"}; pyramid = true; }
             else { fprintf(stderr, "unknown config %s\n", n.c_str()); return 1; }
         } else if (a == "--H") c.H = next(); else if (a == "--W") c.W = next(); else if (a == "--F") c.F = next();
         else if (a == "--kh") c.kh = next(); else if (a == "--kw") c.kw = next(); else if (a == "--K") c.K = next();
@@ -64,6 +66,59 @@ int main(int argc, char** argv) {
     for (auto& v : h_bank) v = Nn(rng);
 
     CK(cudaSetDevice(device));
+    if (pyramid) {
+        // BASELINE config 5 on one GPU: 10-level pyramid (side 256 * 2^(-l/5)) x one PREPARED bank
+        // (fftconv_bank_create: the template spectra are transformed once and serve every level)
+        int side[10];
+        size_t out_floats = 0;
+        for (int l = 0; l < 10; ++l) {
+            side[l] = (int)std::lround(256.0 * std::pow(2.0, -l / 5.0));
+            out_floats = std::max(out_floats, (size_t)fftconv_fft_size16(side[l] + c.kh - 1) * fftconv_fft_size16(side[l] + c.kw - 1));
+        }
+        float *d_lv, *d_bk, *d_o;
+        CK(cudaMalloc(&d_lv, (size_t)256 * 256 * c.F * 4)); CK(cudaMalloc(&d_bk, nk1 * c.K * 4));
+        CK(cudaMalloc(&d_o, out_floats * c.K * 4));
+        CK(cudaMemcpy(d_lv, h_data.data(), (size_t)256 * 256 * c.F * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(d_bk, h_bank.data(), nk1 * c.K * 4, cudaMemcpyHostToDevice));
+        std::vector<const float*> kp(c.K);
+        std::vector<int> khs(c.K, c.kh), kws(c.K, c.kw);
+        std::vector<unsigned char> ond(c.K, 1);
+        for (int k = 0; k < c.K; ++k) kp[k] = d_bk + nk1 * k;
+        cudaStream_t st;
+        CK(cudaStreamCreate(&st));
+        fftconv_bank* bank = nullptr;
+        auto t0 = std::chrono::steady_clock::now();
+        FC(fftconv_bank_create(c.K, kp.data(), khs.data(), kws.data(), nullptr, ond.data(), c.F, device, st, &bank));
+        const double prep_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        std::vector<float*> op(c.K);
+        double nout = 0;
+        auto run = [&]() -> int {
+            nout = 0;
+            for (int l = 0; l < 10; ++l) {          // level l reuses the top-left side x side block of the buffer as its own image
+                const int FHl = fftconv_fft_size16(side[l] + c.kh - 1), FWl = fftconv_fft_size16(side[l] + c.kw - 1);
+                for (int k = 0; k < c.K; ++k) op[k] = d_o + (size_t)FHl * FWl * k;
+                if (int r = fftconv_bank_conv(bank, d_lv, 1, side[l], side[l], op.data(), 1, nullptr, st)) return r;
+                nout += (double)c.K * FHl * FWl;
+            }
+            return 0;
+        };
+        FC(run());
+        CK(cudaStreamSynchronize(st));
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        CK(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) FC(run());
+        CK(cudaEventRecord(e1, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= iters;
+        printf("pyramid x prepared bank: bank transform %.1f ms (once), %.3f ms per pyramid, %.3e conv outputs/s\n", prep_ms, ms,
+               nout / (ms * 1e-3));
+        fftconv_bank_destroy(bank);
+        fftconv_release();
+        return 0;
+    }
     float *d_data, *d_bank, *d_out;
     fftconv_float2* d_spec;
     CK(cudaMalloc(&d_data, nd * 4)); CK(cudaMalloc(&d_bank, nk1 * c.K * 4));
