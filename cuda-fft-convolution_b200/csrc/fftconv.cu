@@ -480,17 +480,39 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
     return true;
 }
 
-static int os_env_int(const char* name, int dflt);
-// gather of the product spectra in the inverse: 1 = TMA tensor copies (os_inverse_tma), 0 = per-thread cp.async
-// (os_inverse); FFTCONV_OS_INV_TMA is an A/B switch
-static bool os_inv_tma() { return os_env_int("FFTCONV_OS_INV_TMA", 1) != 0; }
+// Debug / A-B switches of the overlap-save path, read ONCE (first use), never on the per-chunk path:
+//   FFTCONV_OS_MIN_K      smallest bank that takes the overlap-save path automatically (default 64)
+//   FFTCONV_OS_NTBLK      template blocks of 128 per chunk (default: 8 device outputs, 2 host outputs)
+//   FFTCONV_OS_INV_TMA    0: per-thread cp.async gather in the inverse (os_inverse) instead of TMA tensor copies
+//   FFTCONV_OS_GEMM       "simt": validation GEMM on the SIMT pipe
+//   FFTCONV_OS_GEMM_TMAP  0: one bulk copy per template row in the GEMM epilogue instead of one bulk store per item
+//   FFTCONV_OS_HI_INPLACE 1: rewrite the A stage as tf32(a) in shared memory instead of relying on the operand truncation
+//   FFTCONV_OS_LBO_SWAP   swap the LBO / SBO fields of the shared-memory descriptors
+struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg; };
+static const OsEnv& os_env() {
+    static const OsEnv e = [] {
+        auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+        OsEnv x;
+        x.min_k = geti("FFTCONV_OS_MIN_K", 64);
+        x.ntblk = geti("FFTCONV_OS_NTBLK", 0);
+        x.inv_tma = geti("FFTCONV_OS_INV_TMA", 1);
+        const char* m = getenv("FFTCONV_OS_GEMM");
+        x.gemm_simt = m && !strcmp(m, "simt");
+        x.gemm_tmap = geti("FFTCONV_OS_GEMM_TMAP", 1);
+        x.hi_inplace = geti("FFTCONV_OS_HI_INPLACE", 0);
+        x.lbo_swap = geti("FFTCONV_OS_LBO_SWAP", 0);
+        x.dbg = geti("FFTCONV_OS_DBG", 0);
+        return x;
+    }();
+    return e;
+}
 
-// CUtensorMap of P seen as {RS floats, 64 columns, rows}, box {8, 64, 1}.  cuTensorMapEncodeTiled is fetched through the
+// CUtensorMap of P seen as {RS floats, 128 templates, bins}, box {8 floats, 1 template, 64 bins} (the inverse's gather).  cuTensorMapEncodeTiled is fetched through the
 // runtime (cudaGetDriverEntryPoint): the library does not link libcuda.
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nrows, OsTensorMap* out) {
+static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nbins, OsTensorMap* out) {
     static PFN_tmapEncodeTiled encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -500,19 +522,14 @@ static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nrows
         encode = (PFN_tmapEncodeTiled)fn;
     }
     static_assert(sizeof(CUtensorMap) == sizeof(OsTensorMap), "tensor map size");
-    const cuuint64_t gdim[3] = {(cuuint64_t)RS, 64, (cuuint64_t)nrows};
-    const cuuint64_t gstride[2] = {(cuuint64_t)RS * 4, (cuuint64_t)RS * 4 * 64};
-    const cuuint32_t box[3] = {8, 64, 1}, estride[3] = {1, 1, 1};
+    const cuuint64_t gdim[3] = {(cuuint64_t)RS, OS_TM, (cuuint64_t)nbins};
+    const cuuint64_t gstride[2] = {(cuuint64_t)RS * 4, (cuuint64_t)RS * 4 * OS_TM};
+    const cuuint32_t box[3] = {8, 1, 64}, estride[3] = {1, 1, 1};
     const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P), gdim,
                               gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // (L2 promotion 64/128/256 B: no effect measured)
     if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
-}
-
-static int os_env_int(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v && *v ? atoi(v) : dflt;
 }
 
 // Source plane -> B operand images (once per call).  If d_spec is given the plane is first recovered from
@@ -573,7 +590,7 @@ static size_t os_kern_smem(int NF) {
 // Templates per chunk.  Device outputs: as large as the scratch budget allows (fewer launch tails, the B images are
 // streamed once per chunk).  Host outputs: small chunks, so that the D2H of one chunk overlaps the next one's compute.
 static int os_max_chunk(const OsCfg& g, bool out_on_device) {
-    int ntblk = os_env_int("FFTCONV_OS_NTBLK", 0);
+    int ntblk = os_env().ntblk;
     if (ntblk <= 0) {
         ntblk = out_on_device ? 8 : 2;
         const size_t per_blk = (size_t)OS_NBIN * g.NKS * (g.a_stage / 2) + (size_t)g.NNB * OS_NBIN * g.p_blk;   // A + P
@@ -611,12 +628,14 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.NTBLK = ntblk; a.NNB = g.NNB; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.RS = g.RS;
         a.nitems = (long long)g.NNB * OS_NBIN * ntblk;
         a.nsta = g.nsta;
-        a.lbo_swap = os_env_int("FFTCONV_OS_LBO_SWAP", 0);
+        a.lbo_swap = os_env().lbo_swap;
+        a.hi_inplace = os_env().hi_inplace;
+        a.dbg = os_env().dbg;
         ProfScope ps(PK_OS_GEMM, st);
-        const char* mode = getenv("FFTCONV_OS_GEMM");
-        if (mode && !strcmp(mode, "simt")) {            // validation only, never the default
+        if (os_env().gemm_simt) {                       // validation only, never the default
             os_gemm_simt<<<(unsigned)a.nitems, 128, 0, st>>>(a);
         } else {
+            a.use_tmap = os_env().gemm_tmap;
             const unsigned grid = (unsigned)std::min<long long>(a.nitems, (long long)c.sm_count);
             os_gemm<<<grid, 320, g.gemm_smem, st>>>(a);
         }
@@ -636,7 +655,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         OsTensorMap tm;
         const int ntb = (nk + OS_TM - 1) / OS_TM;
         // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
-        if (os_inv_tma() && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_CH * OS_TM, &tm) == 0) {
+        if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
             dim3 grid(g.NNB * (g.RS / 8), nk);             // (tile block, group of 4 tiles) x template
             os_inverse_tma<<<grid, 256, OS_ITMA_SMEM, st>>>(a, tm);
         } else {
@@ -687,7 +706,7 @@ static int choose_path(const fftconv_options& opt, int F, int FH, int FW, int ma
     if (opt.path == PATH_TILE16) return t16_ok ? PATH_TILE16 : PATH_GENERIC;
     const bool bp_ok = bigplane_supported(FH, FW, F);
     if (opt.path == PATH_BIGPLANE) return bp_ok ? PATH_BIGPLANE : PATH_GENERIC;
-    if (os_ok && K >= os_env_int("FFTCONV_OS_MIN_K", 64)) return PATH_OSGEMM;
+    if (os_ok && K >= os_env().min_k) return PATH_OSGEMM;
     if (t16_ok) return PATH_TILE16;
     // long lines: the in-place pipeline touches whole sectors in the strided pass (kernels_bigplane.cuh)
     return (bp_ok && FH >= 1024 && FW >= 1024) ? PATH_BIGPLANE : PATH_GENERIC;

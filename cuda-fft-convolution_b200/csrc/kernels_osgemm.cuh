@@ -28,9 +28,12 @@
 // Operand images (K-major, no swizzle; one 16-byte unit = 4 consecutive k = channels (2c,2c+1) x (re,im)):
 //   Aimg [tblk][bin][ks][kc][128 templates][4]  plain fp32      (MMA A: rows = templates; hi/lo split on chip)
 //   Bimg [nblk][bin][ks][term hi/lo][kc][NMMA rows     ][4]      (MMA B: rows = (tile, re/im column))
-//   P    [tblk][nblk][u][128 templates][v][RS]  fp32, (re,im) per tile (bin = u*64 + v); a template's 64 bins of a
-//        spectrum row are one contiguous 64*RS*4-byte run: os_gemm writes it with bulk stores, os_inverse_tma reads
-//        boxes {8 floats, 64 columns, 1 row} of it through a 3-D tensor map
+//   P    [tblk][nblk][bin = u*64 + v][128 templates][RS]  fp32, (re,im) per tile: WORK-ITEM MAJOR -- the 128 x RS block
+//        an os_gemm item produces is one contiguous run (one bulk store per item; with the earlier [u][template][v][RS]
+//        order an item scattered 128 pieces of RS*4 bytes 64*RS*4 bytes apart and the kernel ran 0.28 instead of 0.21 ms
+//        at config 2).  os_inverse_tma gathers boxes {8 floats, 1 template, 64 bins} through a 3-D tensor map
+//        {RS, 128 templates, bins}: 32-byte pieces, but the CTAs of neighbouring tile groups / templates that are
+//        resident at the same time read the neighbouring pieces, so DRAM still sees whole rows
 // Core matrix = 8 rows x 16 B contiguous -> SBO = 128 B, LBO (next 16-byte k unit) = rows * 16 B.
 #pragma once
 #include <cstdint>
@@ -499,6 +502,24 @@ __device__ __forceinline__ void os_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with the descriptors given as (low word, high word): between the instructions of one K-stage only the
+// 14-bit start-address field (low word) moves, so the issue loop works on 32-bit values
+__device__ __forceinline__ void os_mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool os_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // mbarrier arrives once every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void os_mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -518,6 +539,13 @@ __device__ __forceinline__ void os_named_bar_sync(int id, int nthreads) {
 // TMA 1-D bulk copy shared -> global (SASS: UBLKCP), bulk-group completion
 __device__ __forceinline__ void os_bulk_s2g(void* gdst, const void* ssrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+struct alignas(64) OsTensorMap { unsigned long long opaque[16]; };       // CUtensorMap (128 bytes), built on the host
+// TMA tensor store shared -> global (SASS: UTMASTG), bulk-group completion
+__device__ __forceinline__ void os_tma_store_3d(const void* tmap, const void* ssrc, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1), "r"(c2) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void os_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -554,6 +582,10 @@ struct OsGemmArgs {
     long long nitems;
     int nsta;
     int lbo_swap;     // debug: swap the LBO / SBO fields of the smem descriptors
+    int use_tmap;     // epilogue: one bulk store per item (the whole 128 x RS staging tile) instead of one per template row
+    int dbg;          // timing experiments only (FFTCONV_OS_DBG): 1 = no P store
+    int hi_inplace;   // 1: the splitter rewrites the landed fp32 K-stage as hi = tf32(a) (debug); 0: the tensor core
+                      // itself ignores the 13 low mantissa bits of a kind::tf32 operand, so the raw stage IS the hi operand
 };
 
 // Walks the work items (tile block, bin, template block) of one CTA without 64-bit divisions in the loop
@@ -582,7 +614,7 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
     const uint32_t a_half = (uint32_t)g.KC * OS_TM * 16u;       // one K-stage of A (fp32 as it travels; one hi or lo image)
     const uint32_t b_stage = 2u * g.KC * g.NMMA * 16u;          // one K-stage of B: [hi | lo]
     const uint32_t b_buf = b_stage * g.NKS;
-    unsigned char* a_sm = os_smem_raw;                          // raw ring [nsta][a_half]: TMA target, rewritten in place as hi
+    unsigned char* a_sm = os_smem_raw;                          // raw ring [nsta][a_half]: TMA target = hi operand
     unsigned char* lo_sm = a_sm + (size_t)g.nsta * a_half;      // lo ring [2][a_half]
     unsigned char* b_sm = lo_sm + 2 * (size_t)a_half;           // [2][b_buf]
     float* stage_sm = reinterpret_cast<float*>(b_sm + 2 * (size_t)b_buf);     // [128][RS] epilogue staging
@@ -645,71 +677,92 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            const uint32_t idesc = os_idesc_tf32(OS_TM, g.NMMA);
-            const uint32_t a_lbo = OS_TM * 16u, b_lbo = (uint32_t)g.NMMA * 16u, sbo = 128u;
-            const uint32_t b_term = (uint32_t)g.KC * g.NMMA * 16u;
-            long long curkey = -1;
-            uint32_t nb = 0, na = 0, nit = 0, bcur = 0;
-            OsItemIter w(lo, g.NTBLK);
-            // descriptor templates: only the 14-bit start-address field changes between instructions
-            const uint64_t adesc0 = g.lbo_swap ? os_smem_desc(0, sbo, a_lbo) : os_smem_desc(0, a_lbo, sbo);
-            const uint64_t bdesc0 = g.lbo_swap ? os_smem_desc(0, sbo, b_lbo) : os_smem_desc(0, b_lbo, sbo);
-            for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
-                const long long key = w.key;
-                if (key != curkey) {
-                    bcur = nb & 1;
-                    mbar_wait(&b_full[bcur], (nb >> 1) & 1);
-                    ++nb;
-                    curkey = key;
-                }
-                const uint32_t acc = nit & 1;
-                if (nit >= 2) mbar_wait(&acc_empty[acc], ((nit >> 1) - 1) & 1);
+        // MMA issue.  The WHOLE warp walks the item list with warp-uniform values and one elected lane issues the
+        // instructions: with a single active thread (`if (lane == 0)`) the compiler cannot prove that the operands of the
+        // uniform-datapath instructions (UTCHMMA / UTCBAR take uniform registers) are uniform and wraps every one of them
+        // in a vote / elect / broadcast loop -- 19 dependent instructions per MMA, 4 600 cycles per item, which made this
+        // single thread the bottleneck of the kernel (ncu r01i: the role never waits on a barrier).
+        const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t idesc = os_idesc_tf32(OS_TM, g.NMMA);
+        const uint32_t a_lbo = OS_TM * 16u, b_lbo = (uint32_t)g.NMMA * 16u, sbo = 128u;
+        const uint32_t b_term = (uint32_t)g.KC * g.NMMA * 16u;
+        // descriptor words: only the 14-bit start-address field of the low word changes between instructions
+        const uint64_t adesc0 = g.lbo_swap ? os_smem_desc(0, sbo, a_lbo) : os_smem_desc(0, a_lbo, sbo);
+        const uint64_t bdesc0 = g.lbo_swap ? os_smem_desc(0, sbo, b_lbo) : os_smem_desc(0, b_lbo, sbo);
+        const uint32_t a_w0 = (uint32_t)adesc0, a_w1 = (uint32_t)(adesc0 >> 32);
+        const uint32_t b_w0 = (uint32_t)bdesc0, b_w1 = (uint32_t)(bdesc0 >> 32);
+        const uint32_t a_step = 2u * a_lbo >> 4, b_step = 2u * b_lbo >> 4;     // K advances by 2 units of 16 bytes
+        const uint32_t a_sm0 = smem_u32(a_sm), lo_sm0 = smem_u32(lo_sm), b_sm0 = smem_u32(b_sm);
+        const int nj = g.KC >> 1;                                              // <= 4
+        long long curkey = -1;
+        uint32_t nb = 0, na = 0, nit = 0, bcur = 0;
+        OsItemIter w(lo, g.NTBLK);
+        for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
+            const long long key = w.key;
+            if (key != curkey) {
+                bcur = nb & 1;
+                mbar_wait(&b_full[bcur], (nb >> 1) & 1);
+                ++nb;
+                curkey = key;
+            }
+            const uint32_t acc = nit & 1;
+            if (nit >= 2) mbar_wait(&acc_empty[acc], ((nit >> 1) - 1) & 1);
+            const uint32_t tmem_d = tb + acc * OS_ACC_COLS;
+            for (int ks = 0; ks < g.NKS; ++ks) {
+                const uint32_t st = na % g.nsta, ls = na & 1;
+                mbar_wait(&a_ready[st], (na / g.nsta) & 1);
                 os_tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * OS_ACC_COLS;
-                for (int ks = 0; ks < g.NKS; ++ks) {
-                    const uint32_t st = na % g.nsta, ls = na & 1;
-                    mbar_wait(&a_ready[st], (na / g.nsta) & 1);
-                    os_tc_fence_after();
-                    const uint32_t hi_base = smem_u32(a_sm + (size_t)st * a_half);
-                    const uint32_t lo_base = smem_u32(lo_sm + (size_t)ls * a_half);
-                    const uint32_t b_base = smem_u32(b_sm + (size_t)bcur * b_buf + (size_t)ks * b_stage);
-                    // small terms first: (A lo, B hi), (A hi, B lo), then (A hi, B hi); per instruction only the
-                    // start-address fields of the two descriptors move (K advances by 2 units of 16 bytes)
-                    const uint64_t ad_lo = adesc0 | (uint64_t)((lo_base >> 4) & 0x3FFFu);
-                    const uint64_t ad_hi = adesc0 | (uint64_t)((hi_base >> 4) & 0x3FFFu);
-                    const uint64_t bd_hi = bdesc0 | (uint64_t)((b_base >> 4) & 0x3FFFu);
-                    const uint64_t bd_lo = bdesc0 | (uint64_t)(((b_base + b_term) >> 4) & 0x3FFFu);
-                    const uint64_t a_step = (uint64_t)(2u * a_lbo >> 4), b_step = (uint64_t)(2u * b_lbo >> 4);
-                    const int nj = g.KC >> 1;
-                    for (int j = 0; j < nj; ++j) os_mma_tf32(tmem_d, ad_lo + j * a_step, bd_hi + j * b_step, idesc, (ks | j) != 0 ? 1u : 0u);
-                    for (int j = 0; j < nj; ++j) os_mma_tf32(tmem_d, ad_hi + j * a_step, bd_lo + j * b_step, idesc, 1u);
-                    for (int j = 0; j < nj; ++j) os_mma_tf32(tmem_d, ad_hi + j * a_step, bd_hi + j * b_step, idesc, 1u);
+                const uint32_t ad_hi = a_w0 | (((a_sm0 + st * a_half) >> 4) & 0x3FFFu);
+                const uint32_t ad_lo = a_w0 | (((lo_sm0 + ls * a_half) >> 4) & 0x3FFFu);
+                const uint32_t b_base = b_sm0 + bcur * b_buf + (uint32_t)ks * b_stage;
+                const uint32_t bd_hi = b_w0 | ((b_base >> 4) & 0x3FFFu);
+                const uint32_t bd_lo = b_w0 | (((b_base + b_term) >> 4) & 0x3FFFu);
+                if (os_elect_one()) {
+                    // small terms first: (A lo, B hi), (A hi, B lo), then (A hi, B hi)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nj) os_mma_tf32_w(tmem_d, ad_lo + j * a_step, a_w1, bd_hi + j * b_step, b_w1, idesc, (ks | j) != 0 ? 1u : 0u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nj) os_mma_tf32_w(tmem_d, ad_hi + j * a_step, a_w1, bd_lo + j * b_step, b_w1, idesc, 1u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (j < nj) os_mma_tf32_w(tmem_d, ad_hi + j * a_step, a_w1, bd_hi + j * b_step, b_w1, idesc, 1u);
                     os_mma_commit(&a_empty[st]);
                     os_mma_commit(&lo_empty[ls]);
-                    ++na;
+                    if (ks + 1 == g.NKS) {
+                        os_mma_commit(&acc_full[acc]);
+                        if (it + 1 == hi || w.last_of_key()) os_mma_commit(&b_empty[bcur]);
+                    }
                 }
-                os_mma_commit(&acc_full[acc]);
-                if (it + 1 == hi || w.last_of_key()) os_mma_commit(&b_empty[bcur]);
+                __syncwarp();
+                ++na;
             }
         }
     } else if (warp >= 6) {
+        // A splitter: lo = a - tf32(a) into the lo ring (the raw stage itself serves as the hi operand: kind::tf32 reads
+        // only the sign, the exponent and the 10 high mantissa bits of each 32-bit element)
         const int sp = threadIdx.x - 192;             // 0..127
-        const uint32_t nvec = a_half / 16u;           // float4 per stage (a multiple of 128)
+        const int kc = g.KC;                          // float4 per thread and stage (a_half / 16 / 128), <= 8
         uint32_t na = 0;
         for (long long it = lo; it < hi; ++it) {
             for (int ks = 0; ks < g.NKS; ++ks, ++na) {
                 const uint32_t st = na % g.nsta, ls = na & 1;
                 mbar_wait(&a_full[st], (na / g.nsta) & 1);
+                float4* hp = reinterpret_cast<float4*>(a_sm + (size_t)st * a_half) + sp;
+                float4* lp = reinterpret_cast<float4*>(lo_sm + (size_t)ls * a_half) + sp;
+                float4 v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < kc) v[i] = hp[128 * i];
                 if (na >= 2) mbar_wait(&lo_empty[ls], ((na >> 1) - 1) & 1);
-                float4* hp = reinterpret_cast<float4*>(a_sm + (size_t)st * a_half);
-                float4* lp = reinterpret_cast<float4*>(lo_sm + (size_t)ls * a_half);
-                for (uint32_t i = sp; i < nvec; i += 128) {
-                    const float4 v = hp[i];
-                    const float4 h = make_float4(os_tf32_hi(v.x), os_tf32_hi(v.y), os_tf32_hi(v.z), os_tf32_hi(v.w));
-                    hp[i] = h;
-                    lp[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < kc) {
+                        const float4 h = make_float4(os_tf32_hi(v[i].x), os_tf32_hi(v[i].y), os_tf32_hi(v[i].z), os_tf32_hi(v[i].w));
+                        if (g.hi_inplace) hp[128 * i] = h;
+                        lp[128 * i] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
+                    }
                 fence_proxy_async();                  // generic-proxy writes -> visible to tcgen05.mma (async proxy)
                 os_mbar_arrive(&a_ready[st]);
             }
@@ -717,6 +770,7 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
     } else {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;                // template row of the block
+        const bool leader = threadIdx.x == 64;        // issues the tensor store of the staging tile
         uint32_t nit = 0;
         OsItemIter w(lo, g.NTBLK);
         for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
@@ -725,29 +779,35 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
             mbar_wait(&acc_full[acc], (nit >> 1) & 1);
             os_tc_fence_after();
             const uint32_t taddr = tmem_base + acc * OS_ACC_COLS + ((uint32_t)(q * 32) << 16);
-            os_bulk_wait_read0();                     // this thread's previous bulk store has finished reading its staging row
             float* srow = stage_sm + (size_t)row * g.RS;
-            {   // all TMEM loads of the row in flight, one wait (RS <= 80 columns)
-                uint32_t r[80];
+            uint32_t r[80];                           // all TMEM loads of the row in flight, one wait (RS <= 80 columns)
 #pragma unroll
-                for (int i = 0; i < 10; ++i)
-                    if (8 * i < g.RS) os_tmem_ld8(taddr + 8 * i, r + 8 * i);
-                os_tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 10; ++i)
-                    if (8 * i < g.RS) {
-                        float4* o = reinterpret_cast<float4*>(srow + 8 * i);
-                        o[0] = make_float4(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]), __uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
-                        o[1] = make_float4(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]), __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
-                    }
-            }
+            for (int i = 0; i < 10; ++i)
+                if (8 * i < g.RS) os_tmem_ld8(taddr + 8 * i, r + 8 * i);
+            os_tmem_ld_wait();
             os_tc_fence_before();
-            os_mbar_arrive(&acc_empty[acc]);
+            os_mbar_arrive(&acc_empty[acc]);          // the accumulator is free again before the store is even staged
+            if (g.use_tmap) {
+                if (leader) os_bulk_wait_read0();     // the previous tensor store has finished reading the staging tile
+                os_named_bar_sync(1, 128);
+            } else {
+                os_bulk_wait_read0();                 // this thread's previous bulk store has finished reading its staging row
+            }
+#pragma unroll
+            for (int i = 0; i < 10; ++i)
+                if (8 * i < g.RS) {
+                    float4* o = reinterpret_cast<float4*>(srow + 8 * i);
+                    o[0] = make_float4(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1]), __uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3]));
+                    o[1] = make_float4(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]), __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
+                }
             fence_proxy_async();                      // this thread's staging writes -> visible to the bulk-copy engine
-            {   // row `row` (template) of the block -> P[tblk][nblk][u][template][v][RS]: one bulk copy per thread
-                const int u = bin >> 6, v = bin & 63;
-                float* dst = g.P + ((((size_t)((size_t)tblk * g.NNB + nblk) * OS_CH + u) * OS_TM + row) * 64 + v) * g.RS;
-                os_bulk_s2g(dst, srow, (uint32_t)g.RS * 4u);
+            // P[tblk][nblk][bin][template][RS]: the staging tile is ONE contiguous run of global memory
+            float* dst = g.P + (((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * ((size_t)OS_TM * g.RS);
+            if (g.use_tmap) {
+                os_named_bar_sync(1, 128);
+                if (leader && !(g.dbg & 1)) os_bulk_s2g(dst, stage_sm, (uint32_t)(OS_TM * g.RS * 4));
+            } else {
+                os_bulk_s2g(dst + (size_t)row * g.RS, srow, (uint32_t)g.RS * 4u);     // one bulk copy per template row
             }
         }
         os_bulk_wait0();
@@ -773,7 +833,7 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
     const float* A = g.Aimg + ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
     const float* B = g.Bimg + (size_t)key * g.NKS * b_stage;
     const int t = threadIdx.x;
-    float* P = g.P + ((((size_t)((size_t)tblk * g.NNB + nblk) * OS_CH + (bin >> 6)) * OS_TM + t) * 64 + (bin & 63)) * g.RS;
+    float* P = g.P + ((((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM + t) * (size_t)g.RS;
     for (int n = 0; n < g.RS; ++n) {
         float acc = 0.f;
         for (int ks = 0; ks < g.NKS; ++ks)
@@ -883,9 +943,9 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         cpx* dst = buf + gq * OS_ITILE + os_icol(v);
         if (m < a.NT) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
-            const size_t ustride = (size_t)OS_TM * 32 * a.RS;              // cpx units; P[tblk][nblk][u][template][v][RS]
+            const size_t ustride = (size_t)64 * OS_TM * (a.RS / 2);        // cpx units; P[tblk][nblk][u*64 + v][template][RS]
             const cpx* pp = reinterpret_cast<const cpx*>(
-                a.P + (((size_t)((size_t)tblk * a.NNB + nblk) * OS_CH * OS_TM + tl) * 64 + v) * a.RS + 2 * ml);
+                a.P + ((((size_t)tblk * a.NNB + nblk) * OS_NBIN + v) * OS_TM + tl) * (size_t)a.RS + 2 * ml);
             const uint32_t d0 = smem_u32(dst);
 #pragma unroll
             for (int u = 0; u <= 32; ++u) {
@@ -1036,8 +1096,6 @@ __device__ __forceinline__ void os_tma_load_3d(void* dst, const void* tmap, int 
                  ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-struct alignas(64) OsTensorMap { unsigned long long opaque[16]; };       // CUtensorMap (128 bytes), built on the host
-
 __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __grid_constant__ OsTensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
@@ -1082,9 +1140,9 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
     // ---- gather: 33 boxes {4 tiles, 64 columns, 1 row}, one thread, all in flight at once
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, OS_CH * 2048u);
-        const int row0 = ((tblk * a.NNB + nblk) * OS_CH) * OS_TM + tl;     // row of u = 0; rows of one u are OS_TM apart
+        const int bin0 = (tblk * a.NNB + nblk) * OS_NBIN;                  // tensor {RS, 128 templates, bins}: box {8, 1, 64}
 #pragma unroll 1
-        for (int u = 0; u < OS_CH; ++u) os_tma_load_3d(buf + u * OS_TROW, &tmap, 8 * g, 0, row0 + u * OS_TM, &bar);
+        for (int u = 0; u < OS_CH; ++u) os_tma_load_3d(buf + u * OS_TROW, &tmap, 8 * g, tl, bin0 + u * 64, &bar);
     }
     mbar_wait(&bar, 0);
     // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
