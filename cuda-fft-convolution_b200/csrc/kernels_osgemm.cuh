@@ -548,6 +548,10 @@ __device__ __forceinline__ void os_tma_store_3d(const void* tmap, const void* ss
                  ::"l"(tmap), "r"(smem_u32(ssrc)), "r"(c0), "r"(c1), "r"(c2) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// L2 prefetch of a contiguous run (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void os_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void os_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void os_bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
@@ -583,6 +587,7 @@ struct OsGemmArgs {
     int nsta;
     int lbo_swap;     // debug: swap the LBO / SBO fields of the smem descriptors
     int use_tmap;     // epilogue: one bulk store per item (the whole 128 x RS staging tile) instead of one per template row
+    int pf_items;     // L2 prefetch distance of the TMA producer, in work items (0 = off)
     int dbg;          // timing experiments only (FFTCONV_OS_DBG): 1 = no P store
     int hi_inplace;   // 1: the splitter rewrites the landed fp32 K-stage as hi = tf32(a) (debug); 0: the tensor core
                       // itself ignores the 13 low mantissa bits of a kind::tf32 operand, so the raw stage IS the hi operand
@@ -653,9 +658,28 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
             long long curkey = -1;
             uint32_t nb = 0, na = 0;
             OsItemIter w(lo, g.NTBLK);
+            // The A images are streamed exactly once, so every ring slot would otherwise pay the full HBM latency under
+            // load (~2.3 us measured: with 4 slots of 16 KB that caps the CTA at ~30 GB/s).  A second iterator runs
+            // `pf` items ahead and pulls the A block of that item (and the B block when a new key starts) into L2: the
+            // bytes in flight towards HBM sit in L2 instead of shared memory and the ring only sees L2 latency.
+            const int pf = g.pf_items;
+            OsItemIter wp(lo, g.NTBLK);
+            long long pit = lo, pkey = -1;
+            auto prefetch_item = [&]() {
+                if (pit >= hi) return;
+                if (wp.key != pkey) {
+                    pkey = wp.key;
+                    if (pit != lo) os_prefetch_l2(reinterpret_cast<const unsigned char*>(g.Bimg) + (size_t)pkey * b_buf, b_buf);
+                }
+                os_prefetch_l2(reinterpret_cast<const unsigned char*>(g.Aimg) + ((size_t)wp.tblk * OS_NBIN + wp.bin) * g.NKS * a_half,
+                               a_half * g.NKS);
+                ++pit; wp.next();
+            };
+            for (int i = 0; i < pf; ++i) prefetch_item();
             for (long long it = lo; it < hi; ++it, w.next()) {
                 const long long key = w.key;
                 const int tblk = w.tblk, bin = w.bin;
+                if (pf) prefetch_item();
                 if (key != curkey) {
                     const uint32_t bb = nb & 1;
                     if (nb >= 2) mbar_wait(&b_empty[bb], ((nb >> 1) - 1) & 1);
@@ -721,10 +745,10 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
                     // small terms first: (A lo, B hi), (A hi, B lo), then (A hi, B hi)
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (j < nj) os_mma_tf32_w(tmem_d, ad_lo + j * a_step, a_w1, bd_hi + j * b_step, b_w1, idesc, (ks | j) != 0 ? 1u : 0u);
+                        if (j < nj && !(g.dbg & 8)) os_mma_tf32_w(tmem_d, ad_lo + j * a_step, a_w1, bd_hi + j * b_step, b_w1, idesc, (ks | j) != 0 ? 1u : 0u);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (j < nj) os_mma_tf32_w(tmem_d, ad_hi + j * a_step, a_w1, bd_lo + j * b_step, b_w1, idesc, 1u);
+                        if (j < nj && !(g.dbg & 8)) os_mma_tf32_w(tmem_d, ad_hi + j * a_step, a_w1, bd_lo + j * b_step, b_w1, idesc, 1u);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         if (j < nj) os_mma_tf32_w(tmem_d, ad_hi + j * a_step, a_w1, bd_hi + j * b_step, b_w1, idesc, 1u);
@@ -758,7 +782,7 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
                 if (na >= 2) mbar_wait(&lo_empty[ls], ((na >> 1) - 1) & 1);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if (i < kc) {
+                    if (i < kc && !(g.dbg & 4)) {
                         const float4 h = make_float4(os_tf32_hi(v[i].x), os_tf32_hi(v[i].y), os_tf32_hi(v[i].z), os_tf32_hi(v[i].w));
                         if (g.hi_inplace) hp[128 * i] = h;
                         lp[128 * i] = make_float4(v[i].x - h.x, v[i].y - h.y, v[i].z - h.z, v[i].w - h.w);
@@ -873,6 +897,7 @@ struct OsInvArgs {
     unsigned long long* peak_keys;
     const int2* khw;        // (kh, kw) per template of the chunk (peak and correlation modes)
     int H, W;
+    int dbg;                // timing experiments only (FFTCONV_OS_DBG): 16 = contiguous load instead of the gather, 32 = no plane store
     int corr;               // correlation mode: plane position (Y, X) of the flipped-template convolution is stored at
                             // ((Y - kh + 1) mod FH, (X - kw + 1) mod FW)
 };
@@ -1141,6 +1166,10 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, OS_CH * 2048u);
         const int bin0 = (tblk * a.NNB + nblk) * OS_NBIN;                  // tensor {RS, 128 templates, bins}: box {8, 1, 64}
+        if (a.dbg & 16) {                                                  // timing experiment: contiguous bytes instead of the gather
+            const size_t cta = (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+            bulk_g2s(buf, reinterpret_cast<const unsigned char*>(a.P) + cta * (OS_CH * 2048u), OS_CH * 2048u, &bar);
+        } else
 #pragma unroll 1
         for (int u = 0; u < OS_CH; ++u) os_tma_load_3d(buf + u * OS_TROW, &tmap, 8 * g, tl, bin0 + u * 64, &bar);
     }
@@ -1248,6 +1277,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
             return;
         }
         float* dst = tile_dst[gq] + ylo;
+        if (a.dbg & 32) { if (reA[3] == 1.2345f) dst[0] = imB[5]; return; }
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) {
             const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
