@@ -13,6 +13,7 @@
 #include <mutex>
 #include <string>
 #include <memory>
+#include <thread>
 #include <vector>
 
 #include "../../include/fftconv.h"
@@ -64,13 +65,14 @@ static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass
 static bool g_prof_on = false;
 struct ProfRec { int kind; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
         if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
     ~ProfScope() {
-        if (a) { cudaEventRecord(b, st); g_prof.push_back({kind, a, b}); }
+        if (a) { cudaEventRecord(b, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back({kind, a, b}); }
     }
 };
 
@@ -118,6 +120,9 @@ struct Ctx {
     DevBuf batchA;                   // fftconv_conv_batch: template spectra shared by the image groups of one call
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
     DevBuf osA, osB, osP, osPlane, osZ, osPeaks;     // overlap-save / tcgen05 path scratch
+    void* bounce = nullptr;          // pinned bounce ring for PAGEABLE host outputs (two halves of one chunk of planes)
+    size_t bounce_cap = 0;
+    cudaEvent_t evb[2] = {nullptr, nullptr};   // D2H into bounce half done
     void* pinned = nullptr;          // host staging (descriptors, packed kernels)
     size_t pinned_cap = 0;
     cudaEvent_t pinned_free = nullptr;   // recorded after the last async copy out of `pinned`
@@ -127,9 +132,18 @@ struct Ctx {
     cudaEvent_t evf[2] = {nullptr, nullptr};
     int sm_count = 148;
     cudaEvent_t spec_ready = nullptr;    // fftconv_spectrum_ready_event: one-shot dependency of the data-side work
+    // One lock per device: a call holds it from its first touch of the cached scratch to its last enqueue (host-output
+    // calls: to the final synchronisation), so calls on different devices never serialise each other (the reference's
+    // own multi-GPU prototype is such a caller, src/cudaConvFFTDataStreams.cu:273-328).  Recursive: the one-shot entry
+    // points nest the two-call ones.
+    std::recursive_mutex mu;
+    int depth = 0;
+    cudaEvent_t last_use = nullptr;      // recorded behind the last enqueue of every call
+    cudaStream_t last_stream = nullptr;
+    bool used = false;
 };
 
-static std::mutex g_mu;
+static std::mutex g_mu;                  // guards g_ctx (the map only; each Ctx has its own lock)
 static std::map<int, Ctx> g_ctx;
 
 static int dev_reserve(DevBuf& b, size_t bytes) {
@@ -164,7 +178,10 @@ static int opt_in_smem(K kernel) {
 }
 
 static int ctx_get(int device, Ctx** out) {
-    Ctx& c = g_ctx[device];
+    Ctx* cp;
+    { std::lock_guard<std::mutex> lk(g_mu); cp = &g_ctx[device]; }      // map nodes are stable
+    Ctx& c = *cp;
+    std::lock_guard<std::recursive_mutex> lkc(c.mu);
     if (!c.inited) {
         c.dev = device;
         cudaDeviceProp prop;
@@ -189,6 +206,7 @@ static int ctx_get(int device, Ctx** out) {
             CU(cudaMemcpyToSymbol(c_os_w64, h_w64, sizeof h_w64));
         }
         CU(cudaEventCreateWithFlags(&c.pinned_free, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c.last_use, cudaEventDisableTiming));
         for (auto& e : c.ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CU(cudaStreamCreateWithFlags(&c.side, cudaStreamNonBlocking));
         {   // data-side transforms are the critical path of a call: they outrank the template transforms they overlap
@@ -197,6 +215,7 @@ static int ctx_get(int device, Ctx** out) {
             CU(cudaStreamCreateWithPriority(&c.side2, cudaStreamNonBlocking, hi));
         }
         for (auto& e : c.evf) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (auto& e : c.evb) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         if (opt_in_smem(fwd_h_pass<PAD_ZERO>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(fwd_h_pass<PAD_CLAMP>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(fwd_w_pass)) return FFTCONV_ERR_CUDA;
@@ -251,6 +270,33 @@ struct DeviceGuard {
         if (prev != device && cudaSetDevice(device) != cudaSuccess) ok = false;
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// A library call on `device` / `stream`: takes the device's lock, selects the device, and orders the call behind the
+// previous call when that one ran on a DIFFERENT stream (the cached scratch -- operand images, product spectra, staging --
+// is shared by all streams of a device: without this two device-output calls on two streams would race on it).
+struct CtxScope {
+    Ctx* c = nullptr;
+    int err = 0;
+    cudaStream_t st;
+    std::unique_lock<std::recursive_mutex> lk;
+    DeviceGuard guard;
+    CtxScope(int device, cudaStream_t stream) : st(stream), guard(device) {
+        if (!guard.ok) { err = fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device); return; }
+        if ((err = ctx_get(device, &c))) { c = nullptr; return; }
+        lk = std::unique_lock<std::recursive_mutex>(c->mu);
+        if (c->depth++ == 0 && c->used && c->last_stream != st) {
+            if (cudaStreamWaitEvent(st, c->last_use, 0) != cudaSuccess)
+                err = fail(FFTCONV_ERR_CUDA, "cudaStreamWaitEvent failed");
+        }
+    }
+    ~CtxScope() {
+        if (!c || !lk.owns_lock()) return;
+        if (--c->depth == 0) {
+            cudaEventRecord(c->last_use, st);
+            c->last_stream = st; c->used = true;
+        }
+    }
 };
 
 static inline int odd_ld(int n) { return n | 1; }   // line stride (float2) avoiding bank conflicts
@@ -693,6 +739,7 @@ struct ConvArgs {
     int bank_maxkh = 0, bank_maxkw = 0;
     unsigned long long* peak_keys = nullptr;   // fused maximum (fftconv_bank_conv_max): K packed keys, no planes
     const int2* bank_khw = nullptr;            // (kh, kw) of every template of the bank (device)
+    cudaEvent_t spec_ready = nullptr;   // one-shot event handed over by fftconv_spectrum_ready_event (consumed by conv_impl)
     int nimg = 1;                  // batched entry point: nimg images [nimg][F][rawW][rawH] (raw, device, overlap-save path
                                    // only); outs then holds nimg*K device planes, image-major
 };
@@ -711,7 +758,10 @@ static int choose_path(const fftconv_options& opt, int F, int FH, int FW, int ma
     if (opt.path == PATH_TILE16) return t16_ok ? PATH_TILE16 : PATH_GENERIC;
     const bool bp_ok = bigplane_supported(FH, FW, F);
     if (opt.path == PATH_BIGPLANE) return bp_ok ? PATH_BIGPLANE : PATH_GENERIC;
-    if (os_ok && K >= os_env().min_k) return PATH_OSGEMM;
+    // very large planes with small templates: the tile spectra (B) and the product spectra of ONE template block (P) must
+    // stay within a sane scratch budget, otherwise the plane goes to the large-plane / generic pipelines
+    const bool os_fits = os_ok && (size_t)g.NNB * OS_NBIN * (g.b_buf + g.p_blk) <= ((size_t)24 << 30);
+    if (os_fits && K >= os_env().min_k) return PATH_OSGEMM;
     if (t16_ok) return PATH_TILE16;
     // long lines: the in-place pipeline touches whole sectors in the strided pass (kernels_bigplane.cuh)
     return (bp_ok && FH >= 1024 && FW >= 1024) ? PATH_BIGPLANE : PATH_GENERIC;
@@ -941,6 +991,36 @@ static size_t plane_floats(const ConvArgs& a, int FH) {
     return (size_t)crop_w * out_ld;
 }
 
+static int bounce_reserve(Ctx& c, size_t bytes) {
+    if (bytes <= c.bounce_cap) return 0;
+    if (c.bounce) { CU(cudaStreamSynchronize(c.side)); CU(cudaFreeHost(c.bounce)); }
+    c.bounce = nullptr; c.bounce_cap = 0;
+    CU(cudaMallocHost(&c.bounce, bytes));
+    c.bounce_cap = bytes;
+    return 0;
+}
+
+// true when the host pointer is page-locked (cudaMallocHost / cudaHostRegister): an async D2H into it runs at PCIe rate
+static bool host_ptr_pinned(const void* p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// n planes of `bytes` each from the pinned bounce half to the caller's (pageable) planes, on a few host threads: first
+// touch of freshly allocated output pages and the copy itself are both host-memory bound
+static void host_copy_planes(float* const* dst, const char* src, size_t bytes, int n) {
+    const size_t total = bytes * (size_t)n;
+    unsigned nt = total < ((size_t)4 << 20) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2));
+    nt = (unsigned)std::min<size_t>(nt, (size_t)n);
+    auto work = [&](int b, int e) { for (int k = b; k < e; ++k) memcpy(dst[k], src + bytes * (size_t)k, bytes); };
+    if (nt <= 1) { work(0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; ++t) th.emplace_back(work, (int)((size_t)n * t / nt), (int)((size_t)n * (t + 1) / nt));
+    work(0, (int)((size_t)n / nt));
+    for (auto& t : th) t.join();
+}
+
 // Convolve the spectrum with the whole bank, chunk by chunk.
 static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     const int CH = a.CH, FW = a.FW, F = a.F, K = a.K;
@@ -958,7 +1038,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         maxkh = std::max(maxkh, std::min(a.kernels[k].kh, FH));
         maxkw = std::max(maxkw, std::min(a.kernels[k].kw, FW));
     }
-    const int path = (a.nimg > 1 || a.bankA) ? PATH_OSGEMM : choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
+    // raw data in (no compat spectrum exists), batches and prepared banks are served by the overlap-save path only
+    const int path = (a.nimg > 1 || a.bankA || a.d_raw) ? PATH_OSGEMM : choose_path(a.opt, F, FH, FW, maxkh, maxkw, K);
     const bool tile16 = path == PATH_TILE16;
     const bool osg = path == PATH_OSGEMM;
     const bool bigp = path == PATH_BIGPLANE;
@@ -966,8 +1047,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     if (osg && !os_config(F, FH, FW, maxkh, maxkw, og, a.nimg))
         return fail(FFTCONV_ERR_UNSUPPORTED, "batch outside the range of the overlap-save path");
     const size_t NO = (size_t)K * a.nimg;                          // output planes
-    cudaEvent_t spec_ready = c.spec_ready;
-    c.spec_ready = nullptr;
+    cudaEvent_t spec_ready = a.spec_ready;
     if (spec_ready && !osg) CU(cudaStreamWaitEvent(st, spec_ready, 0));   // only the overlap-save path has image-independent work to run ahead
 
     // ---- chunking: bound the scratch held per chunk
@@ -1019,8 +1099,16 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)KC * F * maxkw * CH)) return e;
         if (int e = dev_reserve(c.Z, sizeof(cpx) * (size_t)KC * FW * CH)) return e;
     }
-    if (!a.out_on_device)
+    // Host outputs.  Page-locked planes: D2H straight into them.  PAGEABLE planes (what a MEX caller hands over: K separate
+    // mxArrays, src/cudaConvFFTData.cu:275-277) would turn every cudaMemcpyAsync into a blocking staged copy and serialise
+    // the chunk pipeline: they go through a library-owned pinned bounce ring instead, and this thread copies chunk i out
+    // of the ring while the device computes chunk i + 1.
+    bool bounce = false;
+    if (!a.out_on_device) {
         if (int e = dev_reserve(c.outstage, sizeof(float) * plane * KC * 2)) return e;
+        bounce = !(host_ptr_pinned(a.outs[0]) && host_ptr_pinned(a.outs[K - 1]));
+        if (bounce) if (int e = bounce_reserve(c, sizeof(float) * plane * KC * 2)) return e;
+    }
 
     // descriptors / kcols / out pointers for ALL kernels go through pinned staging once
     const size_t desc_bytes = (sizeof(SrcDesc) + sizeof(int2) + sizeof(int)) * (size_t)K + sizeof(float*) * NO + 64;
@@ -1106,6 +1194,20 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         if (!a.out_on_device) {
             CU(cudaEventRecord(c.ev[2 + (chunk & 1)], st));
             CU(cudaStreamWaitEvent(c.side, c.ev[2 + (chunk & 1)], 0));
+            if (bounce) {
+                // (the host copy-out of chunk - 2, which used this ring half, finished in program order below)
+                char* half = reinterpret_cast<char*>(c.bounce) + sizeof(float) * plane * (size_t)KC * (chunk & 1);
+                CU(cudaMemcpyAsync(half, h_outp[k0], sizeof(float) * plane * (size_t)nk, cudaMemcpyDeviceToHost, c.side));
+                CU(cudaEventRecord(c.evb[chunk & 1], c.side));
+                CU(cudaEventRecord(c.ev[chunk & 1], c.side));
+                if (chunk >= 1) {
+                    const int p0 = bounds[chunk - 1], pn = k0 - p0;
+                    CU(cudaEventSynchronize(c.evb[(chunk - 1) & 1]));
+                    host_copy_planes(a.outs + p0, reinterpret_cast<char*>(c.bounce) + sizeof(float) * plane * (size_t)KC * ((chunk - 1) & 1),
+                                     sizeof(float) * plane, pn);
+                }
+                continue;
+            }
             // contiguous host planes -> one copy
             int k = k0;
             while (k < k0 + nk) {
@@ -1119,6 +1221,13 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         }
     }
     if (!a.out_on_device) {
+        if (bounce) {
+            const size_t last = bounds.size() - 2;
+            const int p0 = bounds[last], pn = K - p0;
+            CU(cudaEventSynchronize(c.evb[last & 1]));
+            host_copy_planes(a.outs + p0, reinterpret_cast<char*>(c.bounce) + sizeof(float) * plane * (size_t)KC * (last & 1),
+                             sizeof(float) * plane, pn);
+        }
         CU(cudaStreamSynchronize(c.side));
         CU(cudaStreamSynchronize(st));
     }
@@ -1176,11 +1285,9 @@ static int fft_data_impl(const float* data, int data_on_device, int H, int W, in
     g_err.clear();
     if (!data || !d_spec || H <= 0 || W <= 0 || F <= 0 || KH <= 0 || KW <= 0)
         return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    Ctx* c;
-    if (int e = ctx_get(device, &c)) return e;
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
     cudaStream_t st = (cudaStream_t)stream;
     const int FH = fftconv_fft_size16(H + KH - 1), FW = fftconv_fft_size16(W + KW - 1);
     const float* d_data = data;
@@ -1214,6 +1321,14 @@ static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
                      const fftconv_options* opt, int device, void* stream, bool pipelined,
                      const ConvRaw* raw = nullptr) {
     g_err.clear();
+    // the one-shot spectrum-ready event belongs to THIS call whatever its outcome (a validation error or K == 0 must
+    // not leave a stale event pointer behind for a later call)
+    cudaEvent_t spec_ready = nullptr;
+    {
+        Ctx* c0 = nullptr;
+        { std::lock_guard<std::mutex> lk(g_mu); auto it = g_ctx.find(device); if (it != g_ctx.end()) c0 = &it->second; }
+        if (c0) { std::lock_guard<std::recursive_mutex> lkc(c0->mu); spec_ready = c0->spec_ready; c0->spec_ready = nullptr; }
+    }
     if (!d_spec && !raw) return fail(FFTCONV_ERR_NOT_GPU_ARRAY, "The data must be FFT-ed real array in GPU");
     if (CH < 2 || FW <= 0 || F <= 0 || (K > 0 && !outs)) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
     if (int e = check_threads(threads, nthreads)) return e;
@@ -1225,16 +1340,15 @@ static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
     const size_t nout = (size_t)K * (raw ? raw->nimg : 1);
     for (size_t k = 0; k < nout; ++k)
         if (!outs[k]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    Ctx* c;
-    if (int e = ctx_get(device, &c)) return e;
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
     ConvArgs a;
     a.d_spec = (const cpx*)d_spec; a.CH = CH; a.FW = FW; a.F = F; a.K = K;
     a.kernels = refs.data(); a.outs = outs; a.out_on_device = out_on_device != 0;
     a.opt = opt ? *opt : fftconv_options{};
     a.pipelined = pipelined;
+    a.spec_ready = spec_ready;
     if (raw) { a.d_raw = raw->d_data; a.rawH = raw->H; a.rawW = raw->W; a.nimg = raw->nimg; }
     return run_conv(*c, a, (cudaStream_t)stream);
 }
@@ -1279,12 +1393,12 @@ int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W,
     }
     void* spec = nullptr;
     const float* d_data = data;
+    // the device lock is held across the WHOLE call: the staged image (ddata / dspec) must not be overwritten by another
+    // host thread between the data stage and the bank loop
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        DeviceGuard guard(device);
-        if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-        Ctx* c;
-        if (int e = ctx_get(device, &c)) return e;
+        Ctx* c = cs.c;
         if (!raw_path) {
             if (int e = dev_reserve(c->dspec, sizeof(cpx) * (size_t)CH * FW * F)) return e;
             spec = c->dspec.p;
@@ -1339,6 +1453,8 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
         maxkh = std::max(maxkh, std::min(kh[k], FH));
         maxkw = std::max(maxkw, std::min(kw[k], FW));
     }
+    CtxScope whole_call(device, (cudaStream_t)stream);      // see fftconv_convolution_fft
+    if (whole_call.err) return whole_call.err;
     OsCfg g1;
     const bool batched = K > 0 && N > 1 && out_on_device && !o.correlate && !o.force_generic &&
                          (o.path == PATH_AUTO || o.path == PATH_OSGEMM) && os_config(F, FH, FW, maxkh, maxkw, g1, 1);
@@ -1365,19 +1481,14 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
         const int nimg = std::min(G, N - n0);
         const float* d_data = data + (size_t)n0 * img;
         if (!data_on_device) {
-            std::lock_guard<std::mutex> lk(g_mu);
-            DeviceGuard guard(device);
-            if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-            Ctx* c;
-            if (int e = ctx_get(device, &c)) return e;
+            CtxScope cs(device, (cudaStream_t)stream);
+            if (cs.err) return cs.err;
+            Ctx* c = cs.c;
             if (int e = dev_reserve(c->ddata, sizeof(float) * img * nimg)) return e;
             CU(cudaMemcpyAsync(c->ddata.p, d_data, sizeof(float) * img * nimg, cudaMemcpyHostToDevice, (cudaStream_t)stream));
             d_data = (const float*)c->ddata.p;
         }
         if (tmp_bank) {
-            std::lock_guard<std::mutex> lk(g_mu);
-            DeviceGuard guard(device);
-            if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
             if (int e = bank_conv_images(tmp_bank, d_data, nimg, H, W, outs + (size_t)n0 * K, 1, o, (cudaStream_t)stream)) return e;
             continue;
         }
@@ -1408,11 +1519,9 @@ static int bank_create_impl(int K, const float* const* kernels, const int* kh, c
     OsCfg g;
     if (!os_config(F, 64, 64, maxkh, maxkw, g))
         return fail(FFTCONV_ERR_UNSUPPORTED, "prepared banks need templates of at most 32 x 32 (got %d x %d)", maxkh, maxkw);
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    Ctx* c;
-    if (int e = ctx_get(device, &c)) return e;
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
     cudaStream_t st = (cudaStream_t)stream;
     const int ntblk = (K + OS_TM - 1) / OS_TM;
     std::unique_ptr<fftconv_bank> b(new fftconv_bank{device, K, F, maxkh, maxkw, g.NKS, g.KC, nullptr, 0, nullptr, !in_workspace});
@@ -1492,7 +1601,7 @@ int fftconv_bank_info(const fftconv_bank* b, int* K, int* F, int* maxKH, int* ma
     return 0;
 }
 
-// nimg device-resident images [nimg][F][W][H] against a prepared bank (caller holds g_mu and has selected the device);
+// nimg device-resident images [nimg][F][W][H] against a prepared bank (caller holds the device lock and has selected the device: CtxScope);
 // outs: nimg * K planes, image-major.
 static int bank_conv_images(const fftconv_bank* b, const float* d_data, int nimg, int H, int W, float* const* outs,
                             int out_on_device, const fftconv_options& o, cudaStream_t st) {
@@ -1518,11 +1627,9 @@ int fftconv_bank_conv(const fftconv_bank* b, const float* data, int data_on_devi
     const int FH = fftconv_fft_size16(H + b->maxkh - 1), FW = fftconv_fft_size16(W + b->maxkw - 1);
     for (int k = 0; k < K; ++k)
         if (!outs[k]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(b->device);
-    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
-    Ctx* c;
-    if (int e = ctx_get(b->device, &c)) return e;
+    CtxScope cs(b->device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
     cudaStream_t st = (cudaStream_t)stream;
     const float* d_data = data;
     if (!data_on_device) {
@@ -1541,11 +1648,9 @@ int fftconv_bank_conv_max(const fftconv_bank* b, const float* data, int data_on_
     const int F = b->F, K = b->K;
     const int FH = fftconv_fft_size16(H + b->maxkh - 1), FW = fftconv_fft_size16(W + b->maxkw - 1);
     if (FH > 65535 || FW > 65535) return fail(FFTCONV_ERR_UNSUPPORTED, "plane too large for packed peak positions");
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(b->device);
-    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", b->device);
-    Ctx* c;
-    if (int e = ctx_get(b->device, &c)) return e;
+    CtxScope cs(b->device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
     cudaStream_t st = (cudaStream_t)stream;
     const float* d_data = data;
     if (!data_on_device) {
@@ -1578,9 +1683,9 @@ int fftconv_bank_conv_max(const fftconv_bank* b, const float* data, int data_on_
 
 void fftconv_bank_destroy(fftconv_bank* b) {
     if (!b) return;
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(b->device);
+    CtxScope cs(b->device, nullptr);
     if (b->owns) {
+        cudaDeviceSynchronize();          // calls that read the bank may still be running on any stream
         cudaFree(b->A);
         cudaFree(b->khw);
     }
@@ -1611,11 +1716,9 @@ int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_
     g_err.clear();
     if (!d_a || !d_b || n < 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
     if (n == 0) return 0;
-    std::lock_guard<std::mutex> lk(g_mu);
-    DeviceGuard guard(device);
-    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
-    Ctx* c;
-    if (int e = ctx_get(device, &c)) return e;
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
     const int grid = (int)std::min<long long>((n + 255) / 256, (long long)c->sm_count * 8);
     modulate_and_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((cpx*)d_a, (const cpx*)d_b, n, 1.0f / (float)n);
     LAUNCH_CHECK();
@@ -1625,7 +1728,7 @@ int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_
 long long fftconv_launch_count(void) { return g_launches.load(); }
 
 void fftconv_profile_enable(int on) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof_on = on != 0;
 }
 
@@ -1633,7 +1736,7 @@ int fftconv_profile_kinds(void) { return PK_COUNT; }
 const char* fftconv_profile_name(int kind) { return (kind >= 0 && kind < PK_COUNT) ? kProfNames[kind] : ""; }
 
 int fftconv_profile_read(int kind, double* total_ms, long long* launches, int reset) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     double ms = 0.0;
     long long n = 0;
     for (auto& r : g_prof) {
@@ -1657,10 +1760,15 @@ int fftconv_profile_read(int kind, double* total_ms, long long* launches, int re
 }
 
 long long fftconv_workspace_bytes(int device) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_ctx.find(device);
-    if (it == g_ctx.end()) return 0;
-    const Ctx& c = it->second;
+    Ctx* cp;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_ctx.find(device);
+        if (it == g_ctx.end()) return 0;
+        cp = &it->second;
+    }
+    Ctx& c = *cp;
+    std::lock_guard<std::recursive_mutex> lkc(c.mu);
     size_t s = c.T.cap + c.Z.cap + c.stage.cap + c.desc.cap + c.outstage.cap + c.dspec.cap + c.ddata.cap +
                c.priv.cap + c.Ag.cap + c.Wg.cap + c.osA.cap + c.osB.cap + c.osP.cap +
                c.osPlane.cap + c.osZ.cap + c.osPeaks.cap + c.bpS.cap + c.batchA.cap;
@@ -1669,11 +1777,13 @@ long long fftconv_workspace_bytes(int device) {
 }
 
 void fftconv_release(void) {
-    std::lock_guard<std::mutex> lk(g_mu);
+    std::vector<Ctx*> all;
+    { std::lock_guard<std::mutex> lk(g_mu); for (auto& kv : g_ctx) all.push_back(&kv.second); }
     int prev = -1;
     cudaGetDevice(&prev);
-    for (auto& kv : g_ctx) {
-        Ctx& c = kv.second;
+    for (Ctx* cp : all) {
+        Ctx& c = *cp;
+        std::lock_guard<std::recursive_mutex> lkc(c.mu);
         if (!c.inited) continue;
         cudaSetDevice(c.dev);
         cudaDeviceSynchronize();
@@ -1683,13 +1793,27 @@ void fftconv_release(void) {
                           &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks, &c.bpS, &c.batchA})
             if (b->p) cudaFree(b->p);
         if (c.pinned) cudaFreeHost(c.pinned);
+        if (c.bounce) cudaFreeHost(c.bounce);
+        for (auto& e : c.evb) if (e) cudaEventDestroy(e);
         if (c.pinned_free) cudaEventDestroy(c.pinned_free);
         for (auto& e : c.ev) if (e) cudaEventDestroy(e);
         if (c.side) cudaStreamDestroy(c.side);
         if (c.side2) cudaStreamDestroy(c.side2);
         for (auto& e : c.evf) if (e) cudaEventDestroy(e);
+        if (c.last_use) cudaEventDestroy(c.last_use);
+        // the entry stays in the map (another thread may hold a pointer to it): reset it to its pristine state
+        c.tw.clear(); c.ipmap.clear();
+        for (DevBuf* b : {&c.T, &c.Z, &c.stage, &c.desc, &c.outstage, &c.dspec, &c.ddata, &c.priv, &c.Ag, &c.Wg,
+                          &c.osA, &c.osB, &c.osP, &c.osPlane, &c.osZ, &c.osPeaks, &c.bpS, &c.batchA})
+            *b = DevBuf{};
+        c.pinned = nullptr; c.pinned_cap = 0; c.pinned_free = nullptr; c.side = c.side2 = nullptr;
+        c.bounce = nullptr; c.bounce_cap = 0;
+        for (auto& e : c.evb) e = nullptr;
+        for (auto& e : c.ev) e = nullptr;
+        for (auto& e : c.evf) e = nullptr;
+        c.last_use = nullptr; c.last_stream = nullptr; c.used = false; c.spec_ready = nullptr;
+        c.inited = false;
     }
-    g_ctx.clear();
     if (prev >= 0) cudaSetDevice(prev);
 }
 
@@ -1712,11 +1836,11 @@ int fftconv_query_path(int H, int W, int F, int maxKH, int maxKW, int K, const f
 }
 
 int fftconv_spectrum_ready_event(int device, void* cuda_event) {
-    std::lock_guard<std::mutex> lk(g_mu);
     DeviceGuard dg(device);
     if (!dg.ok) return fail(FFTCONV_ERR_CUDA, "cannot select device %d", device);
     Ctx* c;
     if (int e = ctx_get(device, &c)) return e;
+    std::lock_guard<std::recursive_mutex> lkc(c->mu);
     c->spec_ready = reinterpret_cast<cudaEvent_t>(cuda_event);
     return 0;
 }
@@ -1790,7 +1914,7 @@ int fftconv_peer_pull(void* dst, const void* src_mapped, size_t bytes, int devic
     const size_t n16 = bytes / 16;
     const int ntail = (int)(bytes - n16 * 16);
     Ctx* c;
-    { std::lock_guard<std::mutex> lk(g_mu); if (int e = ctx_get(device, &c)) return e; }
+    if (int e = ctx_get(device, &c)) return e;
     peer_pull_kernel<<<c->sm_count * 2, 512, 0, (cudaStream_t)stream>>>((uint4*)dst, (const uint4*)src_mapped, n16,
                                                                       (unsigned char*)dst + n16 * 16,
                                                                       (const unsigned char*)src_mapped + n16 * 16, ntail);

@@ -7,8 +7,9 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
     int nthreads = 0;
     const double* threads = thread_arg(nrhs, prhs, 2, nthreads);
     const mxGPUArray* spec = mxGPUCreateFromMxArray(prhs[0]);
-    const mwSize* sd = mxGPUGetDimensions(spec);                                    // :92-98
-    const int CH = (int)sd[0], FW = (int)sd[1], F = (int)sd[2], FH = (CH - 1) * 2;
+    int CH, FW, F;
+    spectrum_dims(spec, CH, FW, F);                                                 // :92-98
+    const int FH = (CH - 1) * 2;
     KernelCell c;
     c.handles.push_back(spec);
     marshal_cell(prhs[1], true, c);

@@ -1,9 +1,11 @@
-// Shared marshalling for the MEX shims.  NOT BUILT in this repo's CI (no MATLAB in the image); the
-// shims only translate mxArray / mxGPUArray to the plain-pointer C ABI of include/fftconv.h, so all
-// arithmetic is covered by the C-ABI tests.  Build (on a MATLAB box):
-//   mex -largeArrayDims cudaConvolutionFFT.cpp -I../../include -L../fftconv_b200 -lfftconv -lmwgpu
+// Shared marshalling for the MEX shims.  The shims only translate mxArray / mxGPUArray to the plain-pointer C ABI of
+// include/fftconv.h.  Build on a MATLAB box:
+//   mex -largeArrayDims cudaConvolutionFFT.cpp -I../../include -L../fftconv_b200 -lfftconv -lmwgpu -lcudart
+// No MATLAB in this image: tests/mex_stub/ compiles the same sources against a stand-in mex.h / mxGPUArray.h and drives
+// marshal_cell / alloc_out_cell and the reference's error ids with fake mxArrays (tests/test_mex_shims.py).
 #pragma once
 #include <vector>
+#include <cuda_runtime.h>
 #include "mex.h"
 #include "gpu/mxGPUArray.h"
 #include "../../include/fftconv.h"
@@ -24,7 +26,10 @@ struct KernelCell {
 
 // kernel cell -> pointer arrays; raises the reference's errors (src/cudaConvFFTData.cu:106-107,194-225)
 static void marshal_cell(const mxArray* cell, bool allow_gpu, KernelCell& c) {
-    if (mxGetClassID(cell) != mxCELL_CLASS) mexErrMsgIdAndTxt(kErrConv, "Kernel must be a cell array");
+    if (mxGetClassID(cell) != mxCELL_CLASS) {
+        c.release();                                  // the caller may already hold the spectrum handle in c
+        mexErrMsgIdAndTxt(kErrConv, "Kernel must be a cell array");
+    }
     const mwSize K = mxGetNumberOfElements(cell);
     for (mwSize k = 0; k < K; ++k) {
         const mxArray* a = mxGetCell(cell, k);
@@ -63,6 +68,14 @@ static mxArray* alloc_out_cell(int K, int FH, int FW, std::vector<float*>& outs)
         mxSetCell(cell, k, p);
     }
     return cell;
+}
+
+// (CH, FW, F) of a spectrum gpuArray (src/cudaConvFFTData.cu:92-98).  MATLAB drops trailing singleton dimensions, so a
+// single-channel spectrum has two dimensions: F defaults to 1 instead of reading past the dimension vector.
+static void spectrum_dims(const mxGPUArray* spec, int& CH, int& FW, int& F) {
+    const mwSize nd = mxGPUGetNumberOfDimensions(spec);
+    const mwSize* sd = mxGPUGetDimensions(spec);
+    CH = (int)sd[0]; FW = nd > 1 ? (int)sd[1] : 1; F = nd > 2 ? (int)sd[2] : 1;
 }
 
 static const double* thread_arg(int nrhs, const mxArray* prhs[], int idx, int& n) {

@@ -234,3 +234,70 @@ def test_torch_ops_match_the_mirror(fc, oracle):
         ref = oracle.direct_conv64_c(data, bank[k], FH, FW)
         assert oracle.rel_l2(out[k].cpu().numpy().T, ref) < TOL
         assert oracle.rel_l2(out2[0, k].cpu().numpy().T, ref) < TOL
+
+
+def test_batch_tail_group_of_one_image_small_bank_declared_max_larger(fc, oracle):
+    """A tail group that holds ONE image, a bank below the automatic overlap-save threshold (K < 64) and a declared
+    maximum larger than the kernels (so no per-call bank is built): the group still has no compat spectrum, so it must be
+    served by the overlap-save path (used to dereference a null spectrum)."""
+    import ctypes
+    import torch
+    N, H, W, F, kh, kw, K = 11, 600, 600, 2, 5, 5, 9              # 121 tiles per image -> 10 images per group, tail of 1
+    rng = np.random.default_rng(47)
+    data = rng.random((N, H, W, F), dtype=np.float32)
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.1).astype(np.float32)
+    d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(0, 3, 2, 1))).cuda()
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    mk = 8                                                          # declared maximum 8 x 8 > 5 x 5
+    FH, FW = fc.computeFFTsize16(H + mk - 1), fc.computeFFTsize16(W + mk - 1)
+    out = torch.empty((N, K, FW, FH), device="cuda")
+    kp = (ctypes.c_void_p * K)(*[b_t.data_ptr() + 4 * k * F * kw * kh for k in range(K)])
+    op = (ctypes.c_void_p * (N * K))(*[out.data_ptr() + 4 * FW * FH * i for i in range(N * K)])
+    khs = (ctypes.c_int * K)(*([kh] * K))
+    ond = (ctypes.c_ubyte * K)(*([1] * K))
+    rc = fc.lib().fftconv_conv_batch(d_t.data_ptr(), 1, N, H, W, F, mk, mk, K, kp, khs, khs, None, ond, op, 1, None, 0,
+                                     torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, fc.last_error()
+    torch.cuda.synchronize()
+    for n, k in ((0, 0), (9, 4), (10, 8)):
+        ref = oracle.direct_conv64_c(data[n], bank[k], FH, FW)
+        assert oracle.rel_l2(out[n, k].cpu().numpy().T, ref) < TOL, (n, k)
+
+
+def test_calls_on_two_streams_and_two_host_threads_do_not_race(fc, oracle):
+    """The cached scratch is shared by all streams of a device: device-output calls issued back to back on two streams,
+    and host-output calls from two host threads, must each see their own image."""
+    import threading
+    import torch
+    rng = np.random.default_rng(52)
+    H = W = 120; F = 4; kh = kw = 9; K = 70
+    datas = [rng.random((H, W, F), dtype=np.float32) for _ in range(2)]
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.1).astype(np.float32)
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+    refs = [oracle.direct_conv64_c(d, bank[K - 1], FH, FW) for d in datas]
+    # two streams, device outputs, no host synchronisation in between
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    d_ts = [torch.from_numpy(np.ascontiguousarray(d.transpose(2, 1, 0))).cuda() for d in datas]
+    outs = [torch.empty((K, FW, FH), device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i in range(2):
+            with torch.cuda.stream(streams[i]):
+                spec = fc.fft_data_device(d_ts[i], H, W, F, kh, kw, stream=streams[i])
+                fc.conv_bank(spec, b_t, kh, kw, outs[i], stream=streams[i])
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert oracle.rel_l2(outs[i][K - 1].cpu().numpy().T, refs[i]) < TOL, i
+    # two host threads through the one-shot entry point (host buffers)
+    res = [None, None]
+
+    def work(i):
+        for _ in range(4):
+            res[i] = fc.cudaConvolutionFFT(datas[i], kh, kw, [bank[k] for k in range(K)])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(2):
+        assert oracle.rel_l2(res[i][K - 1], refs[i]) < TOL, i
