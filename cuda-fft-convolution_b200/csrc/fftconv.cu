@@ -654,10 +654,21 @@ static int os_reserve_chunk(Ctx& c, const OsCfg& g, int KC_templates, bool need_
     return 0;
 }
 
+// fused detection (fftconv_bank_conv_detect / _topk): per-template candidate keys, counters, thresholds, biases (device)
+struct OsDetect {
+    int mode = 0;                  // 0 off, 1 threshold, 3 top-k (candidate pass + threshold pass, both over the same P)
+    int cap = 0, k = 0;
+    unsigned long long* keys = nullptr;    // [K][cap]
+    unsigned int* count = nullptr;         // [K]
+    float* thr = nullptr;                  // [K]
+    const float* bias = nullptr;           // [K] or nullptr
+};
+static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStream_t st);
+static int os_chunk_detect(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, const OsDetect& det, int k0, cudaStream_t st);
 static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
                     const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0, const float* bankA = nullptr,
                     unsigned long long* peak_keys = nullptr, const int2* khw = nullptr, int H = 0, int W = 0,
-                    cudaEvent_t data_ready = nullptr) {
+                    cudaEvent_t data_ready = nullptr, const OsDetect* det = nullptr, int det_k0 = 0) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
     if (!bankA) {
         OsKArgs a{};
@@ -702,20 +713,48 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
         a.crop_h = opt.crop_h > 0 ? opt.crop_h : g.FH;
         a.crop_w = opt.crop_w > 0 ? opt.crop_w : g.FW;
         a.out_ld = opt.out_ld > 0 ? opt.out_ld : a.crop_h;
-        ProfScope ps(PK_OS_INV, st);
-        OsTensorMap tm;
-        const int ntb = (nk + OS_TM - 1) / OS_TM;
-        // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
-        if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
-            dim3 grid(g.NNB * (g.RS / 8), nk);             // (tile block, group of 4 tiles) x template
-            os_inverse_tma<<<grid, 256, OS_ITMA_SMEM, st>>>(a, tm);
-        } else {
-            dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
-            os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);
-        }
+        if (det && det->mode) return os_chunk_detect(c, g, a, nk, *det, det_k0, st);
+        return os_chunk_inverse(c, g, a, nk, st);
+    }
+}
+
+static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStream_t st) {
+    ProfScope ps(PK_OS_INV, st);
+    OsTensorMap tm;
+    const int ntb = (nk + OS_TM - 1) / OS_TM;
+    // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
+    if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
+        dim3 grid(g.NNB * (g.RS / 8), nk);             // (tile block, group of 4 tiles) x template
+        os_inverse_tma<<<grid, 256, OS_ITMA_SMEM, st>>>(a, tm);
+    } else {
+        dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
+        os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);
+    }
+    LAUNCH_CHECK();
+    (void)c;
+    return 0;
+}
+
+// Detection over the product spectra of one chunk (templates k0 .. k0 + nk - 1 of the call).
+static int os_chunk_detect(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, const OsDetect& det, int k0, cudaStream_t st) {
+    a.outs = nullptr; a.peak_keys = nullptr; a.corr = 0;
+    a.det_cap = det.cap;
+    a.det_keys = det.keys + (size_t)k0 * det.cap;
+    a.det_count = det.count + k0;
+    a.det_thr = det.thr + k0;
+    a.det_bias = det.bias ? det.bias + k0 : nullptr;
+    if (det.mode == 3) {
+        // pass 1: one candidate per lane (its own best response); the k-th largest candidate bounds the k-th largest
+        // response from below and becomes the template's threshold for pass 2
+        CU(cudaMemsetAsync(a.det_keys, 0, sizeof(unsigned long long) * (size_t)nk * det.cap, st));
+        a.det_mode = 2;
+        if (int e = os_chunk_inverse(c, g, a, nk, st)) return e;
+        os_det_select<<<nk, 256, 0, st>>>(a.det_keys, nullptr, det.cap, det.k, nullptr, det.thr + k0, nullptr);
         LAUNCH_CHECK();
     }
-    return 0;
+    CU(cudaMemsetAsync(a.det_count, 0, sizeof(unsigned int) * (size_t)nk, st));
+    a.det_mode = 1;
+    return os_chunk_inverse(c, g, a, nk, st);
 }
 
 // ------------------------------------------------------------------ conv core
@@ -739,6 +778,7 @@ struct ConvArgs {
     int bank_maxkh = 0, bank_maxkw = 0;
     unsigned long long* peak_keys = nullptr;   // fused maximum (fftconv_bank_conv_max): K packed keys, no planes
     const int2* bank_khw = nullptr;            // (kh, kw) of every template of the bank (device)
+    OsDetect det;                  // fused detection (no planes)
     cudaEvent_t spec_ready = nullptr;   // one-shot event handed over by fftconv_spectrum_ready_event (consumed by conv_impl)
     int nimg = 1;                  // batched entry point: nimg images [nimg][F][rawW][rawH] (raw, device, overlap-save path
                                    // only); outs then holds nimg*K device planes, image-major
@@ -1155,7 +1195,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     }
     for (size_t ch = 0; ch + 1 < bounds.size(); ++ch)
         for (int k = bounds[ch]; k < bounds[ch + 1]; ++k)
-            h_outp[k] = a.peak_keys ? nullptr : a.out_on_device ? a.outs[k]
+            h_outp[k] = (a.peak_keys || a.det.mode) ? nullptr : a.out_on_device ? a.outs[k]
                                         : reinterpret_cast<float*>(c.outstage.p) + plane * (size_t)((k - bounds[ch]) + (ch & 1) * KC);
     for (size_t i = K; i < NO; ++i) h_outp[i] = a.outs[i];         // images 1.. of a batch (device planes)
     CU(cudaMemcpyAsync(c.desc.p, c.pinned, desc_bytes, cudaMemcpyHostToDevice, st));
@@ -1183,7 +1223,7 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
             e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K,
                          a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr,
                          a.peak_keys ? a.peak_keys + k0 : nullptr, (a.bank_khw ? a.bank_khw : d_khw) + k0, a.rawH, a.rawW,
-                         (chunk == 0 && !a.bankA) ? c.evf[1] : nullptr);
+                         (chunk == 0 && !a.bankA) ? c.evf[1] : nullptr, &a.det, k0);
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else if (bigp)
@@ -1679,6 +1719,95 @@ int fftconv_bank_conv_max(const fftconv_bank* b, const float* data, int data_on_
         CU(cudaStreamSynchronize(st));
     }
     return 0;
+}
+
+// shared by fftconv_bank_conv_detect (mode 1) and fftconv_bank_conv_topk (mode 3)
+static int bank_detect_impl(const fftconv_bank* b, const float* data, int data_on_device, int H, int W, const float* bias,
+                            int mode, float threshold, int nsel, fftconv_peak* dets, int* counts, int out_on_device, void* stream) {
+    g_err.clear();
+    if (!b || !data || !dets || H <= 0 || W <= 0 || nsel <= 0 || nsel > 4096)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    const int F = b->F, K = b->K;
+    const int FH = fftconv_fft_size16(H + b->maxkh - 1), FW = fftconv_fft_size16(W + b->maxkw - 1);
+    if (FH > 65535 || FW > 65535) return fail(FFTCONV_ERR_UNSUPPORTED, "plane too large for packed peak positions");
+    OsCfg g;
+    if (!os_config(F, FH, FW, b->maxkh, b->maxkw, g)) return fail(FFTCONV_ERR_UNSUPPORTED, "plane outside the range of the overlap-save path");
+    CtxScope cs(b->device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    Ctx* c = cs.c;
+    cudaStream_t st = (cudaStream_t)stream;
+    const float* d_data = data;
+    if (!data_on_device) {
+        const size_t bytes = sizeof(float) * (size_t)H * W * F;
+        if (int e = dev_reserve(c->ddata, bytes)) return e;
+        CU(cudaMemcpyAsync(c->ddata.p, data, bytes, cudaMemcpyHostToDevice, st));
+        d_data = (const float*)c->ddata.p;
+    }
+    // candidate slots per template: one per lane of the candidate pass (64 per tile), at least 2048, at least 4 per pick
+    const int cap = std::max(std::max(g.NT * 64, 2048), 4 * nsel);
+    const size_t keys_b = sizeof(unsigned long long) * (size_t)K * cap;
+    const size_t peaks_b = sizeof(fftconv_peak) * (size_t)K * nsel;
+    const size_t total = keys_b + peaks_b + (sizeof(unsigned int) + sizeof(int) + 2 * sizeof(float)) * (size_t)K + 256;
+    if (int e = dev_reserve(c->osPeaks, total)) return e;
+    char* base = (char*)c->osPeaks.p;
+    unsigned long long* keys = (unsigned long long*)base;
+    fftconv_peak* d_dets = out_on_device ? dets : (fftconv_peak*)(base + keys_b);
+    unsigned int* count = (unsigned int*)(base + keys_b + peaks_b);
+    int* d_counts = (int*)(count + K);
+    float* thr = (float*)(d_counts + K);
+    float* d_bias = thr + K;
+    if (bias) {                                       // K floats from the host through the pinned staging buffer
+        if (int e = pinned_reserve(*c, sizeof(float) * (size_t)K)) return e;
+        CU(cudaEventSynchronize(c->pinned_free));
+        memcpy(c->pinned, bias, sizeof(float) * (size_t)K);
+        CU(cudaMemcpyAsync(d_bias, c->pinned, sizeof(float) * (size_t)K, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(c->pinned_free, st));
+    }
+    if (mode == 1) {
+        os_fill_f32<<<(K + 255) / 256, 256, 0, st>>>(thr, K, threshold);
+        LAUNCH_CHECK();
+    }
+    ConvArgs a;
+    a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = F; a.K = K;
+    a.kernels = nullptr; a.outs = nullptr; a.out_on_device = true;
+    a.opt = fftconv_options{}; a.pipelined = false;
+    a.d_raw = d_data; a.rawH = H; a.rawW = W;
+    a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw; a.bank_khw = b->khw;
+    a.det.mode = mode; a.det.cap = cap; a.det.k = nsel; a.det.keys = keys; a.det.count = count; a.det.thr = thr;
+    a.det.bias = bias ? d_bias : nullptr;
+    if (int e = run_conv(*c, a, st)) return e;
+    static_assert(sizeof(fftconv_peak) == sizeof(fftconv_peak_dev), "peak layouts differ");
+    os_det_select<<<K, 256, 0, st>>>(keys, count, cap, nsel, reinterpret_cast<fftconv_peak_dev*>(d_dets), nullptr, d_counts);
+    LAUNCH_CHECK();
+    // host results (and the overflow check of the top-k mode) need the counts
+    std::vector<int> h_counts;
+    if (!out_on_device || mode == 3) {
+        h_counts.resize(K);
+        CU(cudaMemcpyAsync(h_counts.data(), d_counts, sizeof(int) * (size_t)K, cudaMemcpyDeviceToHost, st));
+        if (!out_on_device) CU(cudaMemcpyAsync(dets, d_dets, peaks_b, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (mode == 3)
+            for (int k = 0; k < K; ++k)
+                if (h_counts[k] > cap)
+                    return fail(FFTCONV_ERR_UNSUPPORTED, "top-k: template %d has %d responses above its candidate bound (capacity %d): "
+                                "plateau-like response, use fftconv_bank_conv_detect with a threshold", k, h_counts[k], cap);
+    }
+    if (counts) {
+        if (out_on_device) CU(cudaMemcpyAsync(counts, d_counts, sizeof(int) * (size_t)K, cudaMemcpyDeviceToDevice, st));
+        else memcpy(counts, h_counts.data(), sizeof(int) * (size_t)K);
+    }
+    return 0;
+}
+
+int fftconv_bank_conv_detect(const fftconv_bank* b, const float* data, int data_on_device, int H, int W, const float* bias,
+                             float threshold, int max_per_template, fftconv_peak* dets, int* counts, int out_on_device, void* stream) {
+    return bank_detect_impl(b, data, data_on_device, H, W, bias, 1, threshold, max_per_template, dets, counts, out_on_device, stream);
+}
+
+int fftconv_bank_conv_topk(const fftconv_bank* b, const float* data, int data_on_device, int H, int W, const float* bias,
+                           int k, fftconv_peak* dets, int out_on_device, void* stream) {
+    if (k > 64) return fail(FFTCONV_ERR_INVALID_INPUT, "top-k: k must be at most 64");
+    return bank_detect_impl(b, data, data_on_device, H, W, bias, 3, 0.f, k, dets, nullptr, out_on_device, stream);
 }
 
 void fftconv_bank_destroy(fftconv_bank* b) {

@@ -895,7 +895,18 @@ struct OsInvArgs {
     // fused reduction (fftconv_bank_conv_max): when peak_keys != nullptr no plane is written; every template keeps the
     // maximum of its full linear convolution (H + kh - 1) x (W + kw - 1) as a packed (ordered value, position) key
     unsigned long long* peak_keys;
-    const int2* khw;        // (kh, kw) per template of the chunk (peak and correlation modes)
+    const int2* khw;        // (kh, kw) per template of the chunk (peak, detection and correlation modes)
+    // fused detection (fftconv_bank_conv_detect / _topk): no plane is written either.  Every response r = conv + bias[t]
+    // of the template's full linear convolution is compared with thr[t]:
+    //   det_mode 1   r >= thr[t]  ->  key appended to det_keys[t][slot], slot = atomicAdd(det_count[t]) (kept while < det_cap)
+    //   det_mode 2   candidate pass of the top-k selection: every lane writes the key of its own best response to
+    //                det_keys[t][tile * 32 + lane] (0 = none); the k-th largest candidate is a lower bound of the k-th
+    //                largest response, so a det_mode 1 pass with that bound as thr[t] captures the exact top-k
+    int det_mode, det_cap;
+    unsigned long long* det_keys;
+    unsigned int* det_count;
+    const float* det_bias;  // per template of the chunk, or nullptr
+    const float* det_thr;   // per template of the chunk (det_mode 1)
     int H, W;
     int dbg;                // timing experiments only (FFTCONV_OS_DBG): 16 = contiguous load instead of the gather, 32 = no plane store
     int corr;               // correlation mode: plane position (Y, X) of the flipped-template convolution is stored at
@@ -922,6 +933,161 @@ __global__ void os_peak_finalize(const unsigned long long* keys, int K, fftconv_
     out[k].value = __uint_as_float(u); out[k].y = (int)(pos & 0xFFFFu); out[k].x = (int)(pos >> 16); out[k].pad = 0;
 }
 
+// Tail of both inverse kernels: the 64 outputs a lane holds after pass 2 (rows ylo / yhi = lane - oy0 (+32), columns
+// 4*j1 + par (+2) - ox0 of the valid block of its tile) go to the plane (crop fused), to the plane shifted by the template
+// extent (correlation mode), or into the fused reductions (maximum, detections) -- in which case no plane is written.
+struct OsTileOut { float* dst; int ny, nx, y0, x0; };
+__device__ __forceinline__ void os_inverse_emit(const OsInvArgs& a, int t, int lane, int par, int tile_index, const OsTileOut& T,
+                                                const float (&reA)[16], const float (&imA)[16], const float (&reB)[16], const float (&imB)[16])
+{
+    const int ny = T.ny, nx = T.nx;
+    const int y = lane;
+    const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
+    const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
+    if (a.peak_keys || a.det_mode == 2) {
+        const float bias = (a.det_mode && a.det_bias) ? a.det_bias[t] : 0.f;
+        float best = -INFINITY; int by = 0, bx = 0;
+        auto upd = [&](float v, int yy, int xx) { if (v > best) { best = v; by = yy; bx = xx; } };
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) {                             // ascending x: the first maximum wins
+            const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+            if (xa >= 0 && xa < nx) { if (wlo) upd(reA[j1], ylo, xa); if (whi) upd(imA[j1], yhi, xa); }
+            if (xb >= 0 && xb < nx) { if (wlo) upd(reB[j1], ylo, xb); if (whi) upd(imB[j1], yhi, xb); }
+        }
+        unsigned long long key = best > -INFINITY ? os_peak_key(best + bias, T.y0 + by, T.x0 + bx) : 0ull;
+        if (a.det_mode == 2) {                                        // one candidate per (tile, parity, lane)
+            a.det_keys[(size_t)t * a.det_cap + (size_t)(tile_index * 2 + par) * 32 + lane] = key;
+            return;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+            key = other > key ? other : key;
+        }
+        if (lane == 0 && key) atomicMax(a.peak_keys + t, key);
+        return;
+    }
+    if (a.det_mode == 1) {
+        const float bias = a.det_bias ? a.det_bias[t] : 0.f, thr = a.det_thr[t];
+        unsigned long long* keys = a.det_keys + (size_t)t * a.det_cap;
+        auto hit = [&](float v, int yy, int xx) {
+            const float r = v + bias;
+            if (r >= thr) {
+                const unsigned slot = atomicAdd(a.det_count + t, 1u);
+                if (slot < (unsigned)a.det_cap) keys[slot] = os_peak_key(r, T.y0 + yy, T.x0 + xx);
+            }
+        };
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) {
+            const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+            if (xa >= 0 && xa < nx) { if (wlo) hit(reA[j1], ylo, xa); if (whi) hit(imA[j1], yhi, xa); }
+            if (xb >= 0 && xb < nx) { if (wlo) hit(reB[j1], ylo, xb); if (whi) hit(imB[j1], yhi, xb); }
+        }
+        return;
+    }
+    if (a.corr) {
+        const int2 k = a.khw[t];
+        float* base = T.dst;
+        int ydl = T.y0 + ylo - (k.x - 1), ydh = T.y0 + yhi - (k.x - 1);
+        if (ydl < 0) ydl += a.FH;
+        if (ydh < 0) ydh += a.FH;
+        const bool slo = wlo && ydl < a.crop_h, shi = whi && ydh < a.crop_h;
+        const int xs = T.x0 - (k.y - 1);
+        auto put = [&](int xr, float vlo, float vhi) {
+            if (xr < 0 || xr >= nx) return;
+            int xd = xs + xr;
+            if (xd < 0) xd += a.FW;
+            if (xd >= a.crop_w) return;
+            float* d = base + (size_t)xd * a.out_ld;
+            if (slo) d[ydl] = vlo;
+            if (shi) d[ydh] = vhi;
+        };
+#pragma unroll
+        for (int j1 = 0; j1 < 16; ++j1) {
+            put(4 * j1 + par - a.ox0, reA[j1], imA[j1]);
+            put(4 * j1 + par + 2 - a.ox0, reB[j1], imB[j1]);
+        }
+        return;
+    }
+    float* dst = T.dst + ylo;
+    if (a.dbg & 32) { if (reA[3] == 1.2345f) dst[0] = imB[5]; return; }
+#pragma unroll
+    for (int j1 = 0; j1 < 16; ++j1) {
+        const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
+        if (xa >= 0 && xa < nx) {
+            float* d = dst + (size_t)xa * a.out_ld;
+            if (wlo) d[0] = reA[j1];
+            if (whi) d[32] = imA[j1];
+        }
+        if (xb >= 0 && xb < nx) {
+            float* d = dst + (size_t)xb * a.out_ld;
+            if (wlo) d[0] = reB[j1];
+            if (whi) d[32] = imB[j1];
+        }
+    }
+}
+
+// Detection finalisation, one CTA per template: the `nsel` largest of the template's candidate keys, in descending order
+// (repeated block-wide maximum below the previous pick; keys are unique because they carry the position).
+//   n = min(count[t], cap) when count != nullptr, else cap (fixed candidate slots, empty = 0)
+//   out_peaks != nullptr : peaks[t][i] = pick i (value -inf, y = x = -1 when fewer than nsel candidates exist)
+//   out_thr   != nullptr : thr[t] = value of pick nsel-1, or -inf when fewer exist (lower bound for the top-k second pass)
+//   out_counts!= nullptr : counts[t] = count[t] (every response found, including those beyond cap)
+__global__ void __launch_bounds__(256) os_det_select(const unsigned long long* __restrict__ keys, const unsigned int* __restrict__ count,
+                                                     int cap, int nsel, fftconv_peak_dev* out_peaks, float* out_thr, int* out_counts)
+{
+    __shared__ unsigned long long red[8];
+    __shared__ unsigned long long last_s;
+    const int t = blockIdx.x;
+    const unsigned long long* k = keys + (size_t)t * cap;
+    const int n = count ? (int)min(count[t], (unsigned)cap) : cap;
+    if (out_counts && threadIdx.x == 0) out_counts[t] = count ? (int)min(count[t], 0x7fffffffu) : 0;
+    unsigned long long last = ~0ull;
+    for (int i = 0; i < nsel; ++i) {
+        unsigned long long best = 0;
+        for (int j = threadIdx.x; j < n; j += 256) {
+            const unsigned long long v = k[j];
+            if (v < last && v > best) best = v;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) best = red[w] > best ? red[w] : best;
+            last_s = best;
+            if (out_peaks) {
+                fftconv_peak_dev pk;
+                if (best) {
+                    const unsigned o = (unsigned)(best >> 32), pos = 0xFFFFFFFFu - (unsigned)(best & 0xFFFFFFFFu);
+                    const unsigned u = (o & 0x80000000u) ? (o ^ 0x80000000u) : ~o;
+                    pk.value = __uint_as_float(u); pk.y = (int)(pos & 0xFFFFu); pk.x = (int)(pos >> 16); pk.pad = 0;
+                } else { pk.value = -INFINITY; pk.y = -1; pk.x = -1; pk.pad = 0; }
+                out_peaks[(size_t)t * nsel + i] = pk;
+            }
+            if (out_thr && i == nsel - 1) {
+                float thr = -INFINITY;
+                if (best) {
+                    const unsigned o = (unsigned)(best >> 32);
+                    thr = __uint_as_float((o & 0x80000000u) ? (o ^ 0x80000000u) : ~o);
+                }
+                out_thr[t] = thr;
+            }
+        }
+        __syncthreads();
+        last = last_s;
+        if (last == 0) last = 0;           // nothing left: the remaining picks stay empty (best stays 0)
+    }
+}
+
+__global__ void os_fill_f32(float* p, int n, float v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 __device__ __forceinline__ int os_icol(int v) { return v * OS_ICOL + ((v >> 5) << 2); }
 
 __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a)
@@ -943,13 +1109,12 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
             const int img = m / a.NTimg, mt = m - img * a.NTimg;
             const int tj = mt / a.nth, ti = mt - tj * a.nth;
             const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
-            if (a.peak_keys) {                    // region of the full linear convolution of THIS template
+            tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+            if (a.peak_keys || a.det_mode) {      // region of the full linear convolution of THIS template
                 const int2 k = a.khw[t];
                 ny = min(a.Sh, a.H + k.x - 1 - Y0); nx = min(a.Sw, a.W + k.y - 1 - X0);
-                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
             } else if (a.corr) {
                 ny = min(a.Sh, a.FH - Y0); nx = min(a.Sw, a.FW - X0);
-                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
                 d = a.outs[(size_t)img * a.out_img_stride + t];
             } else {
                 ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
@@ -1038,66 +1203,8 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
         else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
-        const int ny = tile_ny[gq], nx = tile_nx[gq];
-        const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
-        const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
-        if (a.peak_keys) {
-            float best = -INFINITY; int by = 0, bx = 0;
-            auto upd = [&](float v, int yy, int xx) { if (v > best) { best = v; by = yy; bx = xx; } };
-#pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {                             // ascending x: the first maximum wins
-                const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
-                if (xa >= 0 && xa < nx) { if (wlo) upd(reA[j1], ylo, xa); if (whi) upd(imA[j1], yhi, xa); }
-                if (xb >= 0 && xb < nx) { if (wlo) upd(reB[j1], ylo, xb); if (whi) upd(imB[j1], yhi, xb); }
-            }
-            unsigned long long key = best > -INFINITY ? os_peak_key(best, tile_y0[gq] + by, tile_x0[gq] + bx) : 0ull;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                key = other > key ? other : key;
-            }
-            if (lane == 0 && key) atomicMax(a.peak_keys + t, key);
-            return;
-        }
-        if (a.corr) {
-            const int2 k = a.khw[t];
-            float* base = tile_dst[gq];
-            int ydl = tile_y0[gq] + ylo - (k.x - 1), ydh = tile_y0[gq] + yhi - (k.x - 1);
-            if (ydl < 0) ydl += a.FH;
-            if (ydh < 0) ydh += a.FH;
-            const bool slo = wlo && ydl < a.crop_h, shi = whi && ydh < a.crop_h;
-            const int xs = tile_x0[gq] - (k.y - 1);
-            auto put = [&](int xr, float vlo, float vhi) {
-                if (xr < 0 || xr >= nx) return;
-                int xd = xs + xr;
-                if (xd < 0) xd += a.FW;
-                if (xd >= a.crop_w) return;
-                float* d = base + (size_t)xd * a.out_ld;
-                if (slo) d[ydl] = vlo;
-                if (shi) d[ydh] = vhi;
-            };
-#pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {
-                put(4 * j1 + par - a.ox0, reA[j1], imA[j1]);
-                put(4 * j1 + par + 2 - a.ox0, reB[j1], imB[j1]);
-            }
-            return;
-        }
-        float* dst = tile_dst[gq] + ylo;
-#pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) {
-            const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
-            if (xa >= 0 && xa < nx) {
-                float* d = dst + (size_t)xa * a.out_ld;
-                if (wlo) d[0] = reA[j1];
-                if (whi) d[32] = imA[j1];
-            }
-            if (xb >= 0 && xb < nx) {
-                float* d = dst + (size_t)xb * a.out_ld;
-                if (wlo) d[0] = reB[j1];
-                if (whi) d[32] = imB[j1];
-            }
-        }
+        const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq]};
+        os_inverse_emit(a, t, lane, par, m0 + gq, T, reA, imA, reB, imB);
     }
 }
 
@@ -1146,13 +1253,12 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
             const int img = m / a.NTimg, mt = m - img * a.NTimg;
             const int tj = mt / a.nth, ti = mt - tj * a.nth;
             const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
-            if (a.peak_keys) {                    // region of the full linear convolution of THIS template
+            tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
+            if (a.peak_keys || a.det_mode) {      // region of the full linear convolution of THIS template
                 const int2 k = a.khw[t];
                 ny = min(a.Sh, a.H + k.x - 1 - Y0); nx = min(a.Sw, a.W + k.y - 1 - X0);
-                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
             } else if (a.corr) {
                 ny = min(a.Sh, a.FH - Y0); nx = min(a.Sw, a.FW - X0);
-                tile_y0[threadIdx.x] = Y0; tile_x0[threadIdx.x] = X0;
                 d = a.outs[(size_t)img * a.out_img_stride + t];
             } else {
                 ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
@@ -1231,67 +1337,8 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
         else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
-        const int ny = tile_ny[gq], nx = tile_nx[gq];
-        const int ylo = y - a.oy0, yhi = y + 32 - a.oy0;                   // rows of the valid block held by this lane
-        const bool wlo = ylo >= 0 && ylo < ny, whi = yhi < ny;
-        if (a.peak_keys) {
-            float best = -INFINITY; int by = 0, bx = 0;
-            auto upd = [&](float v, int yy, int xx) { if (v > best) { best = v; by = yy; bx = xx; } };
-#pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {                             // ascending x: the first maximum wins
-                const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
-                if (xa >= 0 && xa < nx) { if (wlo) upd(reA[j1], ylo, xa); if (whi) upd(imA[j1], yhi, xa); }
-                if (xb >= 0 && xb < nx) { if (wlo) upd(reB[j1], ylo, xb); if (whi) upd(imB[j1], yhi, xb); }
-            }
-            unsigned long long key = best > -INFINITY ? os_peak_key(best, tile_y0[gq] + by, tile_x0[gq] + bx) : 0ull;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                key = other > key ? other : key;
-            }
-            if (lane == 0 && key) atomicMax(a.peak_keys + t, key);
-            return;
-        }
-        if (a.corr) {
-            const int2 k = a.khw[t];
-            float* base = tile_dst[gq];
-            int ydl = tile_y0[gq] + ylo - (k.x - 1), ydh = tile_y0[gq] + yhi - (k.x - 1);
-            if (ydl < 0) ydl += a.FH;
-            if (ydh < 0) ydh += a.FH;
-            const bool slo = wlo && ydl < a.crop_h, shi = whi && ydh < a.crop_h;
-            const int xs = tile_x0[gq] - (k.y - 1);
-            auto put = [&](int xr, float vlo, float vhi) {
-                if (xr < 0 || xr >= nx) return;
-                int xd = xs + xr;
-                if (xd < 0) xd += a.FW;
-                if (xd >= a.crop_w) return;
-                float* d = base + (size_t)xd * a.out_ld;
-                if (slo) d[ydl] = vlo;
-                if (shi) d[ydh] = vhi;
-            };
-#pragma unroll
-            for (int j1 = 0; j1 < 16; ++j1) {
-                put(4 * j1 + par - a.ox0, reA[j1], imA[j1]);
-                put(4 * j1 + par + 2 - a.ox0, reB[j1], imB[j1]);
-            }
-            return;
-        }
-        float* dst = tile_dst[gq] + ylo;
-        if (a.dbg & 32) { if (reA[3] == 1.2345f) dst[0] = imB[5]; return; }
-#pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) {
-            const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
-            if (xa >= 0 && xa < nx) {
-                float* d = dst + (size_t)xa * a.out_ld;
-                if (wlo) d[0] = reA[j1];
-                if (whi) d[32] = imA[j1];
-            }
-            if (xb >= 0 && xb < nx) {
-                float* d = dst + (size_t)xb * a.out_ld;
-                if (wlo) d[0] = reB[j1];
-                if (whi) d[32] = imB[j1];
-            }
-        }
+        const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq]};
+        os_inverse_emit(a, t, lane, par, mbase + gq, T, reA, imA, reB, imB);
     }
 }
 

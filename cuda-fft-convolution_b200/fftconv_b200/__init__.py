@@ -39,6 +39,7 @@ EXPORTED_SYMBOLS = [
     "fftconv_fft_size16", "fftconv_fft_size_pow2", "fftconv_fft_data", "fftconv_fft_data_clamp",
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
     "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv", "fftconv_bank_conv_max",
+    "fftconv_bank_conv_detect", "fftconv_bank_conv_topk",
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
@@ -118,6 +119,8 @@ def lib() -> ctypes.CDLL:
         L.fftconv_bank_info.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.fftconv_bank_conv.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]
         L.fftconv_bank_conv_max.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]
+        L.fftconv_bank_conv_detect.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, ctypes.c_float, c_int, c_vp, c_vp, c_int, c_vp]
+        L.fftconv_bank_conv_topk.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]
         L.fftconv_bank_destroy.argtypes = [c_vp]
         L.fftconv_bank_destroy.restype = None
         L.fftconv_conv_bank.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]
@@ -546,6 +549,47 @@ class Bank:
                                          torch.cuda.current_stream(self.device).cuda_stream)
         _check(rc, ERRID_CONV)
         return peaks[:, 0].copy().view(np.float32), peaks[:, 1].copy(), peaks[:, 2].copy()
+
+    def _bias_arg(self, bias):
+        if bias is None:
+            return None, None
+        b = np.ascontiguousarray(np.asarray(bias, dtype=np.float32).ravel())
+        if b.size != self.K:
+            raise FFTConvError(ERRID_CONV, MSG_INVALID)
+        return b, b.ctypes.data
+
+    def detect(self, data, threshold: float, bias=None, max_per_template: int = 16):
+        """Fused detection (fftconv_bank_conv_detect): every response conv + bias[k] >= threshold of every template's
+        full linear convolution.  -> (counts[K] int32, value[K, M] float32, y[K, M], x[K, M] int32), the M =
+        max_per_template largest per template in descending order (unused slots: -inf, -1, -1); counts may exceed M."""
+        d_fwh = _as_single_3d(data, ERRID_CONV, MSG_INVALID)
+        F, W, H = d_fwh.shape
+        if F != self.F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        M = int(max_per_template)
+        dets = np.zeros((self.K, M, 4), dtype=np.int32)
+        counts = np.zeros(self.K, dtype=np.int32)
+        keep, bp = self._bias_arg(bias)
+        torch = _torch()
+        rc = lib().fftconv_bank_conv_detect(self._h, d_fwh.ctypes.data, 0, H, W, bp, float(threshold), M, dets.ctypes.data,
+                                            counts.ctypes.data, 0, torch.cuda.current_stream(self.device).cuda_stream)
+        _check(rc, ERRID_CONV)
+        return counts, dets[:, :, 0].copy().view(np.float32), dets[:, :, 1].copy(), dets[:, :, 2].copy()
+
+    def topk(self, data, k: int, bias=None):
+        """Fused top-k (fftconv_bank_conv_topk): the k largest responses conv + bias[t] of every template, exact,
+        descending.  -> (value[K, k] float32, y[K, k], x[K, k] int32)."""
+        d_fwh = _as_single_3d(data, ERRID_CONV, MSG_INVALID)
+        F, W, H = d_fwh.shape
+        if F != self.F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        dets = np.zeros((self.K, int(k), 4), dtype=np.int32)
+        keep, bp = self._bias_arg(bias)
+        torch = _torch()
+        rc = lib().fftconv_bank_conv_topk(self._h, d_fwh.ctypes.data, 0, H, W, bp, int(k), dets.ctypes.data, 0,
+                                          torch.cuda.current_stream(self.device).cuda_stream)
+        _check(rc, ERRID_CONV)
+        return dets[:, :, 0].copy().view(np.float32), dets[:, :, 1].copy(), dets[:, :, 2].copy()
 
     def close(self):
         if getattr(self, "_h", None):

@@ -156,6 +156,24 @@ typedef struct fftconv_peak { float value; int y; int x; int pad; } fftconv_peak
 int fftconv_bank_conv_max(const fftconv_bank* bank, const float* data, int data_on_device, int H, int W,
                           fftconv_peak* peaks, int peaks_on_device, void* stream);
 
+/* Extension (the rest of the row): detections instead of planes.  A detection consumer of the reference adds
+ * a per-template bias to each plane, crops it (demoCudaConvolutionFFT.m:149) and keeps the responses above a threshold or
+ * the k best ones -- after the D2H of every plane (src/cudaConvFFTData.cu:277).  Both reductions are fused into the store
+ * of the inverse transform: response r(y, x) = [full linear convolution of template k](y, x) + bias[k] (bias: K floats on
+ * the HOST, NULL = 0), over the (H + kh_k - 1) x (W + kw_k - 1) block; no plane is written or copied.
+ *   fftconv_bank_conv_detect: every response >= threshold.  dets[k * max_per_template + i], i < min(counts[k],
+ *     max_per_template): the largest ones in descending order (ties: smallest x, then y); counts[k] = how many responses
+ *     passed (may exceed max_per_template; at most max(64 * tiles, 2048) are ranked).  Unused slots: value -inf, y = x = -1.
+ *   fftconv_bank_conv_topk: the k <= 64 largest responses of every template, exact: a candidate pass bounds the k-th
+ *     largest response from below, a threshold pass over the same product spectra collects everything above the bound.
+ * dets / counts on the device iff out_on_device (then the call is stream-ordered, except that the top-k mode reads the
+ * counts back to detect a candidate overflow). */
+int fftconv_bank_conv_detect(const fftconv_bank* bank, const float* data, int data_on_device, int H, int W,
+                             const float* bias, float threshold, int max_per_template,
+                             fftconv_peak* dets, int* counts, int out_on_device, void* stream);
+int fftconv_bank_conv_topk(const fftconv_bank* bank, const float* data, int data_on_device, int H, int W,
+                           const float* bias, int k, fftconv_peak* dets, int out_on_device, void* stream);
+
 /* modulateAndNormalize — src/convolutionFFTkernel.cu:84-100: in place a = a*b/dataN. */
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
                                    long long n, int device, void* stream);

@@ -301,3 +301,61 @@ def test_calls_on_two_streams_and_two_host_threads_do_not_race(fc, oracle):
     [t.join() for t in th]
     for i in range(2):
         assert oracle.rel_l2(res[i][K - 1], refs[i]) < TOL, i
+
+
+def _responses(planes, ks, H, W, bias):
+    out = []
+    for k, p in enumerate(planes):
+        kh, kw, _ = ks[k].shape
+        out.append((p[:H + kh - 1, :W + kw - 1] + np.float32(bias[k])).astype(np.float32))
+    return out
+
+
+def test_fused_threshold_detection_with_bias_matches_planes(fc, oracle):
+    """fftconv_bank_conv_detect: responses conv + bias >= threshold, fused into the inverse store; compared
+    bit-for-bit with thresholding the planes of the same bank on the host."""
+    rng = np.random.default_rng(72)
+    F, K, H, W = 5, 140, 83, 61
+    ks = [rng.standard_normal((int(rng.integers(2, 17)), int(rng.integers(2, 13)), F)).astype(np.float32) for _ in range(K)]
+    data = rng.standard_normal((H, W, F)).astype(np.float32)
+    bias = rng.standard_normal(K).astype(np.float32) * 3
+    bank = fc.Bank(ks)
+    resp = _responses(bank.conv(data), ks, H, W, bias)
+    thr = float(np.quantile(np.concatenate([r.ravel() for r in resp]), 0.9995))
+    M = 32
+    counts, val, ys, xs = bank.detect(data, thr, bias=bias, max_per_template=M)
+    assert counts.sum() > K // 2                                            # the threshold is meaningful
+    for k in range(K):
+        r = resp[k]
+        yy, xx = np.nonzero(r >= np.float32(thr))
+        assert counts[k] == yy.size, k
+        order = sorted(zip(-r[yy, xx].astype(np.float64), xx, yy))          # value descending, then smallest x, then y
+        n = min(M, len(order))
+        for i in range(n):
+            assert val[k, i] == np.float32(-order[i][0]) and (xs[k, i], ys[k, i]) == (order[i][1], order[i][2]), (k, i)
+        assert np.all(np.isneginf(val[k, n:])) and np.all(ys[k, n:] == -1)
+    bank.close()
+
+
+@pytest.mark.parametrize("k", [1, 5, 16])
+def test_fused_topk_matches_planes(fc, oracle, k):
+    """fftconv_bank_conv_topk: exact top-k of every template (candidate pass + threshold pass over the same spectra)."""
+    rng = np.random.default_rng(73)
+    F, K, H, W = 4, 96, 150, 97
+    ks = [rng.standard_normal((int(rng.integers(3, 17)), int(rng.integers(3, 17)), F)).astype(np.float32) for _ in range(K)]
+    data = rng.standard_normal((H, W, F)).astype(np.float32)
+    bias = rng.standard_normal(K).astype(np.float32)
+    bank = fc.Bank(ks)
+    resp = _responses(bank.conv(data), ks, H, W, bias)
+    val, ys, xs = bank.topk(data, k, bias=bias)
+    for t in range(K):
+        r = resp[t]
+        flat = sorted(zip(-r.ravel().astype(np.float64), np.tile(np.arange(r.shape[1]), r.shape[0]), np.repeat(np.arange(r.shape[0]), r.shape[1])))[:k]
+        for i in range(k):
+            assert val[t, i] == np.float32(-flat[i][0]), (t, i)
+            assert (xs[t, i], ys[t, i]) == (flat[i][1], flat[i][2]), (t, i)
+    v1, y1, x1 = bank.conv_max(data)
+    if k == 1:                                                             # bias-free maximum agrees with conv_max
+        v0, y0, x0 = bank.topk(data, 1)
+        assert np.array_equal(v0[:, 0], v1) and np.array_equal(y0[:, 0], y1) and np.array_equal(x0[:, 0], x1)
+    bank.close()
