@@ -244,6 +244,17 @@ def config_c1(fc, torch, peak):
         fc.conv_bank(spec, b_t, cn, cm, out)
 
     ms = _median_ms(torch, dev_step, 20)
+    plan = fc.Plan(d_t, b_t, cn, cm)                     # the same two calls captured into one CUDA graph
+    plan_ms = _median_ms(torch, plan.execute, 20)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(200):
+        plan.execute()
+    torch.cuda.synchronize()
+    plan_wall_us = (time.perf_counter() - t0) / 200 * 1e6
+    plan_rel = float((plan.out - out).abs().max())
+    nodes = plan.graph_nodes
+    plan.close()
     t0 = time.perf_counter()
     for _ in range(50):
         outs = fc.cudaConvolutionFFT(data, cn, cm, cells, [8, 8, 8, 16], 0)
@@ -251,7 +262,11 @@ def config_c1(fc, torch, peak):
     rel = max(oracle.rel_l2(o, oracle.direct_conv64(data, k, FH, FW)) for o, k in zip(outs, cells))
     a = 4 * H * W * F + 4 * F * 10 * cn * cm + 4 * 10 * FH * FW
     return _record(10 * FH * FW, ms, a, rel, peak, workload=WORKLOADS["c1"][6], us_per_call_device=ms * 1e3,
-                   us_per_call_host_to_host=host_us, note="launch-latency bound: parity config, microseconds per call")
+                   us_per_call_host_to_host=host_us,
+                   graph_plan={"us_per_execute_device": plan_ms * 1e3, "us_per_execute_back_to_back": plan_wall_us,
+                               "graph_nodes": nodes, "max_abs_diff_vs_eager": plan_rel,
+                               "note": "fftconv_plan_*: cudaFFTData + cudaConvFFTData captured into one CUDA graph"},
+                   note="launch-latency bound: parity config, microseconds per call")
 
 
 def config_c3(fc, torch, peak):
@@ -366,7 +381,8 @@ def ref_gpu_replay(n=64):
 def run_ours(args):
     import torch
     import fftconv_b200 as fc
-    from fftconv_b200.sharding import broadcast_spectrum, broadcast_spectrum_async, bind_host_to_gpu, PeerSpectrum
+    from fftconv_b200.sharding import (broadcast_spectrum, broadcast_spectrum_async, bind_host_to_gpu, PeerSpectrum,
+                                       PeerAllGatherSpectrum)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -400,8 +416,17 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
     # spectrum delivery at N > 1: "peer" = CUDA IPC + NVLink pull ordered by device flags (fftconv_peer_*),
     # "sync" = NCCL broadcast on the step's stream, "async" = NCCL broadcast on a side stream (A/B switches)
-    bcast_mode = os.environ.get("FFTCONV_BENCH_BCAST", "peer") if world > 1 else "local"
+    # "allgather" (default) = every rank transforms its slice of the channels, slices pulled through the peer mappings
+    bcast_mode = os.environ.get("FFTCONV_BENCH_BCAST", "allgather") if world > 1 else "local"
     peer = None
+    ag = None
+    if bcast_mode == "allgather":
+        ag = PeerAllGatherSpectrum((F, FW, CH))
+        if ag.enabled:
+            spec = ag.spec
+        else:
+            ag.close()
+            ag, bcast_mode = None, "peer"
     if bcast_mode == "peer":
         peer = PeerSpectrum((F, FW, CH))
         if peer.enabled:
@@ -411,7 +436,13 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
 
     def step():
-        """data FFT (rank 0) -> [NCCL broadcast of the spectrum] -> bank convolution on every rank"""
+        """data FFT (rank 0, or one channel slice per rank) -> spectrum delivery -> bank convolution on every rank"""
+        if ag is not None:
+            ag.begin_fill()
+            ag.fill(data, H, W, kh, kw)
+            ag.gather()
+            fc.conv_bank(spec, bank, kh, kw, out)
+            return
         if peer is not None:
             peer.begin_fill()
             if rank == 0:
@@ -529,14 +560,22 @@ def run_ours(args):
                                            op, 0, None, 0, None, local, st)
         else:
             rc = 0
-            if peer is not None:
-                peer.begin_fill()
-            if rank == 0:
-                rc = L.fftconv_fft_data(h_data.data_ptr(), 0, H, W, F, kh, kw, spec.data_ptr(), local, st)
-            if peer is not None:
-                peer.publish_and_fetch()
+            if ag is not None:
+                f0, f1 = ag.my_channels()
+                ag.begin_fill()
+                if f1 > f0:                               # only this rank's channels cross its PCIe link
+                    rc = L.fftconv_fft_data(h_data.data_ptr() + 4 * f0 * W * H, 0, H, W, f1 - f0, kh, kw,
+                                            spec.data_ptr() + 8 * f0 * FW * CH, local, st)
+                ag.gather()
             else:
-                broadcast_spectrum(spec, 0)
+                if peer is not None:
+                    peer.begin_fill()
+                if rank == 0:
+                    rc = L.fftconv_fft_data(h_data.data_ptr(), 0, H, W, F, kh, kw, spec.data_ptr(), local, st)
+                if peer is not None:
+                    peer.publish_and_fetch()
+                else:
+                    broadcast_spectrum(spec, 0)
             rc = rc or L.fftconv_conv_fft_data(spec.data_ptr(), CH, FW, F, K, kp, khs, kws, None, None, op, 0,
                                                None, 0, None, local, st)
         if rc != 0:
@@ -628,11 +667,29 @@ def run_ours(args):
         for _ in range(10):
             peak_step()
         peak_ms = (time.perf_counter() - t0) * 1e2
+        h_top = np.zeros((K, 5, 4), dtype=np.int32)
+        h_bias = np.zeros(K, dtype=np.float32)
+
+        def topk_step():
+            if L.fftconv_bank_conv_topk(hb, h_data.data_ptr(), 0, H, W, h_bias.ctypes.data, 5, h_top.ctypes.data, 0, st) != 0:
+                raise SystemExit("bank_conv_topk failed: " + fc.last_error())
+
+        for _ in range(2):
+            topk_step()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            topk_step()
+        topk_ms = (time.perf_counter() - t0) * 1e2
+        topk_ok = bool(np.array_equal(h_top[:, 0, 0], h_peaks.numpy()[:, 0]))        # best of the top-5 == fused maximum
         L.fftconv_bank_destroy(hb)
         extras = {"prepared_bank": {"one_off_transform_ms": prep_ms, "ms_per_step": float(np.median(ts)),
                                     "value": outputs_per_step / (float(np.median(ts)) * 1e-3), "unit": UNIT,
                                     "rel_l2_vs_fp64": bank_rel,
                                     "note": "fftconv_bank_conv: template spectra resident in HBM, raw data in, planes out (device)"},
+                  "fused_top5_host_to_host": {"ms_per_step": topk_ms, "d2h_bytes_per_step": 80 * K + 4 * K,
+                                              "first_equals_fused_max": topk_ok,
+                                              "note": "fftconv_bank_conv_topk (k = 5, per-template bias): host data in, 5 K (value, y, x) "
+                                                      "detections on the host; candidate pass + threshold pass over the same product spectra"},
                   "fused_max_host_to_host": {"ms_per_step": peak_ms, "d2h_bytes_per_step": 16 * K,
                                              "note": "fftconv_bank_conv_max: host data in, K (value, y, x) peaks on the host; "
                                                      "no plane is written or copied"}}
@@ -701,7 +758,9 @@ def run_ours(args):
                        "l2": "flushed between steps by an untimed 256 MiB memset; each step also writes "
                              f"{4 * K * FH * FW / 1e6:.0f} MB of outputs (> 126 MB L2)",
                        "parallelism": f"template bank sharded over {world} GPU(s), data spectrum "
-                                      + ({"peer": "pulled from rank 0 over CUDA IPC + NVLink inside the step (device flags, no collective kernel)",
+                                      + ({"allgather": "all-gathered inside the step: every rank transforms its channel slice of the (replicated) image, "
+                                                       "one kernel per rank pulls the other slices over CUDA IPC + NVLink (device flags)",
+                                          "peer": "pulled from rank 0 over CUDA IPC + NVLink inside the step (device flags, no collective kernel)",
                                           "sync": "broadcast by NCCL inside the step", "async": "broadcast by NCCL on a side stream inside the step",
                                           "local": "local"}[bcast_mode]),
                        "host_affinity": (f"{len(numa_cpus)} cores local to the GPU (NVML)" if numa_cpus else "unchanged"),
@@ -716,6 +775,10 @@ def run_ours(args):
         if peer.status() != 0:
             raise SystemExit("peer spectrum wait timed out: " + fc.last_error())
         peer.close()
+    if ag is not None:
+        if ag.status() != 0:
+            raise SystemExit("peer all-gather wait timed out: " + fc.last_error())
+        ag.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

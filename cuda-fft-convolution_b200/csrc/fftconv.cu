@@ -63,13 +63,14 @@ static const char* kProfNames[PK_COUNT] = {"tile16_relayout", "tile16_kern_hpass
                                            "os_kern_fft(templates)", "os_gemm", "os_inverse",
                                            "bp_repad_spec", "bp_kern_h", "bp_conv_w", "bp_inv_h"};
 static bool g_prof_on = false;
+static thread_local bool g_capturing = false;      // plan capture on this thread: no timing events inside a graph
 struct ProfRec { int kind; cudaEvent_t a, b; };
 static std::vector<ProfRec> g_prof;
 static std::mutex g_prof_mu;
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
-        if (g_prof_on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+        if (g_prof_on && !g_capturing) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
     ~ProfScope() {
         if (a) { cudaEventRecord(b, st); std::lock_guard<std::mutex> lk(g_prof_mu); g_prof.push_back({kind, a, b}); }
@@ -120,6 +121,10 @@ struct Ctx {
     DevBuf batchA;                   // fftconv_conv_batch: template spectra shared by the image groups of one call
     DevBuf T, Z, stage, desc, outstage, dspec, ddata, priv, Ag, Wg;
     DevBuf osA, osB, osP, osPlane, osZ, osPeaks;     // overlap-save / tcgen05 path scratch
+    // plan capture (fftconv_plan_*): descriptor tables are staged through a PLAN-OWNED pinned buffer with bump allocation,
+    // because a captured H2D copy reads its pinned source at every graph launch, long after this call returned
+    char* plan_pin = nullptr;
+    size_t plan_pin_cap = 0, plan_pin_off = 0;
     void* bounce = nullptr;          // pinned bounce ring for PAGEABLE host outputs (two halves of one chunk of planes)
     size_t bounce_cap = 0;
     cudaEvent_t evb[2] = {nullptr, nullptr};   // D2H into bounce half done
@@ -146,8 +151,11 @@ struct Ctx {
 static std::mutex g_mu;                  // guards g_ctx (the map only; each Ctx has its own lock)
 static std::map<int, Ctx> g_ctx;
 
+static std::atomic<long long> g_scratch_gen{0};   // bumped whenever cached device scratch moves (invalidates captured plans)
+
 static int dev_reserve(DevBuf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
+    g_scratch_gen.fetch_add(1, std::memory_order_relaxed);
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr; b.cap = 0;
     size_t cap = bytes + bytes / 8 + 256;
@@ -166,6 +174,28 @@ static int pinned_reserve(Ctx& c, size_t bytes) {
     size_t cap = bytes + bytes / 4 + 4096;
     CU(cudaMallocHost(&c.pinned, cap));
     c.pinned_cap = cap;
+    return 0;
+}
+
+// Host staging for a descriptor table that an async H2D copy on `st` will read: *out = pinned memory of `bytes`.
+// Normal calls: the shared staging buffer, once its previous copy has finished.  Plan capture: a fresh region of the
+// plan's own buffer.  pinned_done marks the copy as enqueued.
+static int pinned_get(Ctx& c, size_t bytes, void** out) {
+    if (c.plan_pin) {
+        const size_t off = (c.plan_pin_off + 63) & ~(size_t)63;
+        if (off + bytes > c.plan_pin_cap) return fail(FFTCONV_ERR_UNSUPPORTED, "plan staging buffer too small");
+        c.plan_pin_off = off + bytes;
+        *out = c.plan_pin + off;
+        return 0;
+    }
+    if (int e = pinned_reserve(c, bytes)) return e;
+    CU(cudaEventSynchronize(c.pinned_free));
+    *out = c.pinned;
+    return 0;
+}
+static int pinned_done(Ctx& c, cudaStream_t st) {
+    if (c.plan_pin) return 0;
+    CU(cudaEventRecord(c.pinned_free, st));
     return 0;
 }
 
@@ -326,13 +356,12 @@ static int run_fft_data(Ctx& c, const float* d_data, int H, int W, int F, int FH
     const int ncols = pad_mode == PAD_CLAMP ? FW : W;
     if (int e = dev_reserve(c.T, sizeof(cpx) * (size_t)F * ncols * CH)) return e;
     // one SrcDesc through pinned staging
-    if (int e = pinned_reserve(c, sizeof(SrcDesc))) return e;
     if (int e = dev_reserve(c.desc, sizeof(SrcDesc))) return e;
-    CU(cudaEventSynchronize(c.pinned_free));
-    SrcDesc* hd = reinterpret_cast<SrcDesc*>(c.pinned);
+    SrcDesc* hd;
+    if (int e = pinned_get(c, sizeof(SrcDesc), (void**)&hd)) return e;
     hd->ptr = d_data; hd->rows = H; hd->cols = W;
     CU(cudaMemcpyAsync(c.desc.p, hd, sizeof(SrcDesc), cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(c.pinned_free, st));
+    if (int e = pinned_done(c, st)) return e;
 
     const int NL = pick_lines(FH, 8);
     const long long nlines = (long long)F * ((ncols + 1) / 2);
@@ -598,12 +627,11 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
         if (int e = dev_reserve(c.osPlane, sizeof(float) * (size_t)F * FW * FH + sizeof(float*) * (size_t)F)) return e;
         float* plane = (float*)c.osPlane.p;
         float** d_planes = reinterpret_cast<float**>(plane + (size_t)F * FW * FH);
-        if (int e = pinned_reserve(c, sizeof(float*) * (size_t)F)) return e;
-        CU(cudaEventSynchronize(c.pinned_free));
-        float** h_planes = reinterpret_cast<float**>(c.pinned);
+        float** h_planes;
+        if (int e = pinned_get(c, sizeof(float*) * (size_t)F, (void**)&h_planes)) return e;
         for (int f = 0; f < F; ++f) h_planes[f] = plane + (size_t)f * FW * FH;
         CU(cudaMemcpyAsync(d_planes, h_planes, sizeof(float*) * (size_t)F, cudaMemcpyHostToDevice, st));
-        CU(cudaEventRecord(c.pinned_free, st));
+        if (int e = pinned_done(c, st)) return e;
         ProfScope ps(PK_OS_PLANE, st);
         int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
         TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
@@ -771,7 +799,6 @@ struct ConvArgs {
     float* const* outs;            // K entries (host or device pointers)
     bool out_on_device;
     fftconv_options opt;
-    bool pipelined;                // use the side copy stream (Streams entry point)
     const float* d_raw = nullptr;  // one-shot entry point: the raw data [F][rawW][rawH] on the device
     int rawH = 0, rawW = 0;
     const float* bankA = nullptr;  // prepared bank (fftconv_bank_*): A operand images of all K templates, path 3 only
@@ -1024,6 +1051,52 @@ __global__ void peer_pull_kernel(uint4* __restrict__ dst, const uint4* __restric
     if (blockIdx.x == 0 && (int)threadIdx.x < ntail) dtail[threadIdx.x] = stail[threadIdx.x];
 }
 
+// All-gather of the spectrum slices through the peer mappings, ONE launch: block group p of rank r waits for rank p's
+// ready flag (through its NVLink mapping), pulls slice p out of rank p's buffer into the same offset of its own buffer and
+// -- the last block of the group -- acknowledges in rank p's memory.  Every buffer has the same layout: [spectrum | ready
+// flag | n acknowledgement slots].  No rank's NVLink egress carries more than (n - 1) slices.
+struct PeerAgArgs {
+    unsigned char* base[16];          // base[p]: rank p's buffer (own pointer for p == rank, mapping otherwise)
+    unsigned long long off[17];       // slice boundaries in bytes (multiples of 16)
+    unsigned long long flag_off;
+    unsigned long long step;
+    int n, rank, bpg;
+};
+__device__ unsigned int g_peer_ag_done[16];
+
+__global__ void __launch_bounds__(512) peer_allgather_kernel(PeerAgArgs a) {
+    const int p = blockIdx.x / a.bpg, b = blockIdx.x - p * a.bpg;
+    if (p == a.rank) return;
+    if (threadIdx.x == 0) {
+        const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(a.base[p] + a.flag_off);
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+            if (v >= a.step) break;
+            if (clock64() - t0 > 4000000000ll) { atomicAdd(&g_peer_timeouts, 1u); break; }
+            __nanosleep(100);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    const size_t n16 = (size_t)(a.off[p + 1] - a.off[p]) / 16;
+    const uint4* src = reinterpret_cast<const uint4*>(a.base[p] + a.off[p]);
+    uint4* dst = reinterpret_cast<uint4*>(a.base[a.rank] + a.off[p]);
+    for (size_t i = (size_t)b * blockDim.x + threadIdx.x; i < n16; i += (size_t)a.bpg * blockDim.x) dst[i] = src[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(&g_peer_ag_done[p], 1u);
+        if (old == (unsigned)a.bpg - 1) {
+            g_peer_ag_done[p] = 0;
+            __threadfence_system();
+            unsigned long long* ack = reinterpret_cast<unsigned long long*>(a.base[p] + a.flag_off) + 1 + a.rank;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ack), "l"(a.step) : "memory");
+        }
+    }
+}
+
 static size_t plane_floats(const ConvArgs& a, int FH) {
     const int crop_h = a.opt.crop_h > 0 ? a.opt.crop_h : FH;
     const int crop_w = a.opt.crop_w > 0 ? a.opt.crop_w : a.FW;
@@ -1155,13 +1228,12 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     size_t host_kernel_bytes = 0;
     for (int k = 0; k < K && !a.bankA; ++k)
         if (!a.kernels[k].on_device) host_kernel_bytes += sizeof(float) * (size_t)a.kernels[k].kh * a.kernels[k].kw * F;
-    if (int e = pinned_reserve(c, desc_bytes)) return e;
     if (int e = dev_reserve(c.desc, desc_bytes)) return e;
     if (host_kernel_bytes)
         if (int e = dev_reserve(c.stage, host_kernel_bytes)) return e;
 
-    CU(cudaEventSynchronize(c.pinned_free));
-    SrcDesc* h_desc = reinterpret_cast<SrcDesc*>(c.pinned);
+    SrcDesc* h_desc;
+    if (int e = pinned_get(c, desc_bytes, (void**)&h_desc)) return e;
     float** h_outp = reinterpret_cast<float**>(h_desc + K);
     int2* h_khw = reinterpret_cast<int2*>(h_outp + NO);
     int* h_kcols = reinterpret_cast<int*>(h_khw + K);
@@ -1198,8 +1270,8 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
             h_outp[k] = (a.peak_keys || a.det.mode) ? nullptr : a.out_on_device ? a.outs[k]
                                         : reinterpret_cast<float*>(c.outstage.p) + plane * (size_t)((k - bounds[ch]) + (ch & 1) * KC);
     for (size_t i = K; i < NO; ++i) h_outp[i] = a.outs[i];         // images 1.. of a batch (device planes)
-    CU(cudaMemcpyAsync(c.desc.p, c.pinned, desc_bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaEventRecord(c.pinned_free, st));
+    CU(cudaMemcpyAsync(c.desc.p, h_desc, desc_bytes, cudaMemcpyHostToDevice, st));
+    if (int e = pinned_done(c, st)) return e;
 
     // ---- chunk loop.  Device outputs: one stream.  Host outputs: the D2H of chunk i runs on the
     // side stream while chunk i+1 uploads its kernels and computes (double-buffered out staging).
@@ -1358,8 +1430,7 @@ struct ConvRaw { const float* d_data; int H, W; int nimg = 1; };
 static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K, const float* const* kernels,
                      const int* kh, const int* kw, const int* kf, const unsigned char* kernel_on_device,
                      float* const* outs, int out_on_device, const double* threads, int nthreads,
-                     const fftconv_options* opt, int device, void* stream, bool pipelined,
-                     const ConvRaw* raw = nullptr) {
+                     const fftconv_options* opt, int device, void* stream, const ConvRaw* raw = nullptr) {
     g_err.clear();
     // the one-shot spectrum-ready event belongs to THIS call whatever its outcome (a validation error or K == 0 must
     // not leave a stale event pointer behind for a later call)
@@ -1387,7 +1458,6 @@ static int conv_impl(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
     a.d_spec = (const cpx*)d_spec; a.CH = CH; a.FW = FW; a.F = F; a.K = K;
     a.kernels = refs.data(); a.outs = outs; a.out_on_device = out_on_device != 0;
     a.opt = opt ? *opt : fftconv_options{};
-    a.pipelined = pipelined;
     a.spec_ready = spec_ready;
     if (raw) { a.d_raw = raw->d_data; a.rawH = raw->H; a.rawW = raw->W; a.nimg = raw->nimg; }
     return run_conv(*c, a, (cudaStream_t)stream);
@@ -1398,7 +1468,7 @@ int fftconv_conv_fft_data(const fftconv_float2* d_spec, int CH, int FW, int F, i
                           float* const* outs, int out_on_device, const double* threads, int nthreads,
                           const fftconv_options* opt, int device, void* stream) {
     return conv_impl(d_spec, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs, out_on_device, threads,
-                     nthreads, opt, device, stream, false);
+                     nthreads, opt, device, stream);
 }
 
 int fftconv_conv_fft_data_streams(const fftconv_float2* d_spec, int CH, int FW, int F, int K,
@@ -1406,7 +1476,7 @@ int fftconv_conv_fft_data_streams(const fftconv_float2* d_spec, int CH, int FW, 
                                   float* const* outs, const double* threads, int nthreads,
                                   const fftconv_options* opt, int device) {
     return conv_impl(d_spec, CH, FW, F, K, kernels, kh, kw, kf, nullptr, outs, 0, threads, nthreads, opt, device,
-                     nullptr, true);
+                     nullptr);
 }
 
 int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W, int F, int maxKH, int maxKW, int K,
@@ -1452,14 +1522,14 @@ int fftconv_convolution_fft(const float* data, int data_on_device, int H, int W,
     if (raw_path) {
         ConvRaw raw{d_data, H, W};
         return conv_impl(nullptr, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs, out_on_device, threads,
-                         nthreads, opt, device, stream, false, &raw);
+                         nthreads, opt, device, stream, &raw);
     }
     // stream-ordered: no sync between the data transform and the bank loop (the reference
     // synchronises the device here, src/cudaConvolutionFFT.cu:168)
     int e = fft_data_impl(data, data_on_device, H, W, F, maxKH, maxKW, PAD_ZERO, 0, 0, (fftconv_float2*)spec, device, stream);
     if (e) return e;
     return conv_impl((const fftconv_float2*)spec, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs,
-                     out_on_device, threads, nthreads, opt, device, stream, false);
+                     out_on_device, threads, nthreads, opt, device, stream);
 }
 
 struct fftconv_bank {
@@ -1534,7 +1604,7 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
         }
         ConvRaw raw{d_data, H, W, nimg};
         if (int e = conv_impl(nullptr, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs + (size_t)n0 * K, 1,
-                              nullptr, 0, opt, device, stream, false, &raw))
+                              nullptr, 0, opt, device, stream, &raw))
             return e;
     }
     return 0;
@@ -1651,7 +1721,7 @@ static int bank_conv_images(const fftconv_bank* b, const float* d_data, int nimg
     ConvArgs a;
     a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = b->F; a.K = b->K;
     a.kernels = nullptr; a.outs = outs; a.out_on_device = out_on_device != 0;
-    a.opt = o; a.pipelined = false;
+    a.opt = o;
     a.d_raw = d_data; a.rawH = H; a.rawW = W; a.nimg = nimg;
     a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw;
     return run_conv(*c, a, st);
@@ -1706,7 +1776,7 @@ int fftconv_bank_conv_max(const fftconv_bank* b, const float* data, int data_on_
     ConvArgs a;
     a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = F; a.K = K;
     a.kernels = nullptr; a.outs = nullptr; a.out_on_device = true;
-    a.opt = fftconv_options{}; a.pipelined = false;
+    a.opt = fftconv_options{};
     a.d_raw = d_data; a.rawH = H; a.rawW = W;
     a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw;
     a.peak_keys = keys; a.bank_khw = b->khw;
@@ -1770,7 +1840,7 @@ static int bank_detect_impl(const fftconv_bank* b, const float* data, int data_o
     ConvArgs a;
     a.d_spec = nullptr; a.CH = FH / 2 + 1; a.FW = FW; a.F = F; a.K = K;
     a.kernels = nullptr; a.outs = nullptr; a.out_on_device = true;
-    a.opt = fftconv_options{}; a.pipelined = false;
+    a.opt = fftconv_options{};
     a.d_raw = d_data; a.rawH = H; a.rawW = W;
     a.bankA = b->A; a.bank_maxkh = b->maxkh; a.bank_maxkw = b->maxkw; a.bank_khw = b->khw;
     a.det.mode = mode; a.det.cap = cap; a.det.k = nsel; a.det.keys = keys; a.det.count = count; a.det.thr = thr;
@@ -1838,7 +1908,140 @@ int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F, int K
         op[k] = d_out + (size_t)k * plane;
     }
     return conv_impl(d_spec, CH, FW, F, K, kp.data(), khs.data(), kws.data(), nullptr, od.data(), op.data(), 1,
-                     nullptr, 0, &o, device, stream, false);
+                     nullptr, 0, &o, device, stream);
+}
+
+// ---- plans: the persistent graph schedule over the kernel bank (the role of the per-stream ConvPlans of
+// src/cudaConvFFTDataStreams.cu:292-328,338-469).  A plan fixes the device buffers of a repeated call -- image (or
+// spectrum), bank, output planes -- runs it once eagerly (which also sizes every cached scratch buffer) and captures the
+// whole launch sequence (data transform, template transforms, per-bin GEMM, inverse; both internal streams) into ONE
+// CUDA graph; every later execution is a single cudaGraphLaunch.  Buffer CONTENTS may change between executions.
+struct fftconv_plan {
+    int device;
+    const float* d_data; int H, W, F, KH, KW;      // d_data == nullptr: the plan starts from the spectrum
+    fftconv_float2* d_spec; int CH, FW;
+    int K, kh, kw;
+    const float* d_bank; float* d_out;
+    fftconv_options opt;
+    std::vector<KernelRef> refs;
+    std::vector<float*> outs;
+    char* pin = nullptr; size_t pin_cap = 0;
+    cudaStream_t cap_stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    long long gen = -1;
+    size_t nodes = 0;
+};
+
+static int plan_enqueue(Ctx& c, fftconv_plan* p, cudaStream_t st) {
+    if (p->d_data)
+        if (int e = run_fft_data(c, p->d_data, p->H, p->W, p->F, (p->CH - 1) * 2, p->FW, PAD_ZERO, 0, 0, (cpx*)p->d_spec, st)) return e;
+    ConvArgs a;
+    a.d_spec = (const cpx*)p->d_spec; a.CH = p->CH; a.FW = p->FW; a.F = p->F; a.K = p->K;
+    a.kernels = p->refs.data(); a.outs = p->outs.data(); a.out_on_device = true;
+    a.opt = p->opt;
+    return run_conv(c, a, st);
+}
+
+// (re)capture; the caller holds the device lock.  `warm`: run once eagerly first so that no allocation happens in capture.
+static int plan_capture(Ctx& c, fftconv_plan* p, cudaStream_t user_stream, bool warm) {
+    if (warm) {
+        if (int e = plan_enqueue(c, p, user_stream)) return e;
+        CU(cudaStreamSynchronize(user_stream));
+    }
+    if (p->exec) { cudaGraphExecDestroy(p->exec); p->exec = nullptr; }
+    if (p->graph) { cudaGraphDestroy(p->graph); p->graph = nullptr; }
+    const long long gen0 = g_scratch_gen.load();
+    c.plan_pin = p->pin; c.plan_pin_cap = p->pin_cap; c.plan_pin_off = 0;
+    g_capturing = true;
+    int e = 0;
+    if (cudaStreamBeginCapture(p->cap_stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess)
+        e = fail(FFTCONV_ERR_CUDA, "cudaStreamBeginCapture failed");
+    if (!e) {
+        e = plan_enqueue(c, p, p->cap_stream);
+        cudaGraph_t gr = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(p->cap_stream, &gr);
+        if (!e && ce != cudaSuccess) e = fail(FFTCONV_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(ce));
+        if (e && gr) cudaGraphDestroy(gr);
+        if (!e) p->graph = gr;
+    }
+    g_capturing = false;
+    c.plan_pin = nullptr; c.plan_pin_cap = c.plan_pin_off = 0;
+    if (e) { cudaGetLastError(); return e; }
+    if (g_scratch_gen.load() != gen0) return fail(FFTCONV_ERR_CUDA, "scratch moved during plan capture");
+    CU(cudaGraphInstantiate(&p->exec, p->graph, 0));
+    CU(cudaGraphGetNodes(p->graph, nullptr, &p->nodes));
+    p->gen = gen0;
+    return 0;
+}
+
+int fftconv_plan_create(const float* d_data, int H, int W, int F, int KH, int KW, fftconv_float2* d_spec,
+                        int K, const float* d_bank, int kh, int kw, float* d_out, const fftconv_options* opt,
+                        int device, void* stream, fftconv_plan** out) {
+    g_err.clear();
+    if (!out) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    *out = nullptr;
+    if (!d_spec || !d_bank || !d_out || H <= 0 || W <= 0 || F <= 0 || KH <= 0 || KW <= 0 || K <= 0 || kh <= 0 || kw <= 0)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    const int FH = fftconv_fft_size16(H + KH - 1), FW = fftconv_fft_size16(W + KW - 1);
+    if (kh > FH || kw > FW) return fail(FFTCONV_ERR_KERNEL_SHAPE, "%s", kMsgKernelShape);
+    std::unique_ptr<fftconv_plan> p(new fftconv_plan{});
+    p->device = device; p->d_data = d_data; p->H = H; p->W = W; p->F = F; p->KH = KH; p->KW = KW;
+    p->d_spec = d_spec; p->CH = FH / 2 + 1; p->FW = FW; p->K = K; p->kh = kh; p->kw = kw; p->d_bank = d_bank; p->d_out = d_out;
+    p->opt = opt ? *opt : fftconv_options{};
+    const int crop_h = p->opt.crop_h > 0 ? p->opt.crop_h : FH, crop_w = p->opt.crop_w > 0 ? p->opt.crop_w : FW;
+    const size_t plane = (size_t)crop_w * (p->opt.out_ld > 0 ? p->opt.out_ld : crop_h);
+    p->refs.resize(K); p->outs.resize(K);
+    for (int k = 0; k < K; ++k) {
+        p->refs[k] = KernelRef{d_bank + (size_t)k * kh * kw * F, kh, kw, true};
+        p->outs[k] = d_out + (size_t)k * plane;
+    }
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    p->pin_cap = (sizeof(SrcDesc) + sizeof(int2) + sizeof(int) + sizeof(float*)) * (size_t)K + sizeof(float*) * (size_t)F + 4096;
+    CU(cudaMallocHost((void**)&p->pin, p->pin_cap));
+    if (cudaStreamCreateWithFlags(&p->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        cudaFreeHost(p->pin);
+        return fail(FFTCONV_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    if (int e = plan_capture(*cs.c, p.get(), (cudaStream_t)stream, true)) {
+        cudaStreamDestroy(p->cap_stream); cudaFreeHost(p->pin);
+        return e;
+    }
+    *out = p.release();
+    return 0;
+}
+
+int fftconv_plan_execute(fftconv_plan* p, void* stream) {
+    g_err.clear();
+    if (!p) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    CtxScope cs(p->device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    if (p->gen != g_scratch_gen.load())               // another call grew (moved) the cached scratch: capture again
+        if (int e = plan_capture(*cs.c, p, (cudaStream_t)stream, true)) return e;
+    CU(cudaGraphLaunch(p->exec, (cudaStream_t)stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return 0;
+}
+
+int fftconv_plan_info(const fftconv_plan* p, int* graph_nodes, int* path) {
+    if (!p) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    if (graph_nodes) *graph_nodes = (int)p->nodes;
+    if (path) *path = choose_path(p->opt, p->F, (p->CH - 1) * 2, p->FW, std::min(p->kh, (p->CH - 1) * 2), std::min(p->kw, p->FW), p->K);
+    return 0;
+}
+
+void fftconv_plan_destroy(fftconv_plan* p) {
+    if (!p) return;
+    {
+        CtxScope cs(p->device, nullptr);
+        cudaDeviceSynchronize();
+        if (p->exec) cudaGraphExecDestroy(p->exec);
+        if (p->graph) cudaGraphDestroy(p->graph);
+        if (p->cap_stream) cudaStreamDestroy(p->cap_stream);
+        if (p->pin) cudaFreeHost(p->pin);
+    }
+    delete p;
 }
 
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b, long long n, int device, void* stream) {
@@ -2050,6 +2253,35 @@ int fftconv_peer_pull(void* dst, const void* src_mapped, size_t bytes, int devic
     LAUNCH_CHECK();
     return 0;
 }
+int fftconv_peer_allgather(void* const* bases, int n, int rank, const unsigned long long* offs, unsigned long long flag_off,
+                           unsigned long long step, int device, void* stream) {
+    g_err.clear();
+    if (!bases || !offs || n < 1 || n > 16 || rank < 0 || rank >= n) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    DeviceGuard guard(device);
+    if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+    PeerAgArgs a{};
+    for (int p = 0; p < n; ++p) {
+        if (!bases[p] || (offs[p] & 15) || offs[p + 1] < offs[p]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+        a.base[p] = (unsigned char*)bases[p];
+        a.off[p] = offs[p];
+    }
+    if (offs[n] & 15) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    a.off[n] = offs[n];
+    a.flag_off = flag_off; a.step = step; a.n = n; a.rank = rank;
+    // the rank's own slice is complete (stream order): raise its ready flag and its own acknowledgement slot
+    unsigned long long* ready = reinterpret_cast<unsigned long long*>(a.base[rank] + flag_off);
+    peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ready, step);
+    LAUNCH_CHECK();
+    peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ready + 1 + rank, step);
+    LAUNCH_CHECK();
+    if (n > 1) {
+        a.bpg = std::max(1, 128 / n);                       // all blocks resident at once: a waiting group never starves another
+        peer_allgather_kernel<<<n * a.bpg, 512, 0, (cudaStream_t)stream>>>(a);
+        LAUNCH_CHECK();
+    }
+    return 0;
+}
+
 int fftconv_peer_status(int device) {
     DeviceGuard guard(device);
     if (!guard.ok) return fail(FFTCONV_ERR_CUDA, "cudaSetDevice(%d) failed", device);

@@ -29,7 +29,7 @@ __all__ = [
     "FFTConvError", "GpuArray", "gpuArray", "gather", "computeFFTsize16", "computeFFTsize",
     "cudaFFTData", "cudaConvFFTData", "cudaConvolutionFFT", "cudaConvFFTDataStreams",
     "cudaFFTDataClamp", "modulateAndNormalize", "Options", "conv_bank", "fft_data_device",
-    "conv_batch", "Bank", "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
+    "conv_batch", "Bank", "Plan", "lib", "LIB_PATH", "launch_count", "last_error", "EXPORTED_SYMBOLS", "profile", "profile_read",
 ]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -40,12 +40,13 @@ EXPORTED_SYMBOLS = [
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
     "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv", "fftconv_bank_conv_max",
     "fftconv_bank_conv_detect", "fftconv_bank_conv_topk",
+    "fftconv_plan_create", "fftconv_plan_execute", "fftconv_plan_info", "fftconv_plan_destroy",
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
     "fftconv_spectrum_ready_event", "fftconv_query_path",
     "fftconv_peer_alloc", "fftconv_peer_open", "fftconv_peer_close", "fftconv_peer_free", "fftconv_peer_signal",
-    "fftconv_peer_wait", "fftconv_peer_wait_all", "fftconv_peer_pull", "fftconv_peer_status",
+    "fftconv_peer_wait", "fftconv_peer_wait_all", "fftconv_peer_pull", "fftconv_peer_status", "fftconv_peer_allgather",
 ]
 
 # error ids / messages of the reference
@@ -104,6 +105,7 @@ def lib() -> ctypes.CDLL:
         L.fftconv_peer_wait_all.argtypes = [c_vp, c_int, ctypes.c_ulonglong, c_int, c_vp]
         L.fftconv_peer_pull.argtypes = [c_vp, c_vp, ctypes.c_size_t, c_int, c_vp]
         L.fftconv_peer_status.argtypes = [c_int]
+        L.fftconv_peer_allgather.argtypes = [c_vp, c_int, c_int, c_vp, ctypes.c_ulonglong, ctypes.c_ulonglong, c_int, c_vp]
         L.fftconv_fft_size_pow2.argtypes = [c_int]
         L.fftconv_fft_data.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
         L.fftconv_fft_data_clamp.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]
@@ -121,6 +123,11 @@ def lib() -> ctypes.CDLL:
         L.fftconv_bank_conv_max.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp]
         L.fftconv_bank_conv_detect.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, ctypes.c_float, c_int, c_vp, c_vp, c_int, c_vp]
         L.fftconv_bank_conv_topk.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_plan_create.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp]
+        L.fftconv_plan_execute.argtypes = [c_vp, c_vp]
+        L.fftconv_plan_info.argtypes = [c_vp, c_vp, c_vp]
+        L.fftconv_plan_destroy.argtypes = [c_vp]
+        L.fftconv_plan_destroy.restype = None
         L.fftconv_bank_destroy.argtypes = [c_vp]
         L.fftconv_bank_destroy.restype = None
         L.fftconv_conv_bank.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]
@@ -594,6 +601,62 @@ class Bank:
     def close(self):
         if getattr(self, "_h", None):
             lib().fftconv_bank_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Plan:
+    """Graph plan (fftconv_plan_*): the launch sequence of cudaFFTData + cudaConvFFTData over fixed device buffers,
+    captured once into a CUDA graph; execute() is one graph launch.  The tensors' CONTENTS may change between executions.
+
+        plan = fc.Plan(data_t, bank_t, kh, kw)       # data_t [F][W][H], bank_t [K][F][kw][kh] float32 on the device
+        data_t.copy_(next_frame); plan.execute()      # -> plan.out [K][FW][FH] (and plan.spec, the cudaFFTData spectrum)
+    With data_t=None and spec_t given the plan starts from the spectrum (cudaConvFFTData only)."""
+
+    def __init__(self, data_t, bank_t, kh: int, kw: int, spec_t=None, out_t=None, shape=None, options: Optional[Options] = None,
+                 stream=None):
+        torch = _torch()
+        K, F, bkw, bkh = (int(x) for x in bank_t.shape)
+        if data_t is not None:
+            Fd, W, H = (int(x) for x in data_t.shape)
+        else:
+            H, W, Fd = shape
+        if Fd != F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        FH, FW = computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)
+        dev = bank_t.device
+        self.device = int(dev.index or 0)
+        self.spec = spec_t if spec_t is not None else torch.empty((F, FW, FH // 2 + 1), dtype=torch.complex64, device=dev)
+        ch = options.crop_h if options is not None and options.crop_h > 0 else FH
+        cw = options.crop_w if options is not None and options.crop_w > 0 else FW
+        ld = options.out_ld if options is not None and options.out_ld > 0 else ch
+        self.out = out_t if out_t is not None else torch.empty((K, cw, ld), dtype=torch.float32, device=dev)
+        self._keep = (data_t, bank_t, options)
+        st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        h = ctypes.c_void_p(0)
+        rc = lib().fftconv_plan_create(data_t.data_ptr() if data_t is not None else None, H, W, F, kh, kw, self.spec.data_ptr(),
+                                       K, bank_t.data_ptr(), bkh, bkw, self.out.data_ptr(),
+                                       ctypes.byref(options) if options is not None else None, self.device, st, ctypes.byref(h))
+        _check(rc, ERRID_CONV)
+        self._h = h
+        n, pth = ctypes.c_int(0), ctypes.c_int(0)
+        lib().fftconv_plan_info(h, ctypes.byref(n), ctypes.byref(pth))
+        self.graph_nodes, self.path = n.value, pth.value
+
+    def execute(self, stream=None):
+        torch = _torch()
+        st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(self.device).cuda_stream
+        _check(lib().fftconv_plan_execute(self._h, st), ERRID_CONV)
+        return self.out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().fftconv_plan_destroy(self._h)
             self._h = None
 
     def __del__(self):

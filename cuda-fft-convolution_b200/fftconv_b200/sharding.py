@@ -215,6 +215,148 @@ class PeerSpectrum:
         self.enabled = False
 
 
+def channel_slices(F: int, world: int) -> List[int]:
+    """Boundaries of `world` contiguous, near-equal channel ranges of 0..F (len world + 1; ranges may be empty)."""
+    return [(F * r) // world for r in range(world + 1)]
+
+
+class PeerAllGatherSpectrum:
+    """The data spectrum assembled on EVERY rank without a single-source fan-out: rank r transforms channels
+    bounds[r]..bounds[r+1] of the (replicated) image into its own CUDA-IPC buffer and one kernel per rank pulls the other
+    ranks' slices through their NVLink mappings, ordered by device-side flags (fftconv_peer_allgather).  Compared with
+    PeerSpectrum (rank 0 transforms everything, N - 1 ranks pull the whole spectrum out of rank 0's egress) no rank sends
+    more than (N - 1)/N of one spectrum and the transform itself is split N ways.
+
+        ag = PeerAllGatherSpectrum((F, FW, CH))          # collective
+        each step:  ag.begin_fill()                       # my previous slice has been pulled by everyone
+                    ag.fill(data_t, H, W, kh, kw)         # cudaFFTData on my channel range, into my slice of ag.spec
+                    spec = ag.gather()                    # complex64 [F][FW][CH], complete on this rank (stream-ordered)
+
+    Falls back to per-slice NCCL / gloo broadcasts when CUDA IPC is unavailable (`enabled` False)."""
+
+    def __init__(self, shape, group=None):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import lib
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.shape = tuple(int(x) for x in shape)
+        F, FW, CH = self.shape
+        self.bounds = channel_slices(F, self.world)
+        self.nbytes = 8 * F * FW * CH
+        self.flag_off = (self.nbytes + 255) // 256 * 256
+        self.step = 0
+        self._L = None
+        self._owned = None
+        self._mapped = {}
+        self.enabled = False
+        cuda = torch.cuda.is_available()
+        self.dev = torch.cuda.current_device() if cuda else None
+        ok, handle = 0, b""
+        if cuda and self.world <= 16:
+            self._L = L = lib()
+            p, h = ctypes.c_void_p(0), (ctypes.c_ubyte * 64)()
+            if L.fftconv_peer_alloc(self.flag_off + 8 * (1 + self.world), self.dev, ctypes.byref(p), h) == 0:
+                self._owned, handle, ok = p.value, bytes(h), 1
+        if self.world > 1:
+            got = [None] * self.world
+            dist.all_gather_object(got, (ok, handle), group=group)
+            ok = min(g[0] for g in got)
+            if ok:
+                for r, (_, hb) in enumerate(got):
+                    if r == self.rank:
+                        continue
+                    p = ctypes.c_void_p(0)
+                    if self._L.fftconv_peer_open((ctypes.c_ubyte * 64)(*hb), self.dev, ctypes.byref(p)) == 0:
+                        self._mapped[r] = p.value
+                    else:
+                        ok = 0
+            oks = [None] * self.world
+            dist.all_gather_object(oks, int(ok), group=group)
+            ok = min(oks)
+        self.enabled = bool(ok)
+        if self.enabled:
+            raw = torch.as_tensor(_RawCuda(self._owned, self.nbytes), device=f"cuda:{self.dev}")
+            self.spec = torch.view_as_complex(raw.view(torch.float32).view(F, FW, CH, 2))
+            bases = [self._owned if r == self.rank else self._mapped[r] for r in range(self.world)]
+            self._bases = (ctypes.c_void_p * self.world)(*bases)
+            per = 8 * FW * CH
+            self._offs = (ctypes.c_ulonglong * (self.world + 1))(*[b * per for b in self.bounds])
+        else:
+            self._release()
+            self.spec = torch.empty(self.shape, dtype=torch.complex64, device=(f"cuda:{self.dev}" if cuda else "cpu"))
+
+    def my_channels(self) -> Tuple[int, int]:
+        return self.bounds[self.rank], self.bounds[self.rank + 1]
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _chk(self, rc):
+        if rc != 0:
+            from . import last_error
+            raise RuntimeError("peer all-gather: " + last_error())
+
+    def begin_fill(self):
+        if self.enabled and self.step > 0:
+            self._chk(self._L.fftconv_peer_wait_all(self._owned + self.flag_off + 8, self.world, self.step, self.dev, self._stream()))
+
+    def fill(self, data_t, H: int, W: int, kh: int, kw: int, fft_fn: Optional[Callable] = None):
+        """cudaFFTData on this rank's channel range of data_t [F][W][H], written into its slice of self.spec.
+        fft_fn(data_slice, n_channels, spec_slice) replaces the CUDA call in the CPU tests."""
+        f0, f1 = self.my_channels()
+        if f1 <= f0:
+            return
+        if fft_fn is not None:
+            fft_fn(data_t[f0:f1], f1 - f0, self.spec[f0:f1])
+            return
+        from . import fft_data_device
+        fft_data_device(data_t[f0:f1], H, W, f1 - f0, kh, kw, spec_t=self.spec[f0:f1])
+
+    def gather(self):
+        self.step += 1
+        if self.enabled:
+            self._chk(self._L.fftconv_peer_allgather(self._bases, self.world, self.rank, self._offs, self.flag_off, self.step,
+                                                     self.dev, self._stream()))
+            return self.spec
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            for r in range(self.world):
+                f0, f1 = self.bounds[r], self.bounds[r + 1]
+                if f1 > f0:
+                    dist.broadcast(torch.view_as_real(self.spec[f0:f1]), src=r, group=self.group)
+        return self.spec
+
+    def status(self) -> int:
+        return self._L.fftconv_peer_status(self.dev) if self.enabled else 0
+
+    def _release(self):
+        for p in self._mapped.values():
+            self._L.fftconv_peer_close(p, self.dev)
+        self._mapped = {}
+
+    def close(self):
+        """Collective: every rank unmaps its peers before any owner frees."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        if self.enabled:
+            import torch
+            torch.cuda.synchronize(self.dev)
+            self._release()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        if self._owned is not None:
+            self._L.fftconv_peer_free(self._owned, self.dev)
+            self._owned = None
+        self.enabled = False
+
+
 def bind_host_to_gpu(device_index: int) -> Optional[List[int]]:
     """Pin the calling process to the CPU cores NVML reports as local to the GPU (same NUMA node / PCIe root), BEFORE
     pinned host buffers are allocated: first touch then places them next to the GPU's PCIe link.  With one process per

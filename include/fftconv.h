@@ -95,7 +95,8 @@ int fftconv_conv_fft_data(const fftconv_float2* d_spec, int CH, int FW, int F,
 
 /* cudaConvFFTDataStreams — src/cudaConvFFTDataStreams.cu:121-522.  Same contract as
  * cudaConvFFTData, host kernels only (:352-374).  The reference's 2-stream round-robin
- * (:292-328,:338-469) is rebuilt as a chunked copy/compute pipeline over the kernel bank. */
+ * (:292-328,:338-469) is rebuilt as a chunked copy/compute pipeline over the kernel bank (the same one
+ * fftconv_conv_fft_data runs); its per-stream ConvPlan objects become the graph plans below (fftconv_plan_*). */
 int fftconv_conv_fft_data_streams(const fftconv_float2* d_spec, int CH, int FW, int F,
                                   int K, const float* const* kernels, const int* kh, const int* kw,
                                   const int* kf, float* const* outs,
@@ -174,6 +175,23 @@ int fftconv_bank_conv_detect(const fftconv_bank* bank, const float* data, int da
 int fftconv_bank_conv_topk(const fftconv_bank* bank, const float* data, int data_on_device, int H, int W,
                            const float* bias, int k, fftconv_peak* dets, int out_on_device, void* stream);
 
+/* PLANS — the persistent graph schedule over the kernel bank.  The reference prototype keeps one ConvPlan per stream
+ * (plans, scratch, stream; src/cudaConvFFTDataStreams.cu:124,292-328) and re-issues every launch of the per-kernel loop on
+ * every call (:338-469).  Here a plan fixes the DEVICE buffers of a repeated call -- image H x W x F (or, with d_data ==
+ * NULL, its spectrum), packed bank of K kernels kh x kw x F, K output planes back to back (as fftconv_conv_bank) -- and
+ * captures the whole launch sequence (cudaFFTData + cudaConvFFTData on whichever pipeline serves the shape, including its
+ * internal copy / data-side streams) into one CUDA graph.  fftconv_plan_execute is then a single graph launch on `stream`;
+ * the contents of the buffers may change between executions (video frames, pyramid levels of one size).  d_spec is the
+ * spectrum buffer (CH*FW*F complex): input when d_data == NULL, otherwise written by every execution.  The library
+ * re-captures transparently when another call has grown its cached scratch. */
+typedef struct fftconv_plan fftconv_plan;
+int fftconv_plan_create(const float* d_data, int H, int W, int F, int KH, int KW, fftconv_float2* d_spec,
+                        int K, const float* d_bank, int kh, int kw, float* d_out, const fftconv_options* opt,
+                        int device, void* stream, fftconv_plan** out);
+int fftconv_plan_execute(fftconv_plan* plan, void* stream);
+int fftconv_plan_info(const fftconv_plan* plan, int* graph_nodes, int* path);
+void fftconv_plan_destroy(fftconv_plan* plan);
+
 /* modulateAndNormalize — src/convolutionFFTkernel.cu:84-100: in place a = a*b/dataN. */
 int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_b,
                                    long long n, int device, void* stream);
@@ -203,6 +221,14 @@ int fftconv_peer_signal(unsigned long long* flag, unsigned long long value, int 
 int fftconv_peer_wait(const unsigned long long* flag, unsigned long long value, int device, void* stream);
 int fftconv_peer_wait_all(const unsigned long long* flags, int n, unsigned long long value, int device, void* stream);
 int fftconv_peer_pull(void* dst, const void* src_mapped, size_t bytes, int device, void* stream);
+/* ALL-GATHER form (no single-source fan-out): every rank owns a peer buffer of the same layout [spectrum | ready flag | n
+ * acknowledgement slots at flag_off], transforms ITS slice of the channels into its own buffer (fftconv_fft_data on a channel
+ * range) and calls fftconv_peer_allgather: the rank raises its ready flag, then ONE kernel waits for every other rank's flag
+ * through the NVLink mappings, pulls that rank's slice [offs[p], offs[p+1]) into the same offset of the local buffer and
+ * acknowledges in the owner's memory.  bases[p] = rank p's buffer (own pointer for p == rank); n <= 16.  Before refilling its
+ * slice for the next step a rank waits for the acknowledgements: fftconv_peer_wait_all(own acks, n, step). */
+int fftconv_peer_allgather(void* const* bases, int n, int rank, const unsigned long long* offs,
+                           unsigned long long flag_off, unsigned long long step, int device, void* stream);
 int fftconv_peer_status(int device);        /* 0: no wait has timed out on this device (synchronises the device) */
 
 /* Which pipeline would serve cudaConvolutionFFT(data H x W x F, declared maximum maxKH x maxKW, K kernels of that size)

@@ -279,3 +279,36 @@ def test_bigplane_c3_scaled_auto_and_device_outputs(fc, oracle):
         assert oracle.rel_l2(o, ref) < TOL
         assert oracle.rel_l2(o, g) < TOL
         assert not np.array_equal(o, g)          # really a different pipeline
+
+
+@pytest.mark.parametrize("shape", ["c1", "os", "big_template"])
+def test_graph_plan_replays_the_whole_schedule(fc, oracle, shape):
+    """fftconv_plan_*: data transform + bank convolution captured into one CUDA graph (the persistent schedule that
+    replaces the per-stream ConvPlans of src/cudaConvFFTDataStreams.cu:292-328,338-469); buffer contents change between
+    executions, another call grows the cached scratch in between (transparent re-capture)."""
+    import torch
+    rng = np.random.default_rng(91)
+    H, W, F, kh, kw, K = {"c1": (64, 8, 5, 10, 4, 10), "os": (120, 100, 6, 12, 9, 130), "big_template": (70, 100, 2, 40, 70, 3)}[shape]
+    bank = rng.standard_normal((K, kh, kw, F)).astype(np.float32)
+    b_t = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    d_t = torch.zeros((F, W, H), device="cuda")
+    plan = fc.Plan(d_t, b_t, kh, kw)
+    assert plan.graph_nodes >= 3 and plan.path == {"c1": 2, "os": 3, "big_template": 1}[shape]
+    FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+    for rep in range(3):
+        data = rng.random((H, W, F), dtype=np.float32)
+        d_t.copy_(torch.from_numpy(np.ascontiguousarray(data.transpose(2, 1, 0))))
+        before = fc.launch_count()
+        out = plan.execute()
+        if rep != 1:                                                # (rep 1 re-captures: the scratch grew behind the plan)
+            assert fc.launch_count() == before + 1                 # one graph launch
+        torch.cuda.synchronize()
+        for k in (0, K - 1):
+            assert oracle.rel_l2(out[k].cpu().numpy().T, oracle.direct_conv64_c(data, bank[k], FH, FW)) < TOL, (rep, k)
+        ref_spec = oracle.fft_data(data, kh, kw)
+        got = plan.spec.cpu().numpy()
+        assert oracle.rel_l2(np.stack([got.real, got.imag]), np.stack([ref_spec.real, ref_spec.imag])) < TOL
+        if rep == 0:                                                # grow the cached scratch behind the plan's back
+            big = rng.random((300, 260, F), dtype=np.float32)
+            fc.cudaConvolutionFFT(big, kh, kw, [bank[k] for k in range(K)])
+    plan.close()

@@ -62,3 +62,54 @@ def test_peer_spectrum_two_processes(fc):
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
     assert res[0][2] == res[1][2]                 # both ranks agree on IPC vs fallback
+
+
+def _ag_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-fft-convolution_b200")]
+    import torch
+    import torch.distributed as dist
+    import fftconv_b200 as fc
+    from fftconv_b200.sharding import PeerAllGatherSpectrum
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.cuda.set_device(0)
+        rng = np.random.default_rng(9)
+        H, W, F, kh, kw = 40, 30, 5, 8, 8                                     # 5 channels over 3 ranks: slices 1, 2, 2
+        ag = PeerAllGatherSpectrum((F, 48, 25))
+        ok, used_ipc = True, ag.enabled
+        for step in range(4):
+            data = rng.random((H, W, F), dtype=np.float32) + step           # the image is replicated: same stream of inputs
+            d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(2, 1, 0))).cuda()
+            ag.begin_fill()
+            ag.fill(d_t, H, W, kh, kw)
+            spec = ag.gather()
+            want = fc.fft_data_device(d_t, H, W, F, kh, kw)
+            torch.cuda.synchronize()
+            ok = ok and bool(torch.equal(torch.view_as_real(spec), torch.view_as_real(want)))
+        ok = ok and ag.status() == 0
+        ag.close()
+        q.put((rank, bool(ok), bool(used_ipc)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_allgather_three_processes(fc):
+    """fftconv_peer_allgather: every rank transforms its channel slice, one kernel per rank pulls the others' slices."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ag_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
+    assert len({r[2] for r in res}) == 1

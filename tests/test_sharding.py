@@ -149,3 +149,63 @@ def test_pyramid_sides_config5(fc):
     sides = pyramid_sides()
     assert sides == [256, 223, 194, 169, 147, 128, 111, 97, 84, 74]
     assert [level_plane(s, s, 16, 16)[0] for s in sides] == [272, 240, 224, 192, 176, 144, 128, 112, 112, 96]
+
+
+def test_channel_slices():
+    from fftconv_b200.sharding import channel_slices
+    for F in (1, 5, 31, 32):
+        for world in (1, 2, 3, 8):
+            b = channel_slices(F, world)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == F and all(b[i] <= b[i + 1] for i in range(world))
+            sizes = [b[i + 1] - b[i] for i in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _ag_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-fft-convolution_b200")]
+    import torch
+    import torch.distributed as dist
+    import oracle
+    from fftconv_b200.sharding import PeerAllGatherSpectrum
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(4)
+        data = rng.random((40, 30, 3), dtype=np.float32)              # replicated image
+        full = oracle.fft_data(data, 8, 8)                            # [F][FW][CH]
+        ag = PeerAllGatherSpectrum(full.shape)                        # no CUDA here: per-slice broadcast fallback
+        d_fwh = torch.from_numpy(np.ascontiguousarray(data.transpose(2, 1, 0)))
+
+        def fft_fn(d_slice, nch, spec_slice):
+            part = oracle.fft_data(np.ascontiguousarray(d_slice.numpy().transpose(2, 1, 0)), 8, 8)
+            spec_slice.copy_(torch.from_numpy(part))
+
+        ok = not ag.enabled
+        for _ in range(2):
+            ag.begin_fill()
+            ag.fill(d_fwh, 40, 30, 8, 8, fft_fn=fft_fn)
+            spec = ag.gather()
+            ok = ok and np.array_equal(spec.numpy(), full)
+        ag.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_allgather_spectrum_fallback_world2():
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ag_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
