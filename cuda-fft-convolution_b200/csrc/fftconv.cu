@@ -541,12 +541,12 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
     g.NMMA = (2 * g.NTn + 15) & ~15;
     g.RS = (2 * g.NTn + 7) & ~7;
     g.a_stage = (size_t)2 * g.KC * OS_TM * 16;
-    g.b_buf = (size_t)g.NKS * 2 * g.KC * g.NMMA * 16;
+    g.b_buf = (size_t)g.NKS * g.KC * g.NMMA * 16;                       // fp32 B image of one (tile block, bin)
     g.p_blk = (size_t)OS_TM * g.RS * 4;
     if (g.b_buf >= (1u << 20) || g.a_stage >= (1u << 20)) return false;       // mbarrier tx-count range
     g.nsta = 0;                                                           // raw A ring depth (fp32 K-stages in flight)
     for (int ns = 8; ns >= 2; --ns) {
-        const size_t tot = (size_t)(ns + 2) * (g.a_stage / 2) + 2 * g.b_buf + g.p_blk + 512;
+        const size_t tot = (size_t)(ns + 2) * (g.a_stage / 2) + 4 * g.b_buf + g.p_blk + 512;   // + raw and lo images of B, double-buffered
         if (tot <= kMaxSmem) { g.nsta = ns; g.gemm_smem = tot; break; }
     }
     if (!g.nsta) return false;
@@ -651,7 +651,9 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
         a.src = src; a.F = F; a.nth = g.nth; a.NTimg = g.NTimg; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = FH; a.FW = FW; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.NTn = g.NTn;
         a.correlate = correlate;
-        dim3 grid(g.NT, g.NKS * g.KC);
+        // channel pair fastest: the CTAs resident at any time complete whole (tile block, bin) blocks of the B image
+        // together (tile-fastest order left every 16-byte row pair of a block to be written at 16 different times)
+        const unsigned grid = (unsigned)g.NT * (unsigned)(g.NKS * g.KC);
         ProfScope ps(PK_OS_DATA, st);
         os_data_fft<<<grid, 128, OS_DATA_SMEM, st>>>(a);
         LAUNCH_CHECK();

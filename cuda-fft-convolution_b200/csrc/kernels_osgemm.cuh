@@ -27,7 +27,7 @@
 //
 // Operand images (K-major, no swizzle; one 16-byte unit = 4 consecutive k = channels (2c,2c+1) x (re,im)):
 //   Aimg [tblk][bin][ks][kc][128 templates][4]  plain fp32      (MMA A: rows = templates; hi/lo split on chip)
-//   Bimg [nblk][bin][ks][term hi/lo][kc][NMMA rows     ][4]      (MMA B: rows = (tile, re/im column))
+//   Bimg [nblk][bin][ks][kc][NMMA rows     ][4]  plain fp32      (MMA B: rows = (tile, re/im column); hi/lo split on chip)
 //   P    [tblk][nblk][bin = u*64 + v][128 templates][RS]  fp32, (re,im) per tile: WORK-ITEM MAJOR -- the 128 x RS block
 //        an os_gemm item produces is one contiguous run (one bulk store per item; with the earlier [u][template][v][RS]
 //        order an item scattered 128 pieces of RS*4 bytes 64*RS*4 bytes apart and the kernel ran 0.28 instead of 0.21 ms
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(256, 2) os_kern_fft(OsKArgs a)
 // the two 64 x 64 windows are gathered with coalesced loads (zero fill beyond the source, circular wrap at
 // FH x FW), transformed along h (two real columns per complex sequence, two threads per line) and along w
 // in shared memory, split hi/lo and stored as the (re-row, im-row) pair of the tile in the B image.
-// grid = (NT, NKS*KC), 128 threads.  NT = images * tiles per image (batched calls: the images only add tiles).
+// grid = NT * NKS*KC (channel pair fastest), 128 threads.  NT = images * tiles per image (batched calls: the images only add tiles).
 struct OsDArgs {
     SrcDesc src;            // image 0: [F][cols][rows]; image n follows at n*F*cols*rows
     int F, nth, NTimg, Sh, Sw, oy0, ox0, FH, FW;
@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     float* raw = reinterpret_cast<float*>(os_smem_raw);                              // [2][64][65]
     cpx* Hs = reinterpret_cast<cpx*>(os_smem_raw + 2 * 64 * OS_DRAW * sizeof(float));   // [2][33][66]
-    const int m = blockIdx.x, fp = blockIdx.y;
+    const int npair = a.NKS * a.KC;
+    const int m = blockIdx.x / npair, fp = blockIdx.x - m * npair;      // channel pair fastest
     const int img = m / a.NTimg, mt = m - img * a.NTimg;          // tiles of a batch are numbered image-major
     const int tj = mt / a.nth, ti = mt - tj * a.nth;
     const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
@@ -442,9 +443,9 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
         if (u < OS_CH) {
             const int nblk = m / a.NTn, sl = m - nblk * a.NTn;
             const int ks = fp / a.KC, kc = fp - ks * a.KC;
-            const size_t term_stride = (size_t)a.KC * a.NMMA * 4;
-            const size_t bin_stride = (size_t)a.NKS * 2 * term_stride;
-            float* base = a.img + ((size_t)nblk * OS_NBIN + (size_t)u * 64 + par) * bin_stride + (size_t)ks * 2 * term_stride +
+            const size_t stage_stride = (size_t)a.KC * a.NMMA * 4;
+            const size_t bin_stride = (size_t)a.NKS * stage_stride;
+            float* base = a.img + ((size_t)nblk * OS_NBIN + (size_t)u * 64 + par) * bin_stride + (size_t)ks * stage_stride +
                           (size_t)kc * a.NMMA * 4 + (size_t)(2 * sl) * 4;
             float r0A[16], i0A[16], r0B[16], i0B[16], r1A[16], i1A[16], r1B[16], i1B[16];
             {
@@ -463,16 +464,11 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
             // correlate: K^ -> conj(K^):  out_re = sum a*c + b*d, out_im = sum a*d - b*c
             // the 1/(64*64) of the inverse transform rides here: a power of two, so the scaling is exact
             const float sc = 1.0f / 4096.0f, sg = a.correlate ? -sc : sc;
+            // plain fp32 (re-row, im-row): os_gemm splits hi / lo on chip, as it does for the A images
             auto emit = [&](float* o, float c0x, float c0y, float c1x, float c1y) {
-                const float4 vr = make_float4(sc * c0x, -sg * c0y, sc * c1x, -sg * c1y);
-                const float4 vi = make_float4(sc * c0y, sg * c0x, sc * c1y, sg * c1x);
-                const float4 hr = make_float4(os_tf32_hi(vr.x), os_tf32_hi(vr.y), os_tf32_hi(vr.z), os_tf32_hi(vr.w));
-                const float4 hq = make_float4(os_tf32_hi(vi.x), os_tf32_hi(vi.y), os_tf32_hi(vi.z), os_tf32_hi(vi.w));
                 float4* oh = reinterpret_cast<float4*>(o);
-                oh[0] = hr; oh[1] = hq;
-                float4* ol = reinterpret_cast<float4*>(o + term_stride);
-                ol[0] = make_float4(vr.x - hr.x, vr.y - hr.y, vr.z - hr.z, vr.w - hr.w);
-                ol[1] = make_float4(vi.x - hq.x, vi.y - hq.y, vi.z - hq.z, vi.w - hq.w);
+                oh[0] = make_float4(sc * c0x, -sg * c0y, sc * c1x, -sg * c1y);
+                oh[1] = make_float4(sc * c0y, sg * c0x, sc * c1y, sg * c1x);
             };
 #pragma unroll
             for (int j1 = 0; j1 < 16; ++j1) {
@@ -570,8 +566,8 @@ __host__ __device__ constexpr uint32_t os_idesc_tf32(int M, int N) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// os_gemm: persistent, warp-specialised.  Work item = (tile block, bin, template block); a CTA owns a
-// contiguous range of items ordered so that consecutive items share the B operand (same tile block & bin).
+// os_gemm: persistent, warp-specialised.  Work item = (bin, tile block, template block); a CTA owns a
+// contiguous range of items ordered so that consecutive items share the B operand (same bin & tile block).
 //   warp 0 : TMA producer (cp.async.bulk + mbarrier expect_tx), A ring of `nsta` K-stages, 2 B buffers
 //   warp 1 : TMEM allocation + single-thread tcgen05.mma issue; 3 passes (lo*hi, hi*lo, hi*hi) per K-stage
 //   warps 2-5 : epilogue, tcgen05.ld -> registers -> smem staging -> one bulk store per template row
@@ -596,33 +592,38 @@ struct OsGemmArgs {
 // Walks the work items (tile block, bin, template block) of one CTA without 64-bit divisions in the loop
 // (the single-thread producer / MMA roles execute every instruction at full dependent latency).
 struct OsItemIter {
-    int tblk, bin, nblk, ntblk;
+    int tblk, bin, nblk, ntblk, nnb;
     long long key;
-    __device__ __forceinline__ OsItemIter(long long it, int NTBLK) : ntblk(NTBLK) {
+    // item = ((bin * NNB + nblk) * NTBLK + tblk): BIN-major.  With several tile blocks (batched images) a CTA stays on one
+    // bin while it walks the tile blocks, so the A images of that bin (NTBLK x 32 KB) are re-read from L2 instead of
+    // being streamed from HBM once per tile block (tile-block-major order: 4.4 GB of A reads per launch at config 4).
+    __device__ __forceinline__ OsItemIter(long long it, int NTBLK, int NNB) : ntblk(NTBLK), nnb(NNB) {
         key = it / NTBLK;
         tblk = (int)(it - key * NTBLK);
-        nblk = (int)(key / OS_NBIN);
-        bin = (int)(key - (long long)nblk * OS_NBIN);
+        bin = (int)(key / NNB);
+        nblk = (int)(key - (long long)bin * NNB);
     }
     __device__ __forceinline__ void next() {
         if (++tblk == ntblk) {
             tblk = 0; ++key;
-            if (++bin == OS_NBIN) { bin = 0; ++nblk; }
+            if (++nblk == nnb) { nblk = 0; ++bin; }
         }
     }
     __device__ __forceinline__ bool last_of_key() const { return tblk + 1 == ntblk; }
+    __device__ __forceinline__ size_t b_block() const { return (size_t)nblk * OS_NBIN + bin; }     // index of the B image block
 };
 
 __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     const uint32_t a_half = (uint32_t)g.KC * OS_TM * 16u;       // one K-stage of A (fp32 as it travels; one hi or lo image)
-    const uint32_t b_stage = 2u * g.KC * g.NMMA * 16u;          // one K-stage of B: [hi | lo]
+    const uint32_t b_stage = (uint32_t)g.KC * g.NMMA * 16u;     // one K-stage of B (fp32 as it travels = hi operand)
     const uint32_t b_buf = b_stage * g.NKS;
     unsigned char* a_sm = os_smem_raw;                          // raw ring [nsta][a_half]: TMA target = hi operand
     unsigned char* lo_sm = a_sm + (size_t)g.nsta * a_half;      // lo ring [2][a_half]
-    unsigned char* b_sm = lo_sm + 2 * (size_t)a_half;           // [2][b_buf]
-    float* stage_sm = reinterpret_cast<float*>(b_sm + 2 * (size_t)b_buf);     // [128][RS] epilogue staging
+    unsigned char* b_sm = lo_sm + 2 * (size_t)a_half;           // [2][b_buf] raw B of the current / next key
+    unsigned char* blo_sm = b_sm + 2 * (size_t)b_buf;           // [2][b_buf] b - tf32(b)
+    float* stage_sm = reinterpret_cast<float*>(blo_sm + 2 * (size_t)b_buf);   // [128][RS] epilogue staging
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage_sm) + (size_t)OS_TM * g.RS * 4u);
     uint64_t* a_full = bars;                 // [nsta]  TMA -> splitter
     uint64_t* a_empty = bars + 8;            // [nsta]  MMA -> TMA
@@ -632,7 +633,8 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
     uint64_t* b_empty = bars + 28;           // [2]
     uint64_t* acc_full = bars + 30;          // [2]
     uint64_t* acc_empty = bars + 32;         // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 34);
+    uint64_t* b_ready = bars + 34;           // [2]     splitter -> MMA (lo image of B written)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long lo = g.nitems * (long long)blockIdx.x / gridDim.x;
@@ -644,6 +646,7 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
             mbar_init(&lo_empty[i], 1);
             mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
             mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128);
+            mbar_init(&b_ready[i], 128);
         }
         fence_barrier_init();
     }
@@ -657,19 +660,19 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
         if (lane == 0) {
             long long curkey = -1;
             uint32_t nb = 0, na = 0;
-            OsItemIter w(lo, g.NTBLK);
+            OsItemIter w(lo, g.NTBLK, g.NNB);
             // The A images are streamed exactly once, so every ring slot would otherwise pay the full HBM latency under
             // load (~2.3 us measured: with 4 slots of 16 KB that caps the CTA at ~30 GB/s).  A second iterator runs
             // `pf` items ahead and pulls the A block of that item (and the B block when a new key starts) into L2: the
             // bytes in flight towards HBM sit in L2 instead of shared memory and the ring only sees L2 latency.
             const int pf = g.pf_items;
-            OsItemIter wp(lo, g.NTBLK);
+            OsItemIter wp(lo, g.NTBLK, g.NNB);
             long long pit = lo, pkey = -1;
             auto prefetch_item = [&]() {
                 if (pit >= hi) return;
                 if (wp.key != pkey) {
                     pkey = wp.key;
-                    if (pit != lo) os_prefetch_l2(reinterpret_cast<const unsigned char*>(g.Bimg) + (size_t)pkey * b_buf, b_buf);
+                    if (pit != lo) os_prefetch_l2(reinterpret_cast<const unsigned char*>(g.Bimg) + wp.b_block() * b_buf, b_buf);
                 }
                 os_prefetch_l2(reinterpret_cast<const unsigned char*>(g.Aimg) + ((size_t)wp.tblk * OS_NBIN + wp.bin) * g.NKS * a_half,
                                a_half * g.NKS);
@@ -684,7 +687,7 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
                     const uint32_t bb = nb & 1;
                     if (nb >= 2) mbar_wait(&b_empty[bb], ((nb >> 1) - 1) & 1);
                     mbar_expect_tx(&b_full[bb], b_buf);
-                    bulk_g2s(b_sm + (size_t)bb * b_buf, reinterpret_cast<const unsigned char*>(g.Bimg) + (size_t)key * b_buf,
+                    bulk_g2s(b_sm + (size_t)bb * b_buf, reinterpret_cast<const unsigned char*>(g.Bimg) + w.b_block() * b_buf,
                              b_buf, &b_full[bb]);
                     ++nb;
                     curkey = key;
@@ -709,23 +712,22 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
         const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
         const uint32_t idesc = os_idesc_tf32(OS_TM, g.NMMA);
         const uint32_t a_lbo = OS_TM * 16u, b_lbo = (uint32_t)g.NMMA * 16u, sbo = 128u;
-        const uint32_t b_term = (uint32_t)g.KC * g.NMMA * 16u;
         // descriptor words: only the 14-bit start-address field of the low word changes between instructions
         const uint64_t adesc0 = g.lbo_swap ? os_smem_desc(0, sbo, a_lbo) : os_smem_desc(0, a_lbo, sbo);
         const uint64_t bdesc0 = g.lbo_swap ? os_smem_desc(0, sbo, b_lbo) : os_smem_desc(0, b_lbo, sbo);
         const uint32_t a_w0 = (uint32_t)adesc0, a_w1 = (uint32_t)(adesc0 >> 32);
         const uint32_t b_w0 = (uint32_t)bdesc0, b_w1 = (uint32_t)(bdesc0 >> 32);
         const uint32_t a_step = 2u * a_lbo >> 4, b_step = 2u * b_lbo >> 4;     // K advances by 2 units of 16 bytes
-        const uint32_t a_sm0 = smem_u32(a_sm), lo_sm0 = smem_u32(lo_sm), b_sm0 = smem_u32(b_sm);
+        const uint32_t a_sm0 = smem_u32(a_sm), lo_sm0 = smem_u32(lo_sm), b_sm0 = smem_u32(b_sm), blo_sm0 = smem_u32(blo_sm);
         const int nj = g.KC >> 1;                                              // <= 4
         long long curkey = -1;
         uint32_t nb = 0, na = 0, nit = 0, bcur = 0;
-        OsItemIter w(lo, g.NTBLK);
+        OsItemIter w(lo, g.NTBLK, g.NNB);
         for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
             const long long key = w.key;
             if (key != curkey) {
                 bcur = nb & 1;
-                mbar_wait(&b_full[bcur], (nb >> 1) & 1);
+                mbar_wait(&b_ready[bcur], (nb >> 1) & 1);
                 ++nb;
                 curkey = key;
             }
@@ -738,9 +740,9 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
                 os_tc_fence_after();
                 const uint32_t ad_hi = a_w0 | (((a_sm0 + st * a_half) >> 4) & 0x3FFFu);
                 const uint32_t ad_lo = a_w0 | (((lo_sm0 + ls * a_half) >> 4) & 0x3FFFu);
-                const uint32_t b_base = b_sm0 + bcur * b_buf + (uint32_t)ks * b_stage;
-                const uint32_t bd_hi = b_w0 | ((b_base >> 4) & 0x3FFFu);
-                const uint32_t bd_lo = b_w0 | (((b_base + b_term) >> 4) & 0x3FFFu);
+                const uint32_t b_off = bcur * b_buf + (uint32_t)ks * b_stage;
+                const uint32_t bd_hi = b_w0 | (((b_sm0 + b_off) >> 4) & 0x3FFFu);
+                const uint32_t bd_lo = b_w0 | (((blo_sm0 + b_off) >> 4) & 0x3FFFu);
                 if (os_elect_one()) {
                     // small terms first: (A lo, B hi), (A hi, B lo), then (A hi, B hi)
 #pragma unroll
@@ -766,10 +768,28 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
     } else if (warp >= 6) {
         // A splitter: lo = a - tf32(a) into the lo ring (the raw stage itself serves as the hi operand: kind::tf32 reads
         // only the sign, the exponent and the 10 high mantissa bits of each 32-bit element)
+        // The B image of a key gets the same treatment once per key (it serves all template blocks of the bin).
         const int sp = threadIdx.x - 192;             // 0..127
         const int kc = g.KC;                          // float4 per thread and stage (a_half / 16 / 128), <= 8
-        uint32_t na = 0;
-        for (long long it = lo; it < hi; ++it) {
+        const uint32_t nbv = b_buf / 16u;
+        uint32_t na = 0, nb = 0;
+        long long curkey = -1;
+        OsItemIter w(lo, g.NTBLK, g.NNB);
+        for (long long it = lo; it < hi; ++it, w.next()) {
+            if (w.key != curkey) {
+                curkey = w.key;
+                const uint32_t bb = nb & 1;
+                mbar_wait(&b_full[bb], (nb >> 1) & 1);
+                const float4* bp = reinterpret_cast<const float4*>(b_sm + (size_t)bb * b_buf);
+                float4* blp = reinterpret_cast<float4*>(blo_sm + (size_t)bb * b_buf);
+                for (uint32_t i = sp; i < nbv; i += 128) {
+                    const float4 v = bp[i];
+                    blp[i] = make_float4(v.x - os_tf32_hi(v.x), v.y - os_tf32_hi(v.y), v.z - os_tf32_hi(v.z), v.w - os_tf32_hi(v.w));
+                }
+                fence_proxy_async();
+                os_mbar_arrive(&b_ready[bb]);
+                ++nb;
+            }
             for (int ks = 0; ks < g.NKS; ++ks, ++na) {
                 const uint32_t st = na % g.nsta, ls = na & 1;
                 mbar_wait(&a_full[st], (na / g.nsta) & 1);
@@ -796,7 +816,7 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
         const int row = q * 32 + lane;                // template row of the block
         const bool leader = threadIdx.x == 64;        // issues the tensor store of the staging tile
         uint32_t nit = 0;
-        OsItemIter w(lo, g.NTBLK);
+        OsItemIter w(lo, g.NTBLK, g.NNB);
         for (long long it = lo; it < hi; ++it, ++nit, w.next()) {
             const int tblk = w.tblk, bin = w.bin, nblk = w.nblk;
             const uint32_t acc = nit & 1;
@@ -851,11 +871,11 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
     const long long it = blockIdx.x;
     const long long key = it / g.NTBLK;
     const int tblk = (int)(it - key * g.NTBLK);
-    const int bin = (int)(key % OS_NBIN);
-    const int nblk = (int)(key / OS_NBIN);
-    const size_t a_stage = (size_t)g.KC * OS_TM * 4, b_stage = (size_t)2 * g.KC * g.NMMA * 4;   // floats
+    const int bin = (int)(key / g.NNB);
+    const int nblk = (int)(key % g.NNB);
+    const size_t a_stage = (size_t)g.KC * OS_TM * 4, b_stage = (size_t)g.KC * g.NMMA * 4;   // floats
     const float* A = g.Aimg + ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
-    const float* B = g.Bimg + (size_t)key * g.NKS * b_stage;
+    const float* B = g.Bimg + ((size_t)nblk * OS_NBIN + bin) * g.NKS * b_stage;
     const int t = threadIdx.x;
     float* P = g.P + ((((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM + t) * (size_t)g.RS;
     for (int n = 0; n < g.RS; ++n) {
@@ -865,7 +885,7 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
                 const float4 ah = *reinterpret_cast<const float4*>(A + ks * a_stage + ((size_t)kc * OS_TM + t) * 4);
                 const float4 al = make_float4(0.f, 0.f, 0.f, 0.f);
                 const float4 bh = *reinterpret_cast<const float4*>(B + ks * b_stage + ((size_t)kc * g.NMMA + n) * 4);
-                const float4 bl = *reinterpret_cast<const float4*>(B + ks * b_stage + ((size_t)(g.KC + kc) * g.NMMA + n) * 4);
+                const float4 bl = make_float4(0.f, 0.f, 0.f, 0.f);
                 acc = fmaf(ah.x + al.x, bh.x + bl.x, acc);
                 acc = fmaf(ah.y + al.y, bh.y + bl.y, acc);
                 acc = fmaf(ah.z + al.z, bh.z + bl.z, acc);
