@@ -34,7 +34,9 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "lts__t_bytes.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__sass_inst_executed_op_local_ld.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "smsp__sass_inst_executed_op_local_ld.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.sum", "dram__bytes.sum.per_second"]
 traffic = {}
 with open(os.path.join(P, f"{R}_hot_kernels_ncu.md"), "w") as f:
     f.write(f"# {R}: `ncu --set full --clock-control none` of the hot kernels (one launch each, C2 workload, one chunk of 1000 templates)\n\n")
