@@ -260,7 +260,10 @@ static int ctx_get(int device, Ctx** out) {
         if (opt_in_smem(os_data_fft)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_gemm)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(os_inverse)) return FFTCONV_ERR_CUDA;
-        if (opt_in_smem(os_inverse_tma)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_inverse_tma<0>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_inverse_tma<6>)) return FFTCONV_ERR_CUDA;
+        if (opt_in_smem(os_inverse_z)) return FFTCONV_ERR_CUDA;
+
         if (opt_in_smem(inv_w_pass)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_conv_w<false, false, 512, 4, 1>)) return FFTCONV_ERR_CUDA;
         if (opt_in_smem(bp_conv_w<true, false, 512, 4, 1>)) return FFTCONV_ERR_CUDA;
@@ -608,6 +611,26 @@ static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nbins
     if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
+static int os_make_p_tensor_map5(const float* P, int RS, unsigned long long nblk, unsigned vbox, OsTensorMap* out) {
+    static PFN_tmapEncodeTiled encode = nullptr;   // P as {RS floats, 128 templates, 64 v, 33 u, template block x tile block}, box {8, 1, vbox, 33, 1}
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = (PFN_tmapEncodeTiled)fn;
+    }
+    static_assert(sizeof(CUtensorMap) == sizeof(OsTensorMap), "tensor map size");
+    const cuuint64_t row = (cuuint64_t)RS * 4;
+    const cuuint64_t gdim[5] = {(cuuint64_t)RS, OS_TM, OS_T, OS_CH, (cuuint64_t)nblk};
+    const cuuint64_t gstride[4] = {row, row * OS_TM, row * OS_TM * OS_T, row * OS_TM * OS_NBIN};
+    const cuuint32_t box[5] = {8, 1, vbox, OS_CH, 1}, estride[5] = {1, 1, 1, 1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(P), gdim,
+                              gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // (L2 promotion 64/128/256 B: no effect measured)
+    if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
 
 // Source plane -> B operand images (once per call).  If d_spec is given the plane is first recovered from
 // the compat spectrum (inverse w, then C2R along h); otherwise the raw data [F][W][H] is tiled directly.
@@ -754,8 +777,24 @@ static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStr
     const int ntb = (nk + OS_TM - 1) / OS_TM;
     // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
     if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
-        dim3 grid(g.NNB * (g.RS / 8), nk);             // (tile block, group of 4 tiles) x template
-        os_inverse_tma<<<grid, 256, OS_ITMA_SMEM, st>>>(a, tm);
+        const long long nitems = (long long)g.NNB * (g.RS / 8) * nk;      // (template, tile block, group of 4 tiles)
+        static const int use_z = []{ const char* v = getenv("FFTCONV_OS_INV_Z"); return v && *v ? atoi(v) : 1; }();
+        OsTensorMap tm8, tm1;
+        if (use_z && os_make_p_tensor_map5(a.P, g.RS, (unsigned long long)ntb * g.NNB, 8, &tm8) == 0 &&
+            os_make_p_tensor_map5(a.P, g.RS, (unsigned long long)ntb * g.NNB, 1, &tm1) == 0) {
+            // One CTA per item by default.  FFTCONV_OS_INV_PERSIST=1 runs 3 persistent CTAs per SM that request the boxes of
+            // their next item while they store the current one: the wait for the boxes disappears (5 % of the stall samples
+            // instead of 34 %), but with all 24 warps of an SM busy the 38 KB of live code thrash the 32 KB instruction cache
+            // (`no_instruction` becomes the top stall) and the tile groups of a template drift apart in time (DRAM reads
+            // 646 MB for the 608 MB of P): 0.254 ms against 0.231 ms at config 2 (profiles/r02_inverse_ab.md).
+            static const int persist = []{ const char* v = getenv("FFTCONV_OS_INV_PERSIST"); return v && *v ? atoi(v) : 0; }();
+            const unsigned grid = (unsigned)(persist ? std::min<long long>(nitems, 3LL * c.sm_count) : nitems);
+            os_inverse_z<<<grid, 256, OS_IZ_SMEM, st>>>(a, tm8, tm1, (int)nitems);
+        } else {
+            const dim3 g1(g.NNB * (g.RS / 8), nk);
+            if (use_z == 0 && os_env().dbg & 128) os_inverse_tma<0><<<g1, 256, OS_ITMA_SMEM, st>>>(a, tm);
+            else os_inverse_tma<6><<<g1, 256, OS_ITMA_SMEM, st>>>(a, tm);
+        }
     } else {
         dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
         os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);

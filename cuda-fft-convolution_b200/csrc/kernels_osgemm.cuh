@@ -169,7 +169,7 @@ __device__ __forceinline__ void os_fft64_task_rt(int r0, Load&& ld, float* re, f
 // outputs X[4*j1 + P] -> (reA, imA) and X[4*j1 + P + 2] -> (reB, imB), P = 0 or 1.
 //     P = 0:  a = x0 + x2, b = x1 + x3:  z_0 = a + b,            z_2 = (a - b) w64^{2c}
 //     P = 1:  a = x0 - x2, b = x1 - x3:  z_1 = (a -+ i b) w64^c, z_3 = (a +- i b) w64^{3c}    (x_q = x[c + 16 q])
-template <int P, bool INV, class Load>
+template <int P, bool INV, class Load, bool DFT = true>     // DFT = false: the first radix-4 stage only (the caller runs the 16-point transforms)
 __device__ __forceinline__ void os_fft64_pair(Load&& ld, float* reA, float* imA, float* reB, float* imB) {
     os_static_for<0, 8>([&](auto c2c) {
         constexpr int c2 = decltype(c2c)::value;
@@ -195,8 +195,10 @@ __device__ __forceinline__ void os_fft64_pair(Load&& ld, float* reA, float* imA,
             }
         });
     });
-    dft_regs<16, INV>(reA, imA);
-    dft_regs<16, INV>(reB, imB);
+    if (DFT) {
+        dft_regs<16, INV>(reA, imA);
+        dft_regs<16, INV>(reB, imB);
+    }
 }
 
 __device__ __forceinline__ int os_wrap(int i, int n) {
@@ -1029,21 +1031,24 @@ __device__ __forceinline__ void os_inverse_emit(const OsInvArgs& a, int t, int l
         }
         return;
     }
-    float* dst = T.dst + ylo;
-    if (a.dbg & 32) { if (reA[3] == 1.2345f) dst[0] = imB[5]; return; }
+    if (a.dbg & 32) { if (reA[3] == 1.2345f) T.dst[0] = imB[5]; return; }
+    // every store carries its own predicate and a 32-bit element offset (the branchy form with 64-bit products cost
+    // 9 instructions per store: a quarter of all instructions of the inverse)
+    float* dlo = T.dst + ylo;
+    const int ld = a.out_ld;
+    const unsigned unx = (unsigned)nx;
+    int off = (par - a.ox0) * ld;
 #pragma unroll
     for (int j1 = 0; j1 < 16; ++j1) {
-        const int xa = 4 * j1 + par - a.ox0, xb = xa + 2;
-        if (xa >= 0 && xa < nx) {
-            float* d = dst + (size_t)xa * a.out_ld;
-            if (wlo) d[0] = reA[j1];
-            if (whi) d[32] = imA[j1];
-        }
-        if (xb >= 0 && xb < nx) {
-            float* d = dst + (size_t)xb * a.out_ld;
-            if (wlo) d[0] = reB[j1];
-            if (whi) d[32] = imB[j1];
-        }
+        const int xa = 4 * j1 + par - a.ox0;
+        const bool pa = (unsigned)xa < unx, pb = (unsigned)(xa + 2) < unx;
+        float* d = dlo + off;
+        float* e = d + 2 * ld;
+        if (pa && wlo) d[0] = reA[j1];
+        if (pa && whi) d[32] = imA[j1];
+        if (pb && wlo) e[0] = reB[j1];
+        if (pb && whi) e[32] = imB[j1];
+        off += 4 * ld;
     }
 }
 
@@ -1241,13 +1246,54 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
 //   pass 2   and the store are os_inverse's: lanes along h, one warp per tile, every store instruction writes one
 //            contiguous run of a plane column.
 constexpr int OS_TROW = 256;          // complex pitch of a landed row: 64 columns x 4 tiles
-constexpr int OS_ITMA_SMEM = (OS_IG * OS_ITILE > OS_CH * OS_TROW ? OS_IG * OS_ITILE : OS_CH * OS_TROW) * 8;
+// per-tile stride of the re-laid buffer: 64 columns x 33 + 4 (columns >= 32 sit 4 elements further).  2116 = 4 mod 16, so
+// the 16 lanes of a half warp (4 tiles x 4 columns) of a pass-1 store hit 16 different 8-byte banks (the 2120 of
+// os_inverse put tiles q and q + 2 on the same banks: 4 wavefronts per store instead of 2)
+constexpr int OS_ITILE2 = 64 * OS_ICOL + 4;
+constexpr int OS_ITMA_SMEM = (OS_IG * OS_ITILE2 > OS_CH * OS_TROW ? OS_IG * OS_ITILE2 : OS_CH * OS_TROW) * 8;
 
 __device__ __forceinline__ void os_tma_load_3d(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                  ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
+template <int P, class Slot, bool DFT = true>
+__device__ __forceinline__ void os_c2r64_pair(Slot&& S, float* reA, float* imA, float* reB, float* imB) {
+    auto bfly = [&](auto cc, const cpx x0, const cpx x1, const cpx x2, const cpx x3) {
+        constexpr int c = decltype(cc)::value;
+        if (P == 0) {
+            const float ar = x0.x + x2.x, ai = x0.y + x2.y, br = x1.x + x3.x, bi = x1.y + x3.y;
+            reA[c] = ar + br; imA[c] = ai + bi;
+            os_twiddle<2 * c, true>(ar - br, ai - bi, reB[c], imB[c]);
+        } else {
+            const float ar = x0.x - x2.x, ai = x0.y - x2.y, br = x1.x - x3.x, bi = x1.y - x3.y;
+            os_twiddle<c, true>(ar - bi, ai + br, reA[c], imA[c]);          // a + i b
+            os_twiddle<3 * c, true>(ar + bi, ai - br, reB[c], imB[c]);      // a - i b
+        }
+    };
+    auto lo = [](const cpx p, const cpx z) { return make_float2(p.x - z.y, p.y + z.x); };    // W[v]
+    auto hi = [](const cpx p, const cpx z) { return make_float2(p.x + z.y, z.x - p.y); };    // W[64 - v]
+    {
+        const cpx p0 = S(0), p32 = S(32), p16 = S(16), p48 = S(48);
+        bfly(std::integral_constant<int, 0>{}, make_float2(p0.x, p32.x), lo(p16, p48), make_float2(p0.y, p32.y), hi(p16, p48));
+        const cpx p8 = S(8), p56 = S(56), p24 = S(24), p40 = S(40);
+        bfly(std::integral_constant<int, 8>{}, lo(p8, p56), lo(p24, p40), hi(p24, p40), hi(p8, p56));
+    }
+    os_static_for<1, 8>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const cpx pa = S(c), za = S(64 - c), pb = S(c + 16), zb = S(48 - c);
+        const cpx pc = S(32 - c), zc = S(c + 32), pd = S(16 - c), zd = S(c + 48);
+        bfly(cc, lo(pa, za), lo(pb, zb), hi(pc, zc), hi(pd, zd));
+        bfly(std::integral_constant<int, 16 - c>{}, lo(pd, zd), lo(pc, zc), hi(pb, zb), hi(pa, za));
+    });
+    if (DFT) {
+        dft_regs<16, true>(reA, imA);
+        dft_regs<16, true>(reB, imB);
+    }
+}
+// One-shot form (one CTA per item, 33 boxes on one mbarrier): FFTCONV_OS_INV_Z=0.  VAR & 1: one warp polls the mbarrier
+// (measured slower: 0.267 vs 0.256 ms), VAR & 2: conflict-free tile stride, VAR & 4: paired pass-2 loads.
+template <int VAR>
 __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __grid_constant__ OsTensorMap tmap)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
@@ -1299,7 +1345,8 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
 #pragma unroll 1
         for (int u = 0; u < OS_CH; ++u) os_tma_load_3d(buf + u * OS_TROW, &tmap, 8 * g, tl, bin0 + u * 64, &bar);
     }
-    mbar_wait(&bar, 0);
+    if (!(VAR & 1) || warp == 0) mbar_wait(&bar, 0);
+    if (VAR & 1) __syncthreads();
     // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
     //     col0[u] := Z[u][0] + i Z[u][32],   col32[u] := Z[u][0] - i Z[u][32]
     if (threadIdx.x < OS_IG * 33) {
@@ -1313,7 +1360,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
     __syncthreads();
     const int par = warp >> OS_IGB;                                        // warp-uniform: tasks (par, par + 2)
     // ---- pass 1: inverse along h.  x[u] = col_v[u] (u <= 32), conj(col_mv[64-u]) (u > 32); landed layout in,
-    //      per-tile layout out (tile q at q * OS_ITILE, column v at os_icol(v))
+    //      per-tile layout out (tile q at q * (VAR & 2 ? OS_ITILE2 : OS_ITILE), column v at os_icol(v))
     {
         const int q = lane & 3;
         const int v = 8 * (warp & 3) + (lane >> 2), mv = v ? 64 - v : 32;
@@ -1329,8 +1376,8 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
         else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
         __syncthreads();                                                   // every input of the CTA has been read
-        cpx* ov = buf + q * OS_ITILE + os_icol(v);
-        cpx* om = buf + q * OS_ITILE + os_icol(mv);
+        cpx* ov = buf + q * (VAR & 2 ? OS_ITILE2 : OS_ITILE) + os_icol(v);
+        cpx* om = buf + q * (VAR & 2 ? OS_ITILE2 : OS_ITILE) + os_icol(mv);
 #pragma unroll
         for (int j1 = 0; j1 < 16; ++j1) {                                  // Y[y]: y < 32 -> col v, y >= 32 -> col mv
             const int ya = 4 * j1 + par, yb = ya + 2;                      // (compile-time split: j1 < 8 <=> y < 32)
@@ -1342,7 +1389,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
     // ---- pass 2: C2R along w.  W[v] = Y[y][v] + i Y[y+32][v]; outputs straight to the plane (as os_inverse)
     {
         const int gq = warp & (OS_IG - 1);                                 // one warp = the 32 lines of one tile
-        const cpx* tile = buf + gq * OS_ITILE;
+        const cpx* tile = buf + gq * (VAR & 2 ? OS_ITILE2 : OS_ITILE);
         const int y = lane;
         if (!tile_ok[gq]) return;                                          // warp-uniform (no barrier below)
         const cpx* ty = tile + y;
@@ -1355,10 +1402,188 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
             return make_float2(p.x + z.y, z.x - p.y);
         };
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
-        if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
-        else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
+        auto slot = [&](int v) -> cpx { return ty[os_icol(v)]; };
+        if (VAR & 4) {
+            if (par == 0) os_c2r64_pair<0>(slot, reA, imA, reB, imB);
+            else          os_c2r64_pair<1>(slot, reA, imA, reB, imB);
+        } else {
+            if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
+            else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
+        }
         const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq]};
         os_inverse_emit(a, t, lane, par, mbase + gq, T, reA, imA, reB, imB);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// os_inverse_z: the inverse with the product spectra landing in four independent ZONES, persistent CTAs.
+// Zone z holds the 16 spectrum columns that pass 1 couples: v in [8z, 8z+8) ("direct") and their mirrors 64 - v.  P is
+// seen as a 5-D tensor {RS floats, 128 templates, 64 v, 33 u, template block x tile block}; one tensor copy with box
+// {8 floats = 4 tiles, 1 template, 8 columns, 33 rows} brings the direct columns of a zone, a second one the mirrors
+// (zone 0: columns 56..63, of which 57..63 are mirrors; column 32, the partner of column 0, comes through a third map
+// with a one-column box).  9 tensor copies per item instead of 33, one mbarrier per zone:
+//   * the two warps of a zone (par 0 / 1) start pass 1 as soon as THEIR 17 KB have landed, and rewrite the zone in place
+//     in the per-tile layout pass 2 reads (64 threads, one named barrier) -- no CTA-wide barrier until pass 2;
+//   * the item loop lets a CTA run persistently (FFTCONV_OS_INV_PERSIST=1: 3 per SM, the boxes of the next item are
+//     requested as soon as pass 2 has its inputs in registers); the default launches one CTA per item, which measured
+//     faster (see os_chunk_inverse in fftconv.cu).
+// Zone layout (complex units): direct box [u][8 v][4 tiles] at +0, mirror box at +1056; after pass 1
+// [4 tiles][16 slots][33] with tile stride 532 (slot s < 8: Y[y][8z+s], slot 8+s: Y[y+32][8z+s], y < 32).
+constexpr int OS_ZS = 4 * 532;                       // zone stride (2128 complex >= 2 * 1056)
+constexpr int OS_ZC32 = 4 * OS_ZS;                   // column 32: [u][4 tiles]
+constexpr int OS_IZ_SMEM = (OS_ZC32 + OS_CH * 4) * 8;
+
+__device__ __forceinline__ void os_tma_load_5d(void* dst, const void* tmap, int c0, int c1, int c2, int c3, int c4, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void os_zone_bar(int z) {                      // 64 threads: the two warps of zone z (ids 1..4)
+    switch (z) {
+        case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+        case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+        case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+        default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+}
+// complex offset of slot(v) of pass 2 inside a tile's share of the zones (compile-time v)
+__host__ __device__ constexpr int os_zslot(int v) {
+    return v < 32 ? (v >> 3) * OS_ZS + (v & 7) * 33
+         : v == 32 ? 8 * 33
+         : ((64 - v) >> 3) * OS_ZS + (8 + ((64 - v) & 7)) * 33;
+}
+
+__global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid_constant__ OsTensorMap tmap8,
+                                                       const __grid_constant__ OsTensorMap tmap1, int nitems)
+{
+    extern __shared__ __align__(128) unsigned char os_smem_raw[];
+    cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);
+    __shared__ __align__(8) uint64_t full[4];
+    __shared__ float* tile_dst[2][OS_IG];
+    __shared__ int tile_ny[2][OS_IG], tile_nx[2][OS_IG], tile_y0[2][OS_IG], tile_x0[2][OS_IG], tile_ok[2][OS_IG];
+    const int NG = a.RS >> 3;
+    const int NX = a.NNB * NG;                                             // items per template
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int par = warp >> 2, zq = warp & 3;                              // pass 1: zone zq; pass 2: tile zq
+    auto request = [&](int item) {                                         // one thread: 9 tensor copies
+        const int t = item / NX, bx = item - t * NX;
+        const int nblk = bx / NG, g = bx - nblk * NG;
+        const int tblk = t / OS_TM, tl = t - tblk * OS_TM;
+        const int blk = tblk * a.NNB + nblk;
+#pragma unroll
+        for (int z = 0; z < 4; ++z) {
+            mbar_expect_tx(&full[z], 2u * 8448u + (z == 0 ? 1056u : 0u));
+            os_tma_load_5d(buf + z * OS_ZS, &tmap8, 8 * g, tl, 8 * z, 0, blk, &full[z]);
+            os_tma_load_5d(buf + z * OS_ZS + 1056, &tmap8, 8 * g, tl, z ? 57 - 8 * z : 56, 0, blk, &full[z]);
+            if (z == 0) os_tma_load_5d(buf + OS_ZC32, &tmap1, 8 * g, tl, 32, 0, blk, &full[0]);
+        }
+    };
+    // grid-stride item order: the CTAs resident at any time work on neighbouring tile groups of the same templates, so the
+    // 32-byte pieces they request are neighbours in DRAM at about the same time.  (A contiguous share of the item list per
+    // CTA makes every CTA walk its own rows: 0.465 instead of 0.31 ms.)
+    const int item0 = (int)blockIdx.x, item1 = nitems, istep = (int)gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int z = 0; z < 4; ++z) mbar_init(&full[z], 1);
+        fence_barrier_init();
+        if (item0 < item1) request(item0);
+    }
+    __syncthreads();                                                       // the barriers exist before anyone polls them
+    int it = 0;
+#pragma unroll 1
+    for (int item = item0; item < item1; item += istep, ++it) {
+        const int sl = it & 1;
+        const int t = item / NX, bx = item - t * NX;
+        const int nblk = bx / NG, g = bx - nblk * NG;
+        const int mbase = nblk * a.NTn + 4 * g;                            // first tile of the group
+        if (threadIdx.x >= 32 && threadIdx.x < 32 + OS_IG) {               // (warp 1: warp 0 issues the copies)
+            const int i = threadIdx.x - 32;
+            const int m = mbase + i;
+            const bool ok = 4 * g + i < a.NTn && m < a.NT;
+            float* d = nullptr; int ny = 0, nx = 0;
+            if (ok) {
+                const int img = m / a.NTimg, mt = m - img * a.NTimg;
+                const int tj = mt / a.nth, ti = mt - tj * a.nth;
+                const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
+                tile_y0[sl][i] = Y0; tile_x0[sl][i] = X0;
+                if (a.peak_keys || a.det_mode) {      // region of the full linear convolution of THIS template
+                    const int2 k = a.khw[t];
+                    ny = min(a.Sh, a.H + k.x - 1 - Y0); nx = min(a.Sw, a.W + k.y - 1 - X0);
+                } else if (a.corr) {
+                    ny = min(a.Sh, a.FH - Y0); nx = min(a.Sw, a.FW - X0);
+                    d = a.outs[(size_t)img * a.out_img_stride + t];
+                } else {
+                    ny = min(a.Sh, a.crop_h - Y0); nx = min(a.Sw, a.crop_w - X0);
+                    d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
+                }
+            }
+            tile_dst[sl][i] = d; tile_ny[sl][i] = ny; tile_nx[sl][i] = nx; tile_ok[sl][i] = ok ? 1 : 0;
+        }
+        float reA[16], imA[16], reB[16], imB[16];
+        // Both passes run through ONE copy of the 16-point register transforms (a two-trip loop that stays rolled); only
+        // the first radix-4 stages are specialised by pass and parity.  With everything inlined per parity the kernel
+        // carried 61 KB of live straight-line code against a 32 KB instruction cache: once the persistent loop had
+        // removed the wait for the boxes, `no_instruction` became 37 % of all stall samples.
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0) {
+                // ---- pass 1 (zone zq): inverse along h.  x[u] = col_v[u] (u <= 32), conj(col_mv[64-u]) (u > 32)
+                cpx* Z = buf + zq * OS_ZS;
+                const int q = lane & 3, vl = lane >> 2;
+                mbar_wait(&full[zq], (uint32_t)sl);
+                if (zq == 0) {
+                    // columns 0 and 32 are spectra of real sequences along h: combine them into one complex column pair
+                    //     col0[u] := Z[u][0] + i Z[u][32],   col32[u] := Z[u][0] - i Z[u][32]     (col32 takes the unused
+                    //     slot of column 56 in the mirror box)
+                    for (int i = par * 32 + lane; i < OS_CH * 4; i += 64) {
+                        const int u = i >> 2, qq = i & 3;
+                        cpx* c0 = Z + u * 32 + qq;
+                        const cpx za = *c0, zb = buf[OS_ZC32 + i];
+                        *c0 = make_float2(za.x - zb.y, za.y + zb.x);
+                        c0[1056] = make_float2(za.x + zb.y, za.y - zb.x);
+                    }
+                    os_zone_bar(0);
+                }
+                const int ml = zq ? 7 - vl : ((8 - vl) & 7);
+                const cpx* cv = Z + vl * 4 + q;                            // element u: cv[u * 32]
+                const cpx* cm = Z + 1056 + ml * 4 + q;
+                auto ld1 = [&](int u) -> cpx {
+                    if (u <= 32) return cv[u * 32];
+                    const cpx z = cm[(64 - u) * 32];
+                    return make_float2(z.x, -z.y);
+                };
+                auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
+                if (par == 0) os_fft64_pair<0, true, decltype(ld)&, false>(ld, reA, imA, reB, imB);
+                else          os_fft64_pair<1, true, decltype(ld)&, false>(ld, reA, imA, reB, imB);
+            } else {
+                // ---- pass 2 (tile zq): C2R along w, rows y and y + 32 packed; one pair of loads gives W[v] and W[64 - v]
+                const cpx* ty = buf + zq * 532 + lane;
+                auto slot = [&](int v) -> cpx { return ty[os_zslot(v)]; };
+                if (par == 0) os_c2r64_pair<0, decltype(slot)&, false>(slot, reA, imA, reB, imB);
+                else          os_c2r64_pair<1, decltype(slot)&, false>(slot, reA, imA, reB, imB);
+            }
+            dft_regs<16, true>(reA, imA);
+            dft_regs<16, true>(reB, imB);
+            if (pass == 0) {
+                os_zone_bar(zq);                                           // both warps of the zone have read their inputs
+                cpx* ov = buf + zq * OS_ZS + (lane & 3) * 532 + (lane >> 2) * 33 + par;
+#pragma unroll
+                for (int j1 = 0; j1 < 16; ++j1) {                          // Y[y]: y < 32 -> slot vl, y >= 32 -> slot 8 + vl
+                    constexpr int dummy = 0; (void)dummy;
+                    const int o = j1 < 8 ? 4 * j1 : 8 * 33 + 4 * j1 - 32;  // y = 4 j1 + par (+ 2)
+                    ov[o] = make_float2(reA[j1], imA[j1]); ov[o + 2] = make_float2(reB[j1], imB[j1]);
+                }
+                __syncthreads();
+            }
+        }
+        __syncthreads();                                                   // the zones are free: request the next boxes
+        if (threadIdx.x == 0 && item + istep < item1) {
+            fence_proxy_async();
+            request(item + istep);
+        }
+        if (tile_ok[sl][zq]) {                                             // warp-uniform
+            const OsTileOut T{tile_dst[sl][zq], tile_ny[sl][zq], tile_nx[sl][zq], tile_y0[sl][zq], tile_x0[sl][zq]};
+            os_inverse_emit(a, t, lane, par, mbase + zq, T, reA, imA, reB, imB);
+        }
     }
 }
 
