@@ -136,6 +136,26 @@ struct Ctx {
     cudaStream_t side2 = nullptr;        // data-side transforms of the overlap-save path run here, next to os_kern_fft
     cudaEvent_t evf[2] = {nullptr, nullptr};
     int sm_count = 148;
+    // Provenance of the last spectrum fftconv_fft_data produced on this device.  The overlap-save path works from the raw
+    // data, not from the compat spectrum; a caller of the two-call interface hands the spectrum back, and inverting it to a
+    // plane again was 6 % of the config-2 step.  fft_data keeps a private copy of the raw data and a 64-bit hash of the
+    // spectrum it wrote; the convolution re-hashes what it is given ON THE DEVICE and its data-side kernels choose between
+    // the kept raw data (hashes equal) and the inverse of the spectrum (anything else: a spectrum the caller modified,
+    // another buffer that happens to live at the same address, ...).  No host synchronisation, no trust in pointers.
+    struct SpecCache {
+        bool valid = false;
+        const void* spec = nullptr;
+        int H = 0, W = 0, F = 0, FH = 0, FW = 0;
+        DevBuf raw, hash;                // raw data [F][W][H]; hash[0] = at fft_data time, hash[1] = at convolution time
+        // tile spectra (B images) computed next to the forward transform, on the data-side stream
+        bool b_valid = false;
+        int b_maxkh = 0, b_maxkw = 0;
+        long long b_gen = -1;
+        // geometry of the last spectrum-fed overlap-save convolution: decides whether the next fft_data tiles eagerly
+        bool want = false;
+        int w_F = 0, w_FH = 0, w_FW = 0, w_maxkh = 0, w_maxkw = 0;
+    } sc;
+    long long osB_gen = 0;               // bumped whenever os_data_fft (re)writes osB
     cudaEvent_t spec_ready = nullptr;    // fftconv_spectrum_ready_event: one-shot dependency of the data-side work
     // One lock per device: a call holds it from its first touch of the cached scratch to its last enqueue (host-output
     // calls: to the final synchronisation), so calls on different devices never serialise each other (the reference's
@@ -566,8 +586,10 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
 //   FFTCONV_OS_GEMM_TMAP  0: one bulk copy per template row in the GEMM epilogue instead of one bulk store per item
 //   FFTCONV_OS_HI_INPLACE 1: rewrite the A stage as tf32(a) in shared memory instead of relying on the operand truncation
 //   FFTCONV_OS_LBO_SWAP   swap the LBO / SBO fields of the shared-memory descriptors
+//   FFTCONV_SPEC_CACHE    0: never reuse the raw data behind a spectrum of fftconv_fft_data (always invert the spectrum);
+//                         1: reuse the raw data; 2 (default): also transform the tiles next to the forward transform
 //   FFTCONV_OS_PF         L2 prefetch distance of os_gemm's TMA producer in work items (default 0 = off: measured 0.21 -> 0.30 ms at config 2 with 6 items ahead, the prefetched lines fight the P stores for L2)
-struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf; };
+struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache; };
 static const OsEnv& os_env() {
     static const OsEnv e = [] {
         auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
@@ -582,6 +604,7 @@ static const OsEnv& os_env() {
         x.lbo_swap = geti("FFTCONV_OS_LBO_SWAP", 0);
         x.dbg = geti("FFTCONV_OS_DBG", 0);
         x.pf = geti("FFTCONV_OS_PF", 0);
+        x.spec_cache = geti("FFTCONV_SPEC_CACHE", 1);
         return x;
     }();
     return e;
@@ -634,8 +657,14 @@ static int os_make_p_tensor_map5(const float* P, int RS, unsigned long long nblk
 
 // Source plane -> B operand images (once per call).  If d_spec is given the plane is first recovered from
 // the compat spectrum (inverse w, then C2R along h); otherwise the raw data [F][W][H] is tiled directly.
+struct OsProv {                      // see Ctx::SpecCache
+    const unsigned long long* hsel = nullptr;
+    SrcDesc alt{};
+    int alt_done = 0;
+};
+static unsigned os_hash_grid(const Ctx& c, size_t n) { return (unsigned)std::min<size_t>((n + 2047) / 2048, (size_t)c.sm_count * 4); }
 static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const float* d_raw, int rawH, int rawW,
-                           int correlate, cudaStream_t st) {
+                           int correlate, cudaStream_t st, const OsProv* prov = nullptr) {
     const int F = g.F, FH = g.FH, FW = g.FW, CH = FH / 2 + 1;
     SrcDesc src;
     if (d_raw) {
@@ -656,15 +685,23 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
         CU(cudaMemcpyAsync(d_planes, h_planes, sizeof(float*) * (size_t)F, cudaMemcpyHostToDevice, st));
         if (int e = pinned_done(c, st)) return e;
         ProfScope ps(PK_OS_PLANE, st);
+        const unsigned long long* skip = prov ? prov->hsel : nullptr;
+        if (skip) {                                                  // hash of the spectrum the caller handed in -> hsel[1]
+            unsigned long long* h1 = const_cast<unsigned long long*>(skip) + 1;
+            const size_t n = (size_t)F * FW * CH;
+            CU(cudaMemsetAsync(h1, 0, sizeof(unsigned long long), st));
+            os_hash64<<<os_hash_grid(c, n), 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_spec), n, h1);
+            LAUNCH_CHECK();
+        }
         int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
         TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
         dim3 g2((CH + TU - 1) / TU, F);
-        inv_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>(d_spec, FW, CH, pW, twW, (cpx*)c.osZ.p, TU, ldW);
+        inv_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>(d_spec, FW, CH, pW, twW, (cpx*)c.osZ.p, TU, ldW, skip);
         LAUNCH_CHECK();
         const int NL = pick_lines(FH, 8);
         const long long nlines = (long long)F * (FW / 2);
         inv_h_pass<<<(unsigned)((nlines + NL - 1) / NL), 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
-            (const cpx*)c.osZ.p, F, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_planes, FH, FW, FH, NL, ldH);
+            (const cpx*)c.osZ.p, F, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_planes, FH, FW, FH, NL, ldH, skip);
         LAUNCH_CHECK();
         src.ptr = plane; src.rows = FH; src.cols = FW;
     }
@@ -674,6 +711,8 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
         a.src = src; a.F = F; a.nth = g.nth; a.NTimg = g.NTimg; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = FH; a.FW = FW; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.NTn = g.NTn;
         a.correlate = correlate;
+        if (prov && !d_raw) { a.hsel = prov->hsel; a.alt = prov->alt; a.alt_done = prov->alt_done; }
+        ++c.osB_gen;
         // channel pair fastest: the CTAs resident at any time complete whole (tile block, bin) blocks of the B image
         // together (tile-fastest order left every 16-byte row pair of a block to be written at 16 different times)
         const unsigned grid = (unsigned)g.NT * (unsigned)(g.NKS * g.KC);
@@ -920,7 +959,7 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
         ProfScope ps(PK_GEN_C2R, st);
         inv_h_pass<<<grid, 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
             (const cpx*)c.Z.p, nk, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_outptrs, crop_h, crop_w,
-            out_ld, NL, ldH);
+            out_ld, NL, ldH, nullptr);
         LAUNCH_CHECK();
     }
     return 0;
@@ -1224,7 +1263,21 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         CU(cudaEventRecord(c.evf[0], st));
         CU(cudaStreamWaitEvent(c.side2, c.evf[0], 0));
         if (spec_ready) CU(cudaStreamWaitEvent(c.side2, spec_ready, 0));
-        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, 0, c.side2)) return e;   // correlation = flipped templates + shifted store
+        OsProv prov;
+        const OsProv* pp = nullptr;
+        Ctx::SpecCache& sc = c.sc;
+        if (!a.d_raw && a.nimg == 1) {
+            if (!g_capturing && !c.plan_pin && os_env().spec_cache && sc.valid && sc.spec == (const void*)a.d_spec && sc.F == F &&
+                sc.FH == FH && sc.FW == FW) {
+                prov.hsel = (const unsigned long long*)sc.hash.p;
+                prov.alt.ptr = (const float*)sc.raw.p; prov.alt.rows = sc.H; prov.alt.cols = sc.W;
+                prov.alt_done = (sc.b_valid && sc.b_maxkh == maxkh && sc.b_maxkw == maxkw && sc.b_gen == c.osB_gen) ? 1 : 0;
+                pp = &prov;
+            }
+            sc.want = true; sc.w_F = F; sc.w_FH = FH; sc.w_FW = FW; sc.w_maxkh = maxkh; sc.w_maxkw = maxkw;
+        }
+        sc.b_valid = false;                                         // whatever happens next, osB belongs to this call
+        if (int e = os_prepare_data(c, og, a.d_raw ? nullptr : a.d_spec, a.d_raw, a.rawH, a.rawW, 0, c.side2, pp)) return e;   // correlation = flipped templates + shifted store
         CU(cudaEventRecord(c.evf[1], c.side2));
         if (a.bankA) CU(cudaStreamWaitEvent(st, c.evf[1], 0));      // prepared bank: nothing to overlap with
     } else if (tile16) {
@@ -1451,6 +1504,33 @@ static int fft_data_impl(const float* data, int data_on_device, int H, int W, in
         d_data = (const float*)c->ddata.p;
     }
     if (int e = run_fft_data(*c, d_data, H, W, F, FH, FW, pad_mode, kernel_y, kernel_x, (cpx*)d_spec, st)) return e;
+    {   // provenance of this spectrum for the overlap-save path (Ctx::SpecCache)
+        Ctx::SpecCache& sc = c->sc;
+        const size_t raw_bytes = sizeof(float) * (size_t)H * W * F;
+        if (sc.spec == (const void*)d_spec) { sc.valid = false; sc.b_valid = false; }
+        if (pad_mode == PAD_ZERO && !g_capturing && !c->plan_pin && os_env().spec_cache && raw_bytes <= ((size_t)512 << 20)) {
+            sc.valid = false; sc.b_valid = false;
+            if (int e = dev_reserve(sc.raw, raw_bytes)) return e;
+            if (int e = dev_reserve(sc.hash, 2 * sizeof(unsigned long long))) return e;
+            CU(cudaMemcpyAsync(sc.raw.p, d_data, raw_bytes, cudaMemcpyDeviceToDevice, st));
+            CU(cudaMemsetAsync(sc.hash.p, 0, 2 * sizeof(unsigned long long), st));
+            const size_t n = (size_t)F * FW * (FH / 2 + 1);
+            os_hash64<<<os_hash_grid(*c, n), 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_spec), n,
+                                                           (unsigned long long*)sc.hash.p);
+            LAUNCH_CHECK();
+            sc.valid = true; sc.spec = d_spec; sc.H = H; sc.W = W; sc.F = F; sc.FH = FH; sc.FW = FW;
+            // the last convolution fed by a spectrum of this geometry took the overlap-save path: transform the tiles now, on
+            // the data-side stream, next to whatever the caller does until it convolves
+            OsCfg og;
+            if (sc.want && sc.w_F == F && sc.w_FH == FH && sc.w_FW == FW && os_env().spec_cache > 1 &&
+                os_config(F, FH, FW, sc.w_maxkh, sc.w_maxkw, og)) {
+                CU(cudaEventRecord(c->evf[0], st));
+                CU(cudaStreamWaitEvent(c->side2, c->evf[0], 0));
+                if (int e = os_prepare_data(*c, og, nullptr, (const float*)sc.raw.p, H, W, 0, c->side2)) return e;
+                sc.b_valid = true; sc.b_maxkh = sc.w_maxkh; sc.b_maxkw = sc.w_maxkw; sc.b_gen = c->osB_gen;
+            }
+        }
+    }
     if (!data_on_device) CU(cudaStreamSynchronize(st));    // src/cudaFFTData.cu:147
     return 0;
 }

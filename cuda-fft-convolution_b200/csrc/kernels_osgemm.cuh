@@ -369,7 +369,35 @@ struct OsDArgs {
     float* img;
     int NKS, KC, NMMA, NTn;
     int correlate;
+    // provenance of a caller-supplied spectrum (SpecCache in fftconv.cu): hsel[0] = hash of the spectrum when
+    // fftconv_fft_data produced it, hsel[1] = hash of what the caller handed to the convolution.  Equal: the raw data
+    // kept from that call (`alt`) is tiled directly -- or, when the tile spectra were already computed next to the
+    // forward transform (alt_done), nothing is left to do.  Different: `src` (the plane recovered from the spectrum).
+    const unsigned long long* hsel;
+    SrcDesc alt;
+    int alt_done;
 };
+// 64-bit position-sensitive hash of a buffer of 8-byte words (wrapping sum of mixed (index, word) pairs: the order of the
+// additions does not matter, so blocks combine with one atomicAdd each).  *out must be zero before the launch.
+__device__ __forceinline__ unsigned long long os_mix64(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+__global__ void __launch_bounds__(256) os_hash64(const unsigned long long* __restrict__ p, size_t n, unsigned long long* out) {
+    unsigned long long h = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        h += os_mix64(p[i] + 0x9E3779B97F4A7C15ull * (unsigned long long)(2 * i + 1));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    __shared__ unsigned long long part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += part[w];
+        atomicAdd(out, t);
+    }
+}
 constexpr int OS_DRAW = 65;           // raw window column stride (floats)
 constexpr size_t OS_DATA_SMEM = 2 * 64 * OS_DRAW * sizeof(float) + 2 * 33 * OS_IROW * sizeof(cpx);
 
@@ -378,6 +406,11 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     float* raw = reinterpret_cast<float*>(os_smem_raw);                              // [2][64][65]
     cpx* Hs = reinterpret_cast<cpx*>(os_smem_raw + 2 * 64 * OS_DRAW * sizeof(float));   // [2][33][66]
+    SrcDesc src = a.src;
+    if (a.hsel && a.hsel[0] == a.hsel[1]) {                             // CTA-uniform (see OsDArgs)
+        if (a.alt_done) return;
+        src = a.alt;
+    }
     const int npair = a.NKS * a.KC;
     const int m = blockIdx.x / npair, fp = blockIdx.x - m * npair;      // channel pair fastest
     const int img = m / a.NTimg, mt = m - img * a.NTimg;          // tiles of a batch are numbered image-major
@@ -388,10 +421,10 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     {
         const int y = threadIdx.x & 63;
         const int gy = os_wrap(oy + y, a.FH);
-        const bool vy = gy < a.src.rows;
+        const bool vy = gy < src.rows;
         for (int ch = 0; ch < 2; ++ch) {
             const int f = 2 * fp + ch;
-            const float* pl = a.src.ptr + ((size_t)img * a.F + f) * a.src.cols * a.src.rows + gy;
+            const float* pl = src.ptr + ((size_t)img * a.F + f) * src.cols * src.rows + gy;
             float* dst = raw + (size_t)ch * 64 * OS_DRAW + y;
             int gx = os_wrap(ox + (threadIdx.x >> 6), a.FW);
             const bool vf = vy && f < a.F;
@@ -400,7 +433,7 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
                 float v[16];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {                      // 16 independent loads in flight
-                    v[k] = (vf && gx < a.src.cols) ? __ldg(pl + (size_t)gx * a.src.rows) : 0.f;
+                    v[k] = (vf && gx < src.cols) ? __ldg(pl + (size_t)gx * src.rows) : 0.f;
                     gx += 2;
                     if (gx >= a.FW) gx -= a.FW;                     // FW >= 16 > 2: one conditional subtract is enough
                 }
@@ -1591,8 +1624,9 @@ __global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid
 // inv_w_pass: inverse complex FFT along w of the compat spectrum S [plane][FW][CH] -> Z [plane][FW][CH]
 // (first half of spectrum -> plane; inv_h_pass finishes).  grid = (ceil(CH/TU), planes).
 __global__ void inv_w_pass(const cpx* __restrict__ S, int FW, int CH, LinePlan plan, const cpx* __restrict__ tw,
-                           cpx* __restrict__ Z, int TU, int ld)
+                           cpx* __restrict__ Z, int TU, int ld, const unsigned long long* __restrict__ skip_if_equal)
 {
+    if (skip_if_equal && skip_if_equal[0] == skip_if_equal[1]) return;     // (see inv_h_pass)
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     cpx* b0 = reinterpret_cast<cpx*>(os_smem_raw);
     cpx* b1 = b0 + (size_t)TU * ld;
