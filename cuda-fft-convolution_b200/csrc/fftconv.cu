@@ -21,6 +21,7 @@
 #include "kernels_tile16.cuh"
 #include "kernels_osgemm.cuh"
 #include "kernels_bigplane.cuh"
+#include "kernels_bigplane_ct.cuh"
 
 namespace fftconv {
 
@@ -587,9 +588,11 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
 //   FFTCONV_OS_HI_INPLACE 1: rewrite the A stage as tf32(a) in shared memory instead of relying on the operand truncation
 //   FFTCONV_OS_LBO_SWAP   swap the LBO / SBO fields of the shared-memory descriptors
 //   FFTCONV_SPEC_CACHE    0: never reuse the raw data behind a spectrum of fftconv_fft_data (always invert the spectrum);
-//                         1: reuse the raw data; 2 (default): also transform the tiles next to the forward transform
+//                         1 (default): reuse the raw data; 2: also transform the tiles next to the forward transform
+//   FFTCONV_BP_CT         -1: large-plane path on the run-time-plan kernels only; v >= 0 (default 0): variant v of the
+//                         size-specialised kernels where one is instantiated for the line length (kernels_bigplane_ct.cuh)
 //   FFTCONV_OS_PF         L2 prefetch distance of os_gemm's TMA producer in work items (default 0 = off: measured 0.21 -> 0.30 ms at config 2 with 6 items ahead, the prefetched lines fight the P stores for L2)
-struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache; };
+struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache, bp_ct; };
 static const OsEnv& os_env() {
     static const OsEnv e = [] {
         auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
@@ -605,6 +608,7 @@ static const OsEnv& os_env() {
         x.dbg = geti("FFTCONV_OS_DBG", 0);
         x.pf = geti("FFTCONV_OS_PF", 0);
         x.spec_cache = geti("FFTCONV_SPEC_CACHE", 1);
+        x.bp_ct = geti("FFTCONV_BP_CT", 0);
         return x;
     }();
     return e;
@@ -969,6 +973,77 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
 // ------------------------------------------------------------------ large-plane path (kernels_bigplane.cuh), host side
 // In-place plan: odd radices first (their stride is the longest, so a zero-padded template prunes the first stage),
 // then the power of two split into radices 8 / 16 / 32.
+// Size-specialised variants (kernels_bigplane_ct.cuh): X(line length, variant, threads of bp_conv_w_ct, threads of
+// bp_inv_h_ct, radices...).  Variant 0 of a length is the product; further variants are kept for A/B runs (FFTCONV_BP_CT=v).
+// The run-time plan of a listed length is built from the SAME radices, so both kernel families share the digit order.
+#define BP_CT_LIST(X) \
+    X(4608, 0, 576, 288, 9, 32, 16) \
+    X(4608, 1, 512, 256, 9, 32, 16) \
+    X(4608, 2, 576, 288, 9, 16, 32) \
+    X(4608, 3, 768, 384, 9, 8, 8, 8)
+
+struct BpCtEntry { int n, var, ns; int R[BP_MAX_STAGES]; };
+static const BpCtEntry* bp_ct_find(int n) {
+#define BP_CT_ROW(N, V, NTW, NTH, ...) {N, V, (int)(sizeof((int[]){__VA_ARGS__}) / sizeof(int)), {__VA_ARGS__}},
+    static const BpCtEntry tab[] = {BP_CT_LIST(BP_CT_ROW)};
+#undef BP_CT_ROW
+    const int want = os_env().bp_ct;
+    if (want < 0) return nullptr;
+    const BpCtEntry* first = nullptr;
+    for (const BpCtEntry& e : tab) {
+        if (e.n != n) continue;
+        if (e.var == want) return &e;
+        if (e.var == 0) first = &e;
+    }
+    return first;
+}
+
+template <class P, int NT>
+static int bp_ct_conv_w_launch(bool conj, bool multi, int nk, const cpx* T, const int* kcols, int maxcols4, const cpx* Sp, int F,
+                               int CHp, const cpx* tw, cpx* Z, cudaStream_t st) {
+    const dim3 grid(multi ? 2 * nk : nk, CHp / 4);
+    const size_t smem4 = (4 * (size_t)P::template ld<4>() + P::TWN) * sizeof(cpx);
+    const size_t smem2 = (4 * (size_t)P::template ld<2>() + P::TWN) * sizeof(cpx);
+    static_assert((4 * (size_t)P::template ld<4>() + P::TWN) * sizeof(cpx) <= kMaxSmem, "4 lines + twiddles must fit shared memory");
+#define BP_CT_GO(CONJ, MULTI, TU, SM) do { \
+        auto kern = bp_conv_w_ct<P, CONJ, MULTI, NT, TU>; \
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
+        kern<<<grid, NT, SM, st>>>(T, kcols, maxcols4, Sp, F, CHp, tw, Z); } while (0)
+    if (multi) { if (conj) BP_CT_GO(true, true, 2, smem2); else BP_CT_GO(false, true, 2, smem2); }
+    else { if (conj) BP_CT_GO(true, false, 4, smem4); else BP_CT_GO(false, false, 4, smem4); }
+#undef BP_CT_GO
+    return 0;
+}
+template <class P, int NT>
+static int bp_ct_inv_h_launch(int nk, const cpx* Z, int FW, int CH, int CHp, const cpx* tw, const unsigned short* pos_of,
+                              float* const* outs, int crop_h, int crop_w, int out_ld, cudaStream_t st) {
+    const dim3 grid(FW / 4, nk);
+    const size_t smem = (2 * (size_t)P::template ld<2>() + P::TWN) * sizeof(cpx);
+    auto kern = bp_inv_h_ct<P, NT, 2, 2>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, NT, smem, st>>>(Z, FW, CH, CHp, tw, pos_of, outs, crop_h, crop_w, out_ld);
+    return 0;
+}
+// returns -1 when no specialised kernel serves this length
+static int bp_ct_conv_w(const BpCtEntry* e, bool conj, bool multi, int nk, const cpx* T, const int* kcols, int maxcols4,
+                        const cpx* Sp, int F, int CHp, const cpx* tw, cpx* Z, cudaStream_t st) {
+    if (!e) return -1;
+#define BP_CT_CASE(N, V, NTW, NTH, ...) \
+    if (e->n == N && e->var == V) return bp_ct_conv_w_launch<CtPlan<N, __VA_ARGS__>, NTW>(conj, multi, nk, T, kcols, maxcols4, Sp, F, CHp, tw, Z, st);
+    BP_CT_LIST(BP_CT_CASE)
+#undef BP_CT_CASE
+    return -1;
+}
+static int bp_ct_inv_h(const BpCtEntry* e, int nk, const cpx* Z, int FW, int CH, int CHp, const cpx* tw,
+                       const unsigned short* pos_of, float* const* outs, int crop_h, int crop_w, int out_ld, cudaStream_t st) {
+    if (!e) return -1;
+#define BP_CT_CASE(N, V, NTW, NTH, ...) \
+    if (e->n == N && e->var == V) return bp_ct_inv_h_launch<CtPlan<N, __VA_ARGS__>, NTH>(nk, Z, FW, CH, CHp, tw, pos_of, outs, crop_h, crop_w, out_ld, st);
+    BP_CT_LIST(BP_CT_CASE)
+#undef BP_CT_CASE
+    return -1;
+}
+
 static bool make_ip_plan(int n, IpPlan& p) {
     p = IpPlan{};
     p.n = n;
@@ -979,6 +1054,12 @@ static bool make_ip_plan(int n, IpPlan& p) {
         p.R[p.ns] = r; p.L[p.ns] = L; ++p.ns; L /= r;
         return true;
     };
+    if (const BpCtEntry* e = bp_ct_find(n)) {       // a size-specialised variant exists: same radices, same digit order
+        for (int i = 0; i < e->ns; ++i) if (!push(e->R[i])) return false;
+        const int m0 = n / p.R[0];
+        p.magic = m0 >= 32 ? (unsigned)((0x100000000ull + m0 - 1) / m0) : 0u;
+        return L == 1;
+    }
     int o = n, e = 0;
     while ((o & 1) == 0) { o >>= 1; ++e; }        // n = o * 2^e, e >= 4
     const int odd[] = {9, 17, 13, 11, 7, 5, 3};
@@ -1083,7 +1164,10 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
         ProfScope ps(PK_BP_CONV_W, st);
         const cpx* T = (const cpx*)c.T.p; const cpx* Sp = (const cpx*)c.bpS.p; cpx* Z = (cpx*)c.Z.p;
 #define BP_LAUNCH(CONJ, MULTI, TU) bp_conv_w<CONJ, MULTI, 512, TU, 1><<<grid, 512, smem, st>>>(T, d_kcols, maxcols4, Sp, F, FW, CHp, pW, twW, Z, ldW)
-        if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, 2); else BP_LAUNCH(false, true, 2); }
+        const int ct = bp_ct_conv_w(bp_ct_find(FW), a.opt.correlate != 0, multi, nk, T, d_kcols, maxcols4, Sp, F, CHp, twW, Z, st);
+        if (ct > 0) return ct;
+        if (ct == 0) { /* size-specialised kernel launched */ }
+        else if (multi) { if (a.opt.correlate) BP_LAUNCH(true, true, 2); else BP_LAUNCH(false, true, 2); }
         else { if (a.opt.correlate) BP_LAUNCH(true, false, 4); else BP_LAUNCH(false, false, 4); }
 #undef BP_LAUNCH
         LAUNCH_CHECK();
@@ -1094,7 +1178,10 @@ static int conv_bigplane_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc*
         const int out_ld = a.opt.out_ld > 0 ? a.opt.out_ld : crop_h;
         dim3 grid(FW / 4, nk);
         ProfScope ps(PK_BP_INV_H, st);
-        bp_inv_h<2><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
+        const int ct = bp_ct_inv_h(bp_ct_find(FH), nk, (const cpx*)c.Z.p, FW, CH, CHp, twH, posH, d_outptrs, crop_h, crop_w, out_ld, st);
+        if (ct > 0) return ct;
+        if (ct < 0)
+            bp_inv_h<2><<<grid, 256, smemH, st>>>((const cpx*)c.Z.p, FH, FW, CH, CHp, pH, twH, posH, d_outptrs, crop_h, crop_w, out_ld, ldH);
         LAUNCH_CHECK();
     }
     return 0;
