@@ -973,18 +973,22 @@ static int conv_generic_chunk(Ctx& c, const ConvArgs& a, int FH, const SrcDesc* 
 // ------------------------------------------------------------------ large-plane path (kernels_bigplane.cuh), host side
 // In-place plan: odd radices first (their stride is the longest, so a zero-padded template prunes the first stage),
 // then the power of two split into radices 8 / 16 / 32.
-// Size-specialised variants (kernels_bigplane_ct.cuh): X(line length, variant, threads of bp_conv_w_ct, threads of
-// bp_inv_h_ct, radices...).  Variant 0 of a length is the product; further variants are kept for A/B runs (FFTCONV_BP_CT=v).
+// Size-specialised variants (kernels_bigplane_ct.cuh): X(line length, variant, threads and lines per CTA of bp_conv_w_ct,
+// threads and complex lines per CTA of bp_inv_h_ct, FLAGS of both kernels, radices...).  Variant 0 of a length is the product; further variants are kept for A/B runs (FFTCONV_BP_CT=v).
 // The run-time plan of a listed length is built from the SAME radices, so both kernel families share the digit order.
+// Measured at config 3 (4608, 16 templates, B200): run-time plan 2.79 + 1.54 ms (bp_conv_w + bp_inv_h) -> 1.16 + 0.80 ms.
+// Alternatives tried at 4608: radices [9,16,32] 1.62 ms and [9,8,8,8] 1.27 ms against 1.22 ms (bp_conv_w); 512 instead
+// of 576 threads 1.28 ms; 2-line CTAs, two per SM 1.75 ms (half sectors); bp_inv_h with 2 lines x 288 threads, two CTAs per
+// SM 0.88 ms against 0.80 ms (1 line x 160 threads, four per SM); FLAGS 0 -> 7: 1.22 -> 1.16 and 0.91 -> 0.88 ms.
 #define BP_CT_LIST(X) \
-    X(4608, 0, 576, 288, 9, 32, 16) \
-    X(4608, 1, 512, 256, 9, 32, 16) \
-    X(4608, 2, 576, 288, 9, 16, 32) \
-    X(4608, 3, 768, 384, 9, 8, 8, 8)
+    X(1152, 0, 288, 4, 160, 1, 7, 9, 8, 16) \
+    X(2048, 0, 512, 4, 128, 1, 7, 8, 16, 16) \
+    X(4096, 0, 512, 4, 128, 1, 7, 16, 16, 16) \
+    X(4608, 0, 576, 4, 160, 1, 7, 9, 32, 16)
 
 struct BpCtEntry { int n, var, ns; int R[BP_MAX_STAGES]; };
 static const BpCtEntry* bp_ct_find(int n) {
-#define BP_CT_ROW(N, V, NTW, NTH, ...) {N, V, (int)(sizeof((int[]){__VA_ARGS__}) / sizeof(int)), {__VA_ARGS__}},
+#define BP_CT_ROW(N, V, NTW, TUW, NTH, NLH, FL, ...) {N, V, (int)(sizeof((int[]){__VA_ARGS__}) / sizeof(int)), {__VA_ARGS__}},
     static const BpCtEntry tab[] = {BP_CT_LIST(BP_CT_ROW)};
 #undef BP_CT_ROW
     const int want = os_env().bp_ct;
@@ -998,28 +1002,37 @@ static const BpCtEntry* bp_ct_find(int n) {
     return first;
 }
 
-template <class P, int NT>
+template <class P, int NTW, int TUW, int FL>
 static int bp_ct_conv_w_launch(bool conj, bool multi, int nk, const cpx* T, const int* kcols, int maxcols4, const cpx* Sp, int F,
                                int CHp, const cpx* tw, cpx* Z, cudaStream_t st) {
-    const dim3 grid(multi ? 2 * nk : nk, CHp / 4);
-    const size_t smem4 = (4 * (size_t)P::template ld<4>() + P::TWN) * sizeof(cpx);
-    const size_t smem2 = (4 * (size_t)P::template ld<2>() + P::TWN) * sizeof(cpx);
-    static_assert((4 * (size_t)P::template ld<4>() + P::TWN) * sizeof(cpx) <= kMaxSmem, "4 lines + twiddles must fit shared memory");
-#define BP_CT_GO(CONJ, MULTI, TU, SM) do { \
-        auto kern = bp_conv_w_ct<P, CONJ, MULTI, NT, TU>; \
+    // single channel: TUW lines per CTA (4: whole sectors, one CTA per SM; 2: two CTAs per SM, the halves of a sector meet
+    // in L2); several channels: 2 lines + 2 accumulator lines
+    const bool two = multi || TUW == 2;
+    const dim3 grid(two ? 2 * nk : nk, CHp / 4);
+    constexpr size_t smem4 = (4 * (size_t)P::template ld<4>() + P::TWN) * sizeof(cpx);
+    constexpr size_t smem2m = (4 * (size_t)P::template ld<2>() + P::TWN) * sizeof(cpx);
+    constexpr size_t smem2 = (2 * (size_t)P::template ld<2>() + P::TWN) * sizeof(cpx);
+    static_assert(smem4 <= kMaxSmem && smem2m <= kMaxSmem, "4 lines + twiddles must fit shared memory");
+    constexpr int NTM = NTW * 2 / TUW;           // threads of the 2-line multi-channel CTA
+#define BP_CT_GO(CONJ, MULTI, NT, TU, MINB, SM) do { \
+        auto kern = bp_conv_w_ct<P, CONJ, MULTI, NT, TU, MINB, FL>; \
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM))); \
         kern<<<grid, NT, SM, st>>>(T, kcols, maxcols4, Sp, F, CHp, tw, Z); } while (0)
-    if (multi) { if (conj) BP_CT_GO(true, true, 2, smem2); else BP_CT_GO(false, true, 2, smem2); }
-    else { if (conj) BP_CT_GO(true, false, 4, smem4); else BP_CT_GO(false, false, 4, smem4); }
+    if (multi) { if (conj) BP_CT_GO(true, true, NTM, 2, 1, smem2m); else BP_CT_GO(false, true, NTM, 2, 1, smem2m); }
+    else if constexpr (TUW == 2) { if (conj) BP_CT_GO(true, false, NTW, 2, 2, smem2); else BP_CT_GO(false, false, NTW, 2, 2, smem2); }
+    else { if (conj) BP_CT_GO(true, false, NTW, 4, 1, smem4); else BP_CT_GO(false, false, NTW, 4, 1, smem4); }
 #undef BP_CT_GO
     return 0;
 }
-template <class P, int NT>
+template <class P, int NT, int NLH, int FL>
 static int bp_ct_inv_h_launch(int nk, const cpx* Z, int FW, int CH, int CHp, const cpx* tw, const unsigned short* pos_of,
                               float* const* outs, int crop_h, int crop_w, int out_ld, cudaStream_t st) {
-    const dim3 grid(FW / 4, nk);
-    const size_t smem = (2 * (size_t)P::template ld<2>() + P::TWN) * sizeof(cpx);
-    auto kern = bp_inv_h_ct<P, NT, 2, 2>;
+    // NLH complex lines = 2 NLH real columns per CTA; as many CTAs per SM as shared memory holds (their load, transform and
+    // store phases overlap)
+    const dim3 grid(FW / (2 * NLH), nk);
+    constexpr size_t smem = (NLH * (size_t)P::template ld<NLH>() + P::TWN) * sizeof(cpx);
+    constexpr int MINB = (int)(kMaxSmem / (smem + 1024)) > 4 ? 4 : (int)(kMaxSmem / (smem + 1024));
+    auto kern = bp_inv_h_ct<P, NT, NLH, MINB, FL>;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, NT, smem, st>>>(Z, FW, CH, CHp, tw, pos_of, outs, crop_h, crop_w, out_ld);
     return 0;
@@ -1028,8 +1041,8 @@ static int bp_ct_inv_h_launch(int nk, const cpx* Z, int FW, int CH, int CHp, con
 static int bp_ct_conv_w(const BpCtEntry* e, bool conj, bool multi, int nk, const cpx* T, const int* kcols, int maxcols4,
                         const cpx* Sp, int F, int CHp, const cpx* tw, cpx* Z, cudaStream_t st) {
     if (!e) return -1;
-#define BP_CT_CASE(N, V, NTW, NTH, ...) \
-    if (e->n == N && e->var == V) return bp_ct_conv_w_launch<CtPlan<N, __VA_ARGS__>, NTW>(conj, multi, nk, T, kcols, maxcols4, Sp, F, CHp, tw, Z, st);
+#define BP_CT_CASE(N, V, NTW, TUW, NTH, NLH, FL, ...) \
+    if (e->n == N && e->var == V) return bp_ct_conv_w_launch<CtPlan<N, __VA_ARGS__>, NTW, TUW, FL>(conj, multi, nk, T, kcols, maxcols4, Sp, F, CHp, tw, Z, st);
     BP_CT_LIST(BP_CT_CASE)
 #undef BP_CT_CASE
     return -1;
@@ -1037,8 +1050,8 @@ static int bp_ct_conv_w(const BpCtEntry* e, bool conj, bool multi, int nk, const
 static int bp_ct_inv_h(const BpCtEntry* e, int nk, const cpx* Z, int FW, int CH, int CHp, const cpx* tw,
                        const unsigned short* pos_of, float* const* outs, int crop_h, int crop_w, int out_ld, cudaStream_t st) {
     if (!e) return -1;
-#define BP_CT_CASE(N, V, NTW, NTH, ...) \
-    if (e->n == N && e->var == V) return bp_ct_inv_h_launch<CtPlan<N, __VA_ARGS__>, NTH>(nk, Z, FW, CH, CHp, tw, pos_of, outs, crop_h, crop_w, out_ld, st);
+#define BP_CT_CASE(N, V, NTW, TUW, NTH, NLH, FL, ...) \
+    if (e->n == N && e->var == V) return bp_ct_inv_h_launch<CtPlan<N, __VA_ARGS__>, NTH, NLH, FL>(nk, Z, FW, CH, CHp, tw, pos_of, outs, crop_h, crop_w, out_ld, st);
     BP_CT_LIST(BP_CT_CASE)
 #undef BP_CT_CASE
     return -1;

@@ -54,6 +54,13 @@ __host__ __device__ constexpr int ct_off(int r) {
     return r * m + (L % 16 == 0 ? ((r * m) >> 4) : 0) + (S == 0 ? r : 0);
 }
 
+// position of natural index v in the digit-reversed order the forward stages leave (the pos_of table, in arithmetic)
+template <class P, int S = 0>
+__device__ __forceinline__ int ct_pos(int v) {
+    if constexpr (S == P::NS - 1) return v;
+    else { const int q = v % P::R(S); return q * P::M(S) + ct_pos<P, S + 1>(v / P::R(S)); }
+}
+
 // rotations w_L^(j q), q = 1..R-1, as R/4 + 2 table reads (two-level split q = 4a + b) for R >= 16
 template <int R, bool INV, class Fetch>
 struct CtTw {
@@ -72,10 +79,30 @@ struct CtTw {
     }
 };
 
+// Rotations of the stride-M0 stage, w_N^(j q), q = 1..R-1, from TWO reads of the global table (w^j and w^4j) and products
+// of depth <= 2 (rounding error <= 3 ulp of the table entries): this stage used to issue R - 1 scattered loads per butterfly,
+// the top long-scoreboard stall of the pass.  R <= 9.
+template <int R, bool INV>
+struct CtTw0 {
+    cpx w[R];
+    __device__ __forceinline__ void load(const cpx* __restrict__ tw, int j) {
+        static_assert(R <= 9, "power chain is laid out for R <= 9");
+        w[1] = twd<INV>(__ldg(&tw[j]));
+        if (R > 2) w[2] = cmul(w[1], w[1]);
+        if (R > 3) w[3] = cmul(w[2], w[1]);
+        if (R > 4) w[4] = twd<INV>(__ldg(&tw[4 * j]));
+        if (R > 5) w[5] = cmul(w[4], w[1]);
+        if (R > 6) w[6] = cmul(w[4], w[2]);
+        if (R > 7) w[7] = cmul(w[4], w[3]);
+        if (R > 8) w[8] = cmul(w[4], w[4]);
+    }
+    __device__ __forceinline__ cpx apply(cpx v, int r) const { return r == 0 ? v : cmul(v, w[r]); }
+};
+
 // One in-place stage over NL lines.  Item = (butterfly b, line l) with the LINE fastest: the lanes of a warp hold the
 // same butterfly of 4 neighbouring lines x 8 neighbouring butterflies (conflict-free 64-bit accesses with LD == 4 mod 16).
 //   forward (DIF):  DFT_R, then output q rotated by w_L^(j q)        inverse (DIT): the exact inverse
-template <class P, int S, bool INV, int NL, int NT>
+template <class P, int S, bool INV, int NL, int NT, bool CHAIN = false>
 __device__ __forceinline__ void ct_stage(cpx* __restrict__ lines, const cpx* __restrict__ twg, const cpx* __restrict__ twsh) {
     constexpr int R = P::R(S), L = P::L(S), m = P::M(S), nb = P::N / R, LDL = P::template ld<NL>();
     constexpr bool rot = m > 1;
@@ -87,8 +114,9 @@ __device__ __forceinline__ void ct_stage(cpx* __restrict__ lines, const cpx* __r
             if constexpr (S == 0) return __ldg(&twg[j * q]);             // w_N^(j q): global table (L1-resident)
             else { const int t = j * q * (P::M0 / L); return twsh[t + (t >> 4)]; }   // w_L^(j q) = w_M0^(j q M0/L): shared table
         };
-        CtTw<R, INV, decltype(fetch)> tw;
-        if (rot) tw.load(fetch);
+        std::conditional_t<(CHAIN && S == 0 && R <= 9), CtTw0<R, INV>, CtTw<R, INV, decltype(fetch)>> tw;
+        if constexpr (CHAIN && S == 0 && R <= 9) tw.load(twg, j);
+        else if (rot) tw.load(fetch);
         float re[R], im[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
@@ -131,8 +159,9 @@ __device__ __forceinline__ void ct_fill_tw(cpx* tab, const cpx* __restrict__ tw)
 
 // ------------------------------------------------------------------------------- bp_conv_w_ct
 // grid (TU == 4: nk, CHp / 4 | TU == 2: 2 nk, CHp / 4), NT threads, one CTA per SM.  Same tile ownership as bp_conv_w.
-template <class P, bool CONJ, bool MULTI, int NT, int TU>
-__global__ void __launch_bounds__(NT, 1) bp_conv_w_ct(const cpx* __restrict__ T, const int* __restrict__ kcols, int maxcols4,
+// FLAGS: 1 = first-stage rotations by power chain (CtTw0), 2 = all global loads of a pass issued before its first use
+template <class P, bool CONJ, bool MULTI, int NT, int TU, int MINB, int FLAGS>
+__global__ void __launch_bounds__(NT, MINB) bp_conv_w_ct(const cpx* __restrict__ T, const int* __restrict__ kcols, int maxcols4,
                                                       const cpx* __restrict__ Sp, int F, int CHp,
                                                       const cpx* __restrict__ tw, cpx* __restrict__ Z)
 {
@@ -156,19 +185,27 @@ __global__ void __launch_bounds__(NT, 1) bp_conv_w_ct(const cpx* __restrict__ T,
         const cpx* Tp = T + ((size_t)(k * F + f) * maxcols4) * CHp + u0 + l;
         if (ncols <= M0) {
             // pass A: only the first M0 samples can be non-zero -> DFT_R0 of (x, 0, ..., 0) = broadcast, rotated by w_N^(j q)
-            for (int jb = p0; jb < M0; jb += 2 * PS) {
-                cpx x[2];
+            constexpr int NA = (FLAGS & 2) ? (M0 + PS - 1) / PS : 2;
+            for (int jb = p0; jb < M0; jb += NA * PS) {
+                cpx x[NA];
 #pragma unroll
-                for (int b = 0; b < 2; ++b) x[b] = __ldcs(&Tp[(size_t)min(jb + b * PS, ncols - 1) * CHp]);
+                for (int b = 0; b < NA; ++b) x[b] = __ldcs(&Tp[(size_t)min(jb + b * PS, ncols - 1) * CHp]);
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < NA; ++b) {
                     const int j = jb + b * PS;
                     if (j < M0) {
                         const cpx v = j < ncols ? x[b] : make_float2(0.f, 0.f);
                         cpx* p = ln + P::pidx(j);
                         p[0] = v;
+                        if constexpr ((FLAGS & 1) && R0 <= 9) {
+                            CtTw0<R0, false> t;
+                            t.load(tw, j);
 #pragma unroll
-                        for (int q = 1; q < R0; ++q) p[ct_off<P, 0>(q)] = cmul(v, __ldg(&tw[j * q]));
+                            for (int q = 1; q < R0; ++q) p[ct_off<P, 0>(q)] = t.apply(v, q);
+                        } else {
+#pragma unroll
+                            for (int q = 1; q < R0; ++q) p[ct_off<P, 0>(q)] = cmul(v, __ldg(&tw[j * q]));
+                        }
                     }
                 }
             }
@@ -176,7 +213,7 @@ __global__ void __launch_bounds__(NT, 1) bp_conv_w_ct(const cpx* __restrict__ T,
         } else {
             for (int x = p0; x < FW; x += PS) ln[P::pidx(x)] = x < ncols ? __ldcs(&Tp[(size_t)x * CHp]) : make_float2(0.f, 0.f);
             __syncthreads();
-            ct_stage<P, 0, false, TU, NT>(lines, tw, twtab);
+            ct_stage<P, 0, false, TU, NT, (FLAGS & 1) != 0>(lines, tw, twtab);
             __syncthreads();
         }
         // pass B
@@ -184,27 +221,38 @@ __global__ void __launch_bounds__(NT, 1) bp_conv_w_ct(const cpx* __restrict__ T,
         // pass C: forward DFT_RL, product with the data spectrum (rows already in digit-reversed order), channel sum,
         // and -- on the last channel -- the inverse DFT_RL
         const cpx* Sf = Sp + (size_t)f * FW * CHp + u0 + l;
-        for (int b = p0; b < FW / RL; b += PS) {
-            cpx* p = ln + P::pidx(b * RL);
-            cpx* pa = p + TU * LDL;
-            cpx d[RL];
+        constexpr int NC = (FLAGS & 2) ? (FW / RL + PS - 1) / PS : 1;
+        for (int bb = p0; bb < FW / RL; bb += NC * PS) {
+            cpx d[NC][RL];
 #pragma unroll
-            for (int r = 0; r < RL; ++r) d[r] = __ldcs(&Sf[(size_t)(b * RL + r) * CHp]);
-            float re[RL], im[RL];
+            for (int i = 0; i < NC; ++i) {
+                const int b = min(bb + i * PS, FW / RL - 1);
 #pragma unroll
-            for (int r = 0; r < RL; ++r) { const cpx v = p[ct_off<P, NS - 1>(r)]; re[r] = v.x; im[r] = v.y; }
-            dft_regs<RL, false>(re, im);
-#pragma unroll
-            for (int r = 0; r < RL; ++r) {
-                const cpx kx = make_float2(re[r], im[r]);
-                cpx pr = CONJ ? cmulc(d[r], kx) : cmul(d[r], kx);
-                if (MULTI && f > 0) { const cpx a = pa[ct_off<P, NS - 1>(r)]; pr.x += a.x; pr.y += a.y; }
-                re[r] = pr.x; im[r] = pr.y;
+                for (int r = 0; r < RL; ++r) d[i][r] = __ldcs(&Sf[(size_t)(b * RL + r) * CHp]);
             }
-            if (!MULTI || f == F - 1) dft_regs<RL, true>(re, im);
-            cpx* po = MULTI ? pa : p;
 #pragma unroll
-            for (int r = 0; r < RL; ++r) po[ct_off<P, NS - 1>(r)] = make_float2(re[r], im[r]);
+            for (int i = 0; i < NC; ++i) {
+                const int b = bb + i * PS;
+                if (b < FW / RL) {
+                    cpx* p = ln + P::pidx(b * RL);
+                    cpx* pa = p + TU * LDL;
+                    float re[RL], im[RL];
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) { const cpx v = p[ct_off<P, NS - 1>(r)]; re[r] = v.x; im[r] = v.y; }
+                    dft_regs<RL, false>(re, im);
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) {
+                        const cpx kx = make_float2(re[r], im[r]);
+                        cpx pr = CONJ ? cmulc(d[i][r], kx) : cmul(d[i][r], kx);
+                        if (MULTI && f > 0) { const cpx a = pa[ct_off<P, NS - 1>(r)]; pr.x += a.x; pr.y += a.y; }
+                        re[r] = pr.x; im[r] = pr.y;
+                    }
+                    if (!MULTI || f == F - 1) dft_regs<RL, true>(re, im);
+                    cpx* po = MULTI ? pa : p;
+#pragma unroll
+                    for (int r = 0; r < RL; ++r) po[ct_off<P, NS - 1>(r)] = make_float2(re[r], im[r]);
+                }
+            }
         }
         __syncthreads();
     }
@@ -220,8 +268,8 @@ __global__ void __launch_bounds__(NT, 1) bp_conv_w_ct(const cpx* __restrict__ T,
         for (int j = p0; j < m; j += PS) {
             const cpx* p = rl + P::pidx(j);
             auto fetch = [&](int q) -> cpx { return __ldg(&tw[j * q]); };
-            CtTw<R0, true, decltype(fetch)> t;
-            t.load(fetch);
+            std::conditional_t<((FLAGS & 1) && R0 <= 9), CtTw0<R0, true>, CtTw<R0, true, decltype(fetch)>> t;
+            if constexpr ((FLAGS & 1) && R0 <= 9) t.load(tw, j); else t.load(fetch);
             float re[R0], im[R0];
 #pragma unroll
             for (int r = 0; r < R0; ++r) { const cpx v = t.apply(p[ct_off<P, 0>(r)], r); re[r] = v.x; im[r] = v.y; }
@@ -234,7 +282,8 @@ __global__ void __launch_bounds__(NT, 1) bp_conv_w_ct(const cpx* __restrict__ T,
 
 // ------------------------------------------------------------------------------- bp_inv_h_ct
 // grid (FW / (2 NLN), nk) x NT; Z [k][FW][CHp] (already scaled) -> 2 NLN real columns of plane k (NLN complex lines)
-template <class P, int NT, int NLN, int MINB>
+// FLAGS: 1 = first-stage rotations by power chain, 4 = digit-reversed positions in arithmetic instead of the pos_of table
+template <class P, int NT, int NLN, int MINB, int FLAGS>
 __global__ void __launch_bounds__(NT, MINB) bp_inv_h_ct(const cpx* __restrict__ Z, int FW, int CH, int CHp,
                                                         const cpx* __restrict__ tw, const unsigned short* __restrict__ pos_of,
                                                         float* const* __restrict__ outs, int crop_h, int crop_w, int out_ld)
@@ -261,7 +310,9 @@ __global__ void __launch_bounds__(NT, MINB) bp_inv_h_ct(const cpx* __restrict__ 
 #pragma unroll
             for (int b = 0; b < MB; ++b) {
                 const int uc = min(ub + b * NT, CH - 1);
-                za[b] = __ldcs(&Za[uc]); zb[b] = __ldcs(&Zb[uc]); pa[b] = pos_of[uc]; pb[b] = pos_of[uc == 0 ? 0 : FH - uc];
+                za[b] = __ldcs(&Za[uc]); zb[b] = __ldcs(&Zb[uc]);
+                if constexpr (FLAGS & 4) { pa[b] = ct_pos<P>(uc); pb[b] = ct_pos<P>(uc == 0 ? 0 : FH - uc); }
+                else { pa[b] = pos_of[uc]; pb[b] = pos_of[uc == 0 ? 0 : FH - uc]; }
             }
 #pragma unroll
             for (int b = 0; b < MB; ++b) {
@@ -286,8 +337,8 @@ __global__ void __launch_bounds__(NT, MINB) bp_inv_h_ct(const cpx* __restrict__ 
             const int l = it / M0, j = it - l * M0;
             const cpx* p = lines + l * LDL + P::pidx(j);
             auto fetch = [&](int q) -> cpx { return __ldg(&tw[j * q]); };
-            CtTw<R0, true, decltype(fetch)> t;
-            t.load(fetch);
+            std::conditional_t<((FLAGS & 1) && R0 <= 9), CtTw0<R0, true>, CtTw<R0, true, decltype(fetch)>> t;
+            if constexpr ((FLAGS & 1) && R0 <= 9) t.load(tw, j); else t.load(fetch);
             float re[R0], im[R0];
 #pragma unroll
             for (int r = 0; r < R0; ++r) { const cpx v = t.apply(p[ct_off<P, 0>(r)], r); re[r] = v.x; im[r] = v.y; }

@@ -281,6 +281,41 @@ def test_bigplane_c3_scaled_auto_and_device_outputs(fc, oracle):
         assert not np.array_equal(o, g)          # really a different pipeline
 
 
+@pytest.mark.parametrize("FH,FW,F,kh,kw,opts", [
+    (64, 1152, 1, 5, 20, {}),                          # size-specialised w pass (pruned first stage), run-time h passes
+    (64, 1152, 3, 5, 200, dict(correlate=1)),          # ... channel sum, template wider than the first-stage stride
+    (1152, 48, 2, 30, 7, dict(crop_h=1000, crop_w=40)),  # size-specialised C2R along h, cropped store
+    (1152, 1152, 1, 128, 128, dict(correlate=1)),
+    (2048, 2048, 1, 49, 30, {}),
+    (4096, 2048, 2, 300, 17, {}),
+])
+def test_bigplane_size_specialised_kernels(fc, oracle, FH, FW, F, kh, kw, opts):
+    """kernels_bigplane_ct.cuh: the line lengths with a compile-time plan (1152, 2048, 4096, 4608 -- the last one is covered
+    at full size by test_c3_full_size_large_plane) against the generic pipeline and the float64 FFT convolution."""
+    import scipy.fft as sfft
+    rng = np.random.default_rng(FH + FW + F)
+    H, W = FH - kh + 1 - 3, FW - kw + 1 - 2
+    assert fc.computeFFTsize16(H + kh - 1) == FH and fc.computeFFTsize16(W + kw - 1) == FW
+    data = rng.random((H, W, F), dtype=np.float32)
+    ks = [(rng.standard_normal((kh, kw, F)) / kh).astype(np.float32),
+          (rng.standard_normal((max(1, kh - 2), max(1, kw // 2), F)) / kh).astype(np.float32)]
+    a = fc.cudaConvolutionFFT(data, kh, kw, ks, options=fc.Options(path=4, **opts))
+    b = fc.cudaConvolutionFFT(data, kh, kw, ks, options=fc.Options(path=1, **opts))
+    for x, y in zip(a, b):
+        assert x.shape == y.shape
+        if "crop_h" in opts:
+            ch, cw = opts["crop_h"], opts["crop_w"]
+            x = x.T.reshape(-1)[: cw * ch].reshape(cw, ch)
+            y = y.T.reshape(-1)[: cw * ch].reshape(cw, ch)
+        assert oracle.rel_l2(x, y) < TOL
+        assert not np.array_equal(x, y)
+    if not opts:
+        D = sfft.rfft2(data.astype(np.float64).transpose(2, 0, 1), s=(FH, FW), workers=-1)
+        for k, o in zip(ks, a):
+            ref = sfft.irfft2(D * sfft.rfft2(k.astype(np.float64).transpose(2, 0, 1), s=(FH, FW), workers=-1), s=(FH, FW), workers=-1).sum(0)
+            assert oracle.rel_l2(o, ref) < TOL
+
+
 @pytest.mark.parametrize("shape", ["c1", "os", "big_template"])
 def test_graph_plan_replays_the_whole_schedule(fc, oracle, shape):
     """fftconv_plan_*: data transform + bank convolution captured into one CUDA graph (the persistent schedule that
