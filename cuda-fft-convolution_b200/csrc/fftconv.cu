@@ -545,8 +545,11 @@ struct OsCfg {
     int nsta;                     // A ring depth
     size_t gemm_smem, inv_smem;
     size_t a_stage, b_buf, p_blk; // bytes
+    const OsLevel* d_levels = nullptr;   // pyramid batch (fftconv_conv_pyramid): per-level geometry on the device
+    int nlevels = 0;
 };
 
+static bool os_config_tiles(OsCfg& g);
 static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int nimg = 1) {
     g = OsCfg{};
     if (maxkh > 32 || maxkw > 32 || maxkh < 1 || maxkw < 1) return false;
@@ -557,6 +560,11 @@ static bool os_config(int F, int FH, int FW, int maxkh, int maxkw, OsCfg& g, int
     g.nth = (FH + g.Sh - 1) / g.Sh; g.ntw = (FW + g.Sw - 1) / g.Sw;
     g.nimg = nimg; g.NTimg = g.nth * g.ntw;
     g.NT = g.nimg * g.NTimg;
+    return os_config_tiles(g);
+}
+// everything that follows from the NUMBER of tiles (the GEMM does not care where a tile comes from)
+static bool os_config_tiles(OsCfg& g) {
+    const int F = g.F;
     g.NKS = (2 * F + 31) / 32;
     const int units = (2 * F + 3) / 4;
     g.KC = ((units + g.NKS - 1) / g.NKS + 1) & ~1;
@@ -800,6 +808,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
     }
     {
         OsInvArgs a{};
+        a.levels = g.d_levels; a.nlevels = g.nlevels;
         a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS;
         a.NT = g.NT; a.NTimg = g.NTimg; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
@@ -834,11 +843,13 @@ static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStr
             const unsigned grid = (unsigned)(persist ? std::min<long long>(nitems, 3LL * c.sm_count) : nitems);
             os_inverse_z<<<grid, 256, OS_IZ_SMEM, st>>>(a, tm8, tm1, (int)nitems);
         } else {
+            if (a.levels) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch: the zone inverse (os_inverse_z) is not available");
             const dim3 g1(g.NNB * (g.RS / 8), nk);
             if (use_z == 0 && os_env().dbg & 128) os_inverse_tma<0><<<g1, 256, OS_ITMA_SMEM, st>>>(a, tm);
             else os_inverse_tma<6><<<g1, 256, OS_ITMA_SMEM, st>>>(a, tm);
         }
     } else {
+        if (a.levels) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch: no tensor maps on this driver");
         dim3 grid((g.NT + OS_IG - 1) / OS_IG, nk);
         os_inverse<<<grid, OS_IG * 64, g.inv_smem, st>>>(a);
     }
@@ -1827,6 +1838,195 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
         if (int e = conv_impl(nullptr, CH, FW, F, K, kernels, kh, kw, kf, kernel_on_device, outs + (size_t)n0 * K, 1,
                               nullptr, 0, opt, device, stream, &raw))
             return e;
+    }
+    return 0;
+}
+
+// ---- feature pyramid x one bank in one call (BASELINE config 5).  The levels differ in size, the templates do not: the
+// tiles of ALL levels go through the per-bin GEMM as one N dimension (level-major tile numbering, OsLevel table), so the
+// template spectra are computed ONCE and the A operand images are read once per template block instead of once per level,
+// and a template chunk costs one GEMM launch and one inverse launch instead of one per level.
+struct PyrLevel { const float* d_raw; const cpx* d_spec; int H, W, FH, FW; };
+
+static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh, int maxkw, int K, const KernelRef* kernels,
+                            float* const* outs, const fftconv_options& opt, cudaStream_t st) {
+    OsCfg og;
+    if (!os_config(F, 64, 64, maxkh, maxkw, og)) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch needs templates of at most 32 x 32");
+    std::vector<OsLevel> hl((size_t)L);
+    int NT = 0;
+    size_t plane_floats_total = 0, z_max = 0;
+    int nspec_planes = 0;
+    for (int l = 0; l < L; ++l) {
+        OsLevel& o = hl[(size_t)l];
+        o.FH = lv[l].FH; o.FW = lv[l].FW;
+        o.nth = (o.FH + og.Sh - 1) / og.Sh;
+        const int ntw = (o.FW + og.Sw - 1) / og.Sw;
+        o.m0 = NT; NT += o.nth * ntw;
+        o.crop_h = o.FH; o.crop_w = o.FW; o.out_ld = o.FH;
+        if (lv[l].d_raw) { o.src = lv[l].d_raw; o.rows = lv[l].H; o.cols = lv[l].W; }
+        else {
+            o.src = nullptr; o.rows = o.FH; o.cols = o.FW;             // plane recovered from the spectrum (below)
+            plane_floats_total += (size_t)F * o.FW * o.FH;
+            z_max = std::max(z_max, (size_t)F * o.FW * (o.FH / 2 + 1));
+            nspec_planes += F;
+        }
+    }
+    og.FH = 0; og.FW = 0; og.nimg = L; og.nth = 1; og.ntw = 1; og.NT = NT; og.NTimg = NT;
+    if (!os_config_tiles(og)) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch outside the range of the overlap-save path");
+
+    // ---- descriptor tables: [OsLevel L][SrcDesc K][float* L*K][int2 K][float* nspec_planes], one staged copy
+    const size_t NO = (size_t)L * K;
+    const size_t off_desc = (sizeof(OsLevel) * (size_t)L + 15) & ~(size_t)15;
+    const size_t off_outp = off_desc + sizeof(SrcDesc) * (size_t)K;
+    const size_t off_khw = off_outp + sizeof(float*) * NO;
+    const size_t off_pl = (off_khw + sizeof(int2) * (size_t)K + 15) & ~(size_t)15;
+    const size_t desc_bytes = off_pl + sizeof(float*) * (size_t)nspec_planes + 64;
+    if (int e = dev_reserve(c.desc, desc_bytes)) return e;
+    size_t host_kernel_bytes = 0;
+    for (int k = 0; k < K; ++k)
+        if (!kernels[k].on_device) host_kernel_bytes += sizeof(float) * (size_t)kernels[k].kh * kernels[k].kw * F;
+    if (host_kernel_bytes) if (int e = dev_reserve(c.stage, host_kernel_bytes)) return e;
+    if (plane_floats_total) {
+        if (int e = dev_reserve(c.osPlane, sizeof(float) * plane_floats_total)) return e;
+        if (int e = dev_reserve(c.osZ, sizeof(cpx) * z_max)) return e;
+    }
+    if (int e = dev_reserve(c.osB, (size_t)og.NNB * OS_NBIN * og.b_buf)) return e;
+    const int KC = std::min(K, os_max_chunk(og, true));
+    if (int e = os_reserve_chunk(c, og, KC, true)) return e;
+
+    char* h_tab;
+    if (int e = pinned_get(c, desc_bytes, (void**)&h_tab)) return e;
+    char* d_tab = reinterpret_cast<char*>(c.desc.p);
+    OsLevel* h_lv = reinterpret_cast<OsLevel*>(h_tab);
+    SrcDesc* h_desc = reinterpret_cast<SrcDesc*>(h_tab + off_desc);
+    float** h_outp = reinterpret_cast<float**>(h_tab + off_outp);
+    int2* h_khw = reinterpret_cast<int2*>(h_tab + off_khw);
+    float** h_pl = reinterpret_cast<float**>(h_tab + off_pl);
+    float* plane = reinterpret_cast<float*>(c.osPlane.p);
+    std::vector<float*> level_plane((size_t)L, nullptr);
+    {
+        size_t po = 0; int pi = 0;
+        for (int l = 0; l < L; ++l) {
+            if (!lv[l].d_raw) {
+                level_plane[(size_t)l] = plane + po;
+                hl[(size_t)l].src = plane + po;
+                for (int f = 0; f < F; ++f) h_pl[pi++] = plane + po + (size_t)f * hl[(size_t)l].FW * hl[(size_t)l].FH;
+                po += (size_t)F * hl[(size_t)l].FW * hl[(size_t)l].FH;
+            }
+            h_lv[l] = hl[(size_t)l];
+        }
+    }
+    size_t so = 0;
+    for (int k = 0; k < K; ++k) {
+        const size_t b = kernels[k].on_device ? 0 : sizeof(float) * (size_t)kernels[k].kh * kernels[k].kw * F;
+        h_desc[k].ptr = kernels[k].on_device ? kernels[k].ptr : reinterpret_cast<const float*>(reinterpret_cast<char*>(c.stage.p) + so);
+        h_desc[k].rows = kernels[k].kh; h_desc[k].cols = kernels[k].kw;
+        h_khw[k] = make_int2(kernels[k].kh, kernels[k].kw);
+        if (b) CU(cudaMemcpyAsync(reinterpret_cast<char*>(c.stage.p) + so, kernels[k].ptr, b, cudaMemcpyHostToDevice, st));
+        so += b;
+    }
+    for (size_t i = 0; i < NO; ++i) h_outp[i] = outs[i];
+    CU(cudaMemcpyAsync(d_tab, h_tab, desc_bytes, cudaMemcpyHostToDevice, st));
+    if (int e = pinned_done(c, st)) return e;
+    og.d_levels = reinterpret_cast<const OsLevel*>(d_tab);
+    og.nlevels = L;
+
+    // ---- data side: spectrum -> plane for the levels that arrive as cudaFFTData spectra, then one tiling launch
+    {
+        float** d_pl = reinterpret_cast<float**>(d_tab + off_pl);
+        int pi = 0;
+        for (int l = 0; l < L; ++l) {
+            if (lv[l].d_raw) continue;
+            const int FH = lv[l].FH, FW = lv[l].FW, CH = FH / 2 + 1;
+            const cpx *twH, *twW;
+            if (int e = get_twiddles(c, FH, st, &twH)) return e;
+            if (int e = get_twiddles(c, FW, st, &twW)) return e;
+            const LinePlan pH = make_line_plan(FH), pW = make_line_plan(FW);
+            const int ldH = odd_ld(FH), ldW = odd_ld(FW);
+            ProfScope ps(PK_OS_PLANE, st);
+            int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
+            TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
+            dim3 g2((CH + TU - 1) / TU, F);
+            inv_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>(lv[l].d_spec, FW, CH, pW, twW, (cpx*)c.osZ.p, TU, ldW, nullptr);
+            LAUNCH_CHECK();
+            const int NL = pick_lines(FH, 8);
+            const long long nlines = (long long)F * (FW / 2);
+            inv_h_pass<<<(unsigned)((nlines + NL - 1) / NL), 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
+                (const cpx*)c.osZ.p, F, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_pl + pi, FH, FW, FH, NL, ldH, nullptr);
+            LAUNCH_CHECK();
+            pi += F;
+        }
+        OsDArgs a{};
+        a.levels = og.d_levels; a.nlevels = L;
+        a.F = F; a.nth = 1; a.NTimg = NT; a.Sh = og.Sh; a.Sw = og.Sw; a.oy0 = maxkh - 1; a.ox0 = maxkw - 1;
+        a.FH = 64; a.FW = 64; a.img = (float*)c.osB.p; a.NKS = og.NKS; a.KC = og.KC; a.NMMA = og.NMMA; a.NTn = og.NTn;
+        a.correlate = 0;
+        c.sc.b_valid = false; ++c.osB_gen;                             // the B images now belong to this call
+        const unsigned grid = (unsigned)NT * (unsigned)(og.NKS * og.KC);
+        ProfScope ps(PK_OS_DATA, st);
+        os_data_fft<<<grid, 128, OS_DATA_SMEM, st>>>(a);
+        LAUNCH_CHECK();
+    }
+    // ---- template chunks
+    const SrcDesc* d_desc = reinterpret_cast<const SrcDesc*>(d_tab + off_desc);
+    float* const* d_outp = reinterpret_cast<float* const*>(d_tab + off_outp);
+    const int2* d_khw = reinterpret_cast<const int2*>(d_tab + off_khw);
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        const int nk = std::min(KC, K - k0);
+        if (int e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, opt, st, K, nullptr, nullptr, d_khw + k0, 0, 0, nullptr, nullptr, 0))
+            return e;
+    }
+    return 0;
+}
+
+int fftconv_conv_pyramid(int L, const float* const* level_data, const fftconv_float2* const* level_spec, const int* H,
+                         const int* W, int F, int maxKH, int maxKW, int K, const float* const* kernels, const int* kh,
+                         const int* kw, const int* kf, const unsigned char* kernel_on_device, float* const* outs,
+                         const fftconv_options* opt, int device, void* stream) {
+    g_err.clear();
+    if (L <= 0 || L > OS_MAX_LEVELS || !H || !W || F <= 0 || maxKH <= 0 || maxKW <= 0 || (!level_data && !level_spec))
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
+    if (K > 0 && (!kernels || !kh || !kw || !outs)) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    if (K == 0) return 0;
+    const fftconv_options o = opt ? *opt : fftconv_options{};
+    std::vector<PyrLevel> lv((size_t)L);
+    int minFH = 1 << 30, minFW = 1 << 30;
+    for (int l = 0; l < L; ++l) {
+        PyrLevel& p = lv[(size_t)l];
+        p.d_raw = level_data ? level_data[l] : nullptr;
+        p.d_spec = (!p.d_raw && level_spec) ? (const cpx*)level_spec[l] : nullptr;
+        if ((!p.d_raw && !p.d_spec) || H[l] <= 0 || W[l] <= 0) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
+        p.H = H[l]; p.W = W[l];
+        p.FH = fftconv_fft_size16(H[l] + maxKH - 1); p.FW = fftconv_fft_size16(W[l] + maxKW - 1);   // src/cudaFFTData.cu:109-112
+        minFH = std::min(minFH, p.FH); minFW = std::min(minFW, p.FW);
+    }
+    for (size_t i = 0; i < (size_t)L * K; ++i)
+        if (!outs[i]) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
+    std::vector<KernelRef> refs;
+    if (int e = build_kernel_refs(K, kernels, kh, kw, kf, kernel_on_device, F, minFH, minFW, refs)) return e;
+    int maxkh = 1, maxkw = 1;
+    for (int k = 0; k < K; ++k) { maxkh = std::max(maxkh, refs[k].kh); maxkw = std::max(maxkw, refs[k].kw); }
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    OsCfg g1;
+    // the tiles must reproduce the planes the declared maxKernel sizes imply: an actual template larger than the declared
+    // maximum wraps around the plane and is left to the per-level calls
+    const bool batched = !o.correlate && !o.force_generic && (o.path == PATH_AUTO || o.path == PATH_OSGEMM) &&
+                         o.crop_h <= 0 && o.crop_w <= 0 && o.out_ld <= 0 && maxkh <= maxKH && maxkw <= maxKW &&
+                         os_config(F, 64, 64, maxkh, maxkw, g1);
+    if (batched) {
+        const int e = run_conv_pyramid(*cs.c, L, lv.data(), F, maxkh, maxkw, K, refs.data(), outs, o, (cudaStream_t)stream);
+        if (e != FFTCONV_ERR_UNSUPPORTED) return e;
+        g_err.clear();
+    }
+    for (int l = 0; l < L; ++l) {                   // level by level through the single-image entry points
+        const PyrLevel& p = lv[(size_t)l];
+        int e;
+        if (p.d_raw) e = fftconv_convolution_fft(p.d_raw, 1, p.H, p.W, F, maxKH, maxKW, K, kernels, kh, kw, kf, kernel_on_device,
+                                                 outs + (size_t)l * K, 1, nullptr, 0, opt, device, stream);
+        else e = conv_impl((const fftconv_float2*)p.d_spec, p.FH / 2 + 1, p.FW, F, K, kernels, kh, kw, kf, kernel_on_device,
+                           outs + (size_t)l * K, 1, nullptr, 0, opt, device, stream);
+        if (e) return e;
     }
     return 0;
 }

@@ -363,7 +363,26 @@ __global__ void __launch_bounds__(256, 2) os_kern_fft(OsKArgs a)
 // FH x FW), transformed along h (two real columns per complex sequence, two threads per line) and along w
 // in shared memory, split hi/lo and stored as the (re-row, im-row) pair of the tile in the B image.
 // grid = NT * NKS*KC (channel pair fastest), 128 threads.  NT = images * tiles per image (batched calls: the images only add tiles).
+// Per-level geometry of a PYRAMID batch (fftconv_conv_pyramid): the levels of a feature pyramid differ in size, so the
+// "images" of the batch no longer share one tile grid.  Tiles are numbered level-major; level l owns tiles
+// m0 .. m0 + nth*ntw - 1.  With a table the uniform fields (NTimg, nth, FH, FW, crop, out_ld, src) are ignored.
+struct OsLevel {
+    const float* src;       // [F][cols][rows] on the device (raw level, or the plane recovered from its spectrum)
+    int rows, cols;
+    int FH, FW;             // plane of the level (computeFFTsize16 of size + maxK - 1)
+    int nth, m0;            // tile rows of the level's grid, first tile
+    int crop_h, crop_w, out_ld;
+};
+constexpr int OS_MAX_LEVELS = 64;
+__device__ __forceinline__ int os_level_of(const OsLevel* __restrict__ lv, int nlevels, int m) {
+    int l = 0;
+    while (l + 1 < nlevels && m >= lv[l + 1].m0) ++l;
+    return l;
+}
+
 struct OsDArgs {
+    const OsLevel* levels;  // pyramid batch: per-level geometry (device), else nullptr
+    int nlevels;
     SrcDesc src;            // image 0: [F][cols][rows]; image n follows at n*F*cols*rows
     int F, nth, NTimg, Sh, Sw, oy0, ox0, FH, FW;
     float* img;
@@ -413,20 +432,26 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     }
     const int npair = a.NKS * a.KC;
     const int m = blockIdx.x / npair, fp = blockIdx.x - m * npair;      // channel pair fastest
-    const int img = m / a.NTimg, mt = m - img * a.NTimg;          // tiles of a batch are numbered image-major
-    const int tj = mt / a.nth, ti = mt - tj * a.nth;
+    int img = m / a.NTimg, mt = m - img * a.NTimg;                // tiles of a batch are numbered image-major
+    int nth = a.nth, FH = a.FH, FW = a.FW;
+    if (a.levels) {                                               // pyramid batch: the level's own plane and tile grid
+        const OsLevel lv = a.levels[os_level_of(a.levels, a.nlevels, m)];
+        src.ptr = lv.src; src.rows = lv.rows; src.cols = lv.cols;
+        FH = lv.FH; FW = lv.FW; nth = lv.nth; mt = m - lv.m0; img = 0;
+    }
+    const int tj = mt / nth, ti = mt - tj * nth;
     const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // ---- gather: thread = (row y, column parity); lanes run along h (contiguous in the source)
     {
         const int y = threadIdx.x & 63;
-        const int gy = os_wrap(oy + y, a.FH);
+        const int gy = os_wrap(oy + y, FH);
         const bool vy = gy < src.rows;
         for (int ch = 0; ch < 2; ++ch) {
             const int f = 2 * fp + ch;
             const float* pl = src.ptr + ((size_t)img * a.F + f) * src.cols * src.rows + gy;
             float* dst = raw + (size_t)ch * 64 * OS_DRAW + y;
-            int gx = os_wrap(ox + (threadIdx.x >> 6), a.FW);
+            int gx = os_wrap(ox + (threadIdx.x >> 6), FW);
             const bool vf = vy && f < a.F;
 #pragma unroll
             for (int b = 0; b < 2; ++b) {
@@ -435,7 +460,7 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
                 for (int k = 0; k < 16; ++k) {                      // 16 independent loads in flight
                     v[k] = (vf && gx < src.cols) ? __ldg(pl + (size_t)gx * src.rows) : 0.f;
                     gx += 2;
-                    if (gx >= a.FW) gx -= a.FW;                     // FW >= 16 > 2: one conditional subtract is enough
+                    if (gx >= FW) gx -= FW;                     // FW >= 16 > 2: one conditional subtract is enough
                 }
 #pragma unroll
                 for (int k = 0; k < 16; ++k) dst[((threadIdx.x >> 6) + 2 * (16 * b + k)) * OS_DRAW] = v[k];
@@ -942,6 +967,8 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
 // The 1/4096 of the inverse transform is folded into the B operand images (os_data_fft).
 // grid = (ceil(NT/OS_IG), templates in chunk); smem = OS_IG * OS_ITILE * 8 B.
 struct OsInvArgs {
+    const OsLevel* levels;  // pyramid batch (os_inverse_z only): per-level geometry; plane of (level l, template t) =
+    int nlevels;            // outs[l * out_img_stride + t], stored with the level's own crop / out_ld
     const float* P;
     float* const* outs;
     int nk, NNB, NTn, RS, NT, NTimg, nth, Sh, Sw, oy0, ox0;
@@ -991,7 +1018,7 @@ __global__ void os_peak_finalize(const unsigned long long* keys, int K, fftconv_
 // Tail of both inverse kernels: the 64 outputs a lane holds after pass 2 (rows ylo / yhi = lane - oy0 (+32), columns
 // 4*j1 + par (+2) - ox0 of the valid block of its tile) go to the plane (crop fused), to the plane shifted by the template
 // extent (correlation mode), or into the fused reductions (maximum, detections) -- in which case no plane is written.
-struct OsTileOut { float* dst; int ny, nx, y0, x0; };
+struct OsTileOut { float* dst; int ny, nx, y0, x0, ld; };
 __device__ __forceinline__ void os_inverse_emit(const OsInvArgs& a, int t, int lane, int par, int tile_index, const OsTileOut& T,
                                                 const float (&reA)[16], const float (&imA)[16], const float (&reB)[16], const float (&imB)[16])
 {
@@ -1068,7 +1095,7 @@ __device__ __forceinline__ void os_inverse_emit(const OsInvArgs& a, int t, int l
     // every store carries its own predicate and a 32-bit element offset (the branchy form with 64-bit products cost
     // 9 instructions per store: a quarter of all instructions of the inverse)
     float* dlo = T.dst + ylo;
-    const int ld = a.out_ld;
+    const int ld = T.ld;
     const unsigned unx = (unsigned)nx;
     int off = (par - a.ox0) * ld;
 #pragma unroll
@@ -1261,7 +1288,7 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         auto ld = [&](int j) { const cpx z0 = ld1(j), z1 = ld1(j + 1); return make_float4(z0.x, z0.y, z1.x, z1.y); };
         if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
         else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
-        const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq]};
+        const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq], a.out_ld};
         os_inverse_emit(a, t, lane, par, m0 + gq, T, reA, imA, reB, imB);
     }
 }
@@ -1443,7 +1470,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_tma(OsInvArgs a, const __gr
             if (par == 0) os_fft64_pair<0, true>(ld, reA, imA, reB, imB);
             else          os_fft64_pair<1, true>(ld, reA, imA, reB, imB);
         }
-        const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq]};
+        const OsTileOut T{tile_dst[gq], tile_ny[gq], tile_nx[gq], tile_y0[gq], tile_x0[gq], a.out_ld};
         os_inverse_emit(a, t, lane, par, mbase + gq, T, reA, imA, reB, imB);
     }
 }
@@ -1492,7 +1519,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid
     cpx* buf = reinterpret_cast<cpx*>(os_smem_raw);
     __shared__ __align__(8) uint64_t full[4];
     __shared__ float* tile_dst[2][OS_IG];
-    __shared__ int tile_ny[2][OS_IG], tile_nx[2][OS_IG], tile_y0[2][OS_IG], tile_x0[2][OS_IG], tile_ok[2][OS_IG];
+    __shared__ int tile_ny[2][OS_IG], tile_nx[2][OS_IG], tile_y0[2][OS_IG], tile_x0[2][OS_IG], tile_ok[2][OS_IG], tile_ld[2][OS_IG];
     const int NG = a.RS >> 3;
     const int NX = a.NNB * NG;                                             // items per template
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1532,8 +1559,18 @@ __global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid
             const int i = threadIdx.x - 32;
             const int m = mbase + i;
             const bool ok = 4 * g + i < a.NTn && m < a.NT;
-            float* d = nullptr; int ny = 0, nx = 0;
-            if (ok) {
+            float* d = nullptr; int ny = 0, nx = 0, ld = a.out_ld;
+            if (ok && a.levels) {                     // pyramid batch: planes only (no peak / detection / correlation mode)
+                const int l = os_level_of(a.levels, a.nlevels, m);
+                const OsLevel lv = a.levels[l];
+                const int mt = m - lv.m0;
+                const int tj = mt / lv.nth, ti = mt - tj * lv.nth;
+                const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
+                tile_y0[sl][i] = Y0; tile_x0[sl][i] = X0;
+                ld = lv.out_ld;
+                ny = min(a.Sh, lv.crop_h - Y0); nx = min(a.Sw, lv.crop_w - X0);
+                d = a.outs[(size_t)l * a.out_img_stride + t] + (size_t)X0 * ld + Y0;
+            } else if (ok) {
                 const int img = m / a.NTimg, mt = m - img * a.NTimg;
                 const int tj = mt / a.nth, ti = mt - tj * a.nth;
                 const int Y0 = ti * a.Sh, X0 = tj * a.Sw;
@@ -1549,7 +1586,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid
                     d = a.outs[(size_t)img * a.out_img_stride + t] + (size_t)X0 * a.out_ld + Y0;
                 }
             }
-            tile_dst[sl][i] = d; tile_ny[sl][i] = ny; tile_nx[sl][i] = nx; tile_ok[sl][i] = ok ? 1 : 0;
+            tile_dst[sl][i] = d; tile_ny[sl][i] = ny; tile_nx[sl][i] = nx; tile_ok[sl][i] = ok ? 1 : 0; tile_ld[sl][i] = ld;
         }
         float reA[16], imA[16], reB[16], imB[16];
         // Both passes run through ONE copy of the 16-point register transforms (a two-trip loop that stays rolled); only
@@ -1614,7 +1651,7 @@ __global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid
             request(item + istep);
         }
         if (tile_ok[sl][zq]) {                                             // warp-uniform
-            const OsTileOut T{tile_dst[sl][zq], tile_ny[sl][zq], tile_nx[sl][zq], tile_y0[sl][zq], tile_x0[sl][zq]};
+            const OsTileOut T{tile_dst[sl][zq], tile_ny[sl][zq], tile_nx[sl][zq], tile_y0[sl][zq], tile_x0[sl][zq], tile_ld[sl][zq]};
             os_inverse_emit(a, t, lane, par, mbase + zq, T, reA, imA, reB, imB);
         }
     }

@@ -38,7 +38,7 @@ LIB_PATH = os.environ.get("FFTCONV_LIB") or os.path.join(_HERE, "libfftconv.so")
 EXPORTED_SYMBOLS = [
     "fftconv_fft_size16", "fftconv_fft_size_pow2", "fftconv_fft_data", "fftconv_fft_data_clamp",
     "fftconv_conv_fft_data", "fftconv_conv_fft_data_streams", "fftconv_convolution_fft",
-    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv", "fftconv_bank_conv_max",
+    "fftconv_conv_bank", "fftconv_conv_batch", "fftconv_conv_pyramid", "fftconv_bank_create", "fftconv_bank_info", "fftconv_bank_conv", "fftconv_bank_conv_max",
     "fftconv_bank_conv_detect", "fftconv_bank_conv_topk",
     "fftconv_plan_create", "fftconv_plan_execute", "fftconv_plan_info", "fftconv_plan_destroy",
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
@@ -117,6 +117,8 @@ def lib() -> ctypes.CDLL:
                                               c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp]
         L.fftconv_conv_batch.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                          c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_conv_pyramid.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                           c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
         L.fftconv_bank_create.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]
         L.fftconv_bank_info.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]
         L.fftconv_bank_conv.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp]
@@ -471,16 +473,60 @@ def conv_batch(data_t, bank_t, out_t=None, options: Optional[Options] = None, st
     if out_t is None:
         out_t = torch.empty((N, K, FW, FH), dtype=torch.float32, device=data_t.device)
     plane = FW * FH * 4
-    kp = (ctypes.c_void_p * K)(*[bank_t.data_ptr() + 4 * k * F * kw * kh for k in range(K)])
-    op = (ctypes.c_void_p * (N * K))(*[out_t.data_ptr() + plane * i for i in range(N * K)])
-    khs = (ctypes.c_int * K)(*([kh] * K))
-    kws = (ctypes.c_int * K)(*([kw] * K))
-    ond = (ctypes.c_ubyte * K)(*([1] * K))
+    kp = np.uint64(bank_t.data_ptr()) + np.uint64(4 * F * kw * kh) * np.arange(K, dtype=np.uint64)     # (no Python loop over
+    op = np.uint64(out_t.data_ptr()) + np.uint64(plane) * np.arange(N * K, dtype=np.uint64)            # N*K plane pointers)
+    khs = np.full(K, kh, dtype=np.int32)
+    kws = np.full(K, kw, dtype=np.int32)
+    ond = np.ones(K, dtype=np.uint8)
     st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
     o = ctypes.byref(options) if options is not None else None
-    rc = lib().fftconv_conv_batch(data_t.data_ptr(), 1, N, H, W, F, kh, kw, K, kp, khs, kws, None, ond, op, 1, o, dev, st)
+    rc = lib().fftconv_conv_batch(data_t.data_ptr(), 1, N, H, W, F, kh, kw, K, kp.ctypes.data, khs.ctypes.data, kws.ctypes.data,
+                                  None, ond.ctypes.data, op.ctypes.data, 1, o, dev, st)
     _check(rc, ERRID_CONV)
     return out_t
+
+
+def conv_pyramid(levels, bank_t, kh: int, kw: int, outs=None, specs=None, shapes=None,
+                 options: Optional[Options] = None, stream=None):
+    """Feature pyramid x one device-resident bank in ONE call (fftconv_conv_pyramid, BASELINE config 5).
+
+    levels   list of float32 torch tensors [F][W_l][H_l] on the device -- or None when every level arrives as a spectrum
+    specs    optional list of complex64 [F][FW_l][CH_l] spectra from fft_data_device (used where levels is None / levels[l] is None);
+             `shapes` = [(H_l, W_l)] is then required
+    bank_t   float32 [K][F][kw][kh] on the device; kh x kw is also the declared maximum template size
+    Returns [out_l float32 [K][FW_l][FH_l]] (allocated here unless `outs` is given).  Stream-ordered, no host sync."""
+    torch = _torch()
+    K, F, kw_, kh_ = (int(x) for x in bank_t.shape)
+    if (kh_, kw_) != (kh, kw):
+        raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+    L = len(levels) if levels is not None else len(specs)
+    if shapes is None:
+        shapes = [(int(t.shape[2]), int(t.shape[1])) for t in levels]
+    dev_t = bank_t.device
+    dev = int(dev_t.index or 0)
+    planes = [(computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)) for (H, W) in shapes]
+    if outs is None:
+        outs = [torch.empty((K, FW, FH), dtype=torch.float32, device=dev_t) for (FH, FW) in planes]
+    dp = (ctypes.c_void_p * L)(*[(levels[l].data_ptr() if levels is not None and levels[l] is not None else None) for l in range(L)])
+    sp = None
+    if specs is not None:
+        sp = (ctypes.c_void_p * L)(*[(specs[l].data_ptr() if specs[l] is not None else None) for l in range(L)])
+    Hs = (ctypes.c_int * L)(*[h for h, _ in shapes])
+    Ws = (ctypes.c_int * L)(*[w for _, w in shapes])
+    # pointer tables as numpy arrays (a bank of 20 000 templates x 10 levels is 200 000 plane pointers: a Python loop over
+    # them costs more than the convolution)
+    ks = np.arange(K, dtype=np.uint64)
+    kp = np.uint64(bank_t.data_ptr()) + np.uint64(4 * F * kw * kh) * ks
+    op = np.concatenate([np.uint64(outs[l].data_ptr()) + np.uint64(4 * FW * FH) * ks for l, (FH, FW) in enumerate(planes)])
+    khs = np.full(K, kh, dtype=np.int32)
+    kws = np.full(K, kw, dtype=np.int32)
+    ond = np.ones(K, dtype=np.uint8)
+    st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    o = ctypes.byref(options) if options is not None else None
+    rc = lib().fftconv_conv_pyramid(L, dp if levels is not None else None, sp, Hs, Ws, F, kh, kw, K, kp.ctypes.data,
+                                    khs.ctypes.data, kws.ctypes.data, None, ond.ctypes.data, op.ctypes.data, o, dev, st)
+    _check(rc, ERRID_CONV)
+    return outs
 
 
 class Bank:

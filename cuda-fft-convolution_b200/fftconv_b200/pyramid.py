@@ -59,10 +59,12 @@ def pyramid_convolution(levels: Optional[Sequence], max_kh: int, max_kw: int, n_
 
 
 def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Sequence[Tuple[int, int, int]],
-                             bank_t, kh: int, kw: int, outs: Optional[List] = None, options=None, group=None):
+                             bank_t, kh: int, kw: int, outs: Optional[List] = None, options=None, group=None,
+                             one_call: bool = True):
     """CUDA instance of the schedule: level_tensors[l] float32 [F][W][H] on this rank's device (rank 0),
     bank_t float32 [K][F][kw][kh] — the FULL bank, identical on every rank; each rank convolves its shard.
-    Returns (begin, end, [out_l float32 [end-begin][FW_l][FH_l]])."""
+    one_call (default): all levels x the shard through fftconv_conv_pyramid; False: one cudaConvFFTData-style call per
+    level (the reference caller's loop).  Returns (begin, end, [out_l float32 [end-begin][FW_l][FH_l]])."""
     import torch
     import fftconv_b200 as fc
     K = int(bank_t.shape[0])
@@ -75,6 +77,24 @@ def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Se
     def alloc_spec(H, W, F):
         FH, FW = level_plane(H, W, kh, kw)
         return torch.empty((F, FW, FH // 2 + 1), dtype=torch.complex64, device=dev)
+
+    if one_call:
+        # fftconv_conv_pyramid: the spectra of all levels (transformed / received below) and the shard of the bank go
+        # through ONE call -- the tiles of every level share one per-bin GEMM, the template spectra are computed once
+        got = {}
+
+        def conv_fn(l, spec, b, e):
+            got[l] = spec
+            if l + 1 < len(level_shapes):
+                return None
+            if e == b:
+                return [outs[i] if outs is not None else None for i in range(len(level_shapes))]
+            specs = [got[i] for i in range(len(level_shapes))]
+            shapes = [(H, W) for (H, W, _) in level_shapes]
+            return fc.conv_pyramid(None, bank_t[b:e], kh, kw, outs=outs, specs=specs, shapes=shapes, options=options)
+
+        b, e, res = pyramid_convolution(level_tensors, kh, kw, K, None, fft_fn, alloc_spec, conv_fn, level_shapes, group)
+        return b, e, res[-1]
 
     def conv_fn(l, spec, b, e):
         out = outs[l] if outs is not None else None

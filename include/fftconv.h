@@ -120,6 +120,21 @@ int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F,
                       int K, const float* d_bank, int kh, int kw,
                       float* d_out, const fftconv_options* opt, int device, void* stream);
 
+/* Extension (BASELINE config "exemplar-SVM scale": feature pyramid x template bank): L levels of different sizes
+ * against ONE bank in one call -- what a caller of the reference does with one cudaFFTData + one cudaConvFFTData per
+ * level (demoCudaConvolutionFFT.m:111-129 is one level of it).  Level l is either raw data level_data[l] =
+ * [F][W[l]][H[l]] on the device or, where level_data is NULL / level_data[l] is NULL, the spectrum level_spec[l] that
+ * fftconv_fft_data produced for it with the same maxKH x maxKW ([F][FW_l][CH_l] on the device).  Plane (l, k) goes to
+ * outs[l*K + k], a device buffer of FW_l*FH_l floats (FH_l = computeFFTsize16(H[l] + maxKH - 1), ...).  With templates
+ * up to 32 x 32 the overlap-save tiles of ALL levels form one N dimension of the per-frequency-bin complex GEMM: the
+ * template spectra are computed and streamed once per call instead of once per level.  Otherwise (or with
+ * correlate / crop options) the call is L calls of the single-image entry points.  Stream-ordered. */
+int fftconv_conv_pyramid(int L, const float* const* level_data, const fftconv_float2* const* level_spec,
+                         const int* H, const int* W, int F, int maxKH, int maxKW,
+                         int K, const float* const* kernels, const int* kh, const int* kw,
+                         const int* kf, const unsigned char* kernel_on_device,
+                         float* const* outs, const fftconv_options* opt, int device, void* stream);
+
 /* Extension (BASELINE config "batched"): N images of identical H x W x F stored back to back
  * (data: C array [N][F][W][H]) against ONE bank; plane (n, k) goes to outs[n*K + k].  With device outputs
  * and kernels up to 32 x 32 the images only add overlap-save tiles to the N dimension of the per-frequency-bin

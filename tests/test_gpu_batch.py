@@ -75,6 +75,63 @@ def test_batch_falls_back_for_large_kernels(fc, oracle):
     _case(fc, oracle, N=2, H=80, W=70, F=2, kh=40, kw=33, K=3, seed=45)
 
 
+@pytest.mark.parametrize("feed", ["raw", "spectra", "mixed"])
+def test_conv_pyramid_one_call_equals_level_by_level(fc, oracle, feed):
+    """fftconv_conv_pyramid: the ten level sizes of BASELINE config 5 (F = 31, 16 x 16 templates) against one bank of 150
+    templates in ONE call (tiles of all levels share the per-bin GEMM; 158 tiles = 4 tile blocks that straddle level
+    boundaries) -- against the per-level two-call sequence cudaFFTData -> cudaConvFFTData, and against float64."""
+    import torch
+    from fftconv_b200.pyramid import pyramid_sides, level_plane
+    rng = np.random.default_rng(57)
+    F, kh, kw, K = 31, 16, 16, 150
+    sides = pyramid_sides()
+    levels = [(rng.random((s, s + (l % 3), F), dtype=np.float32) * 0.2).astype(np.float32) for l, s in enumerate(sides)]   # H = s, W = s + l%3
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.05).astype(np.float32)
+    lt = [torch.from_numpy(np.ascontiguousarray(lv.transpose(2, 1, 0))).cuda() for lv in levels]
+    bt = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    shapes = [(lv.shape[0], lv.shape[1]) for lv in levels]
+    specs = [fc.fft_data_device(t, H, W, F, kh, kw).clone() for t, (H, W) in zip(lt, shapes)]
+    ref_outs = [fc.conv_bank(sp, bt, kh, kw).clone() for sp in specs]
+    fc.profile(True); fc.profile_read(True)
+    if feed == "raw":
+        outs = fc.conv_pyramid(lt, bt, kh, kw)
+    elif feed == "spectra":
+        outs = fc.conv_pyramid(None, bt, kh, kw, specs=specs, shapes=shapes)
+    else:
+        outs = fc.conv_pyramid([t if l % 2 else None for l, t in enumerate(lt)], bt, kh, kw, specs=specs, shapes=shapes)
+    torch.cuda.synchronize()
+    prof = fc.profile_read(True)
+    fc.profile(False)
+    assert prof["os_gemm"][1] == 1 and prof["os_inverse"][1] == 1 and prof["os_kern_fft(templates)"][1] == 1, prof
+    for l, (H, W) in enumerate(shapes):
+        FH, FW = level_plane(H, W, kh, kw)
+        got, want = outs[l].cpu().numpy(), ref_outs[l].cpu().numpy()
+        assert got.shape == (K, FW, FH)
+        assert oracle.rel_l2(got, want) < TOL, l
+        for k in (0, 127, 128, K - 1):
+            ref = oracle.direct_conv64_c(levels[l], bank[k], FH, FW)
+            assert oracle.rel_l2(got[k].T, ref) < TOL, (l, k)
+
+
+def test_conv_pyramid_falls_back_level_by_level(fc, oracle):
+    """templates above 32 x 32 (no overlap-save tiles) and correlation mode: the call is L single-image calls."""
+    import torch
+    rng = np.random.default_rng(58)
+    F, K = 2, 3
+    for kh, kw, opts in ((40, 9, None), (7, 7, fc.Options(correlate=1))):
+        levels = [rng.random((s, s + 5, F), dtype=np.float32) for s in (70, 50)]
+        bank = rng.standard_normal((K, kh, kw, F)).astype(np.float32)
+        lt = [torch.from_numpy(np.ascontiguousarray(lv.transpose(2, 1, 0))).cuda() for lv in levels]
+        bt = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+        outs = fc.conv_pyramid(lt, bt, kh, kw, options=opts)
+        torch.cuda.synchronize()
+        for l, lv in enumerate(levels):
+            H, W = lv.shape[:2]
+            spec = fc.fft_data_device(lt[l], H, W, F, kh, kw)
+            want = fc.conv_bank(spec, bt, kh, kw, options=opts)
+            assert oracle.rel_l2(outs[l].cpu().numpy(), want.cpu().numpy()) < TOL
+
+
 def test_pyramid_schedule_single_rank(fc, oracle):
     """config 5 scaled down: 4-level pyramid x 80 templates through the sharded schedule (world = 1)."""
     import torch
