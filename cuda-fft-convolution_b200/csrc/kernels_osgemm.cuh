@@ -442,7 +442,9 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     const int tj = mt / nth, ti = mt - tj * nth;
     const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // ---- gather: thread = (row y, column parity); lanes run along h (contiguous in the source)
+    // ---- gather: thread = (row y, column parity); lanes run along h (contiguous in the source).  Asynchronous 4-byte
+    // copies straight into shared memory: all 64 of a thread are in flight at once and cost no registers (the register-
+    // staged form ran 4 dependent rounds of 16 loads: the kernel's top stall was long_scoreboard at 4.1 warps per issue)
     {
         const int y = threadIdx.x & 63;
         const int gy = os_wrap(oy + y, FH);
@@ -450,22 +452,21 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
         for (int ch = 0; ch < 2; ++ch) {
             const int f = 2 * fp + ch;
             const float* pl = src.ptr + ((size_t)img * a.F + f) * src.cols * src.rows + gy;
-            float* dst = raw + (size_t)ch * 64 * OS_DRAW + y;
+            float* dst = raw + (size_t)ch * 64 * OS_DRAW + y + (threadIdx.x >> 6) * OS_DRAW;
             int gx = os_wrap(ox + (threadIdx.x >> 6), FW);
             const bool vf = vy && f < a.F;
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                float v[16];
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {                      // 16 independent loads in flight
-                    v[k] = (vf && gx < src.cols) ? __ldg(pl + (size_t)gx * src.rows) : 0.f;
-                    gx += 2;
-                    if (gx >= FW) gx -= FW;                     // FW >= 16 > 2: one conditional subtract is enough
-                }
-#pragma unroll
-                for (int k = 0; k < 16; ++k) dst[((threadIdx.x >> 6) + 2 * (16 * b + k)) * OS_DRAW] = v[k];
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                if (vf && gx < src.cols)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(pl + (size_t)gx * src.rows) : "memory");
+                else
+                    *dst = 0.f;
+                dst += 2 * OS_DRAW;
+                gx += 2;
+                if (gx >= FW) gx -= FW;                             // FW >= 16 > 2: one conditional subtract is enough
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
     }
     __syncthreads();
     const int par = warp >> 1;                       // warp-uniform: tasks (par, par + 2)
