@@ -116,6 +116,39 @@ int main(int argc, char** argv) {
         printf("pyramid x prepared bank: bank transform %.1f ms (once), %.3f ms per pyramid, %.3e conv outputs/s\n", prep_ms, ms,
                nout / (ms * 1e-3));
         fftconv_bank_destroy(bank);
+        // the same pyramid through fftconv_conv_pyramid: ONE call, the tiles of all levels share the per-bin GEMM and the
+        // template spectra are computed once per call (no prepared bank needed)
+        {
+            CK(cudaFree(d_o));
+            size_t tot = 0;
+            std::vector<size_t> off(10);
+            std::vector<int> Hs(10), Ws(10);
+            std::vector<const float*> lvp(10, d_lv);
+            for (int l = 0; l < 10; ++l) {
+                Hs[l] = Ws[l] = side[l];
+                off[l] = tot;
+                tot += (size_t)fftconv_fft_size16(side[l] + c.kh - 1) * fftconv_fft_size16(side[l] + c.kw - 1) * c.K;
+            }
+            CK(cudaMalloc(&d_o, tot * 4));
+            std::vector<float*> opl((size_t)10 * c.K);
+            for (int l = 0; l < 10; ++l) {
+                const size_t pl = (size_t)fftconv_fft_size16(side[l] + c.kh - 1) * fftconv_fft_size16(side[l] + c.kw - 1);
+                for (int k = 0; k < c.K; ++k) opl[(size_t)l * c.K + k] = d_o + off[l] + pl * k;
+            }
+            auto run1 = [&]() {
+                return fftconv_conv_pyramid(10, lvp.data(), nullptr, Hs.data(), Ws.data(), c.F, c.kh, c.kw, c.K, kp.data(), khs.data(),
+                                            kws.data(), nullptr, ond.data(), opl.data(), nullptr, device, st);
+            };
+            FC(run1());
+            CK(cudaStreamSynchronize(st));
+            CK(cudaEventRecord(e0, st));
+            for (int i = 0; i < iters; ++i) FC(run1());
+            CK(cudaEventRecord(e1, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            ms /= iters;
+            printf("pyramid in one call (fftconv_conv_pyramid): %.3f ms per pyramid, %.3e conv outputs/s\n", ms, nout / (ms * 1e-3));
+        }
         fftconv_release();
         return 0;
     }
