@@ -1597,6 +1597,50 @@ int fftconv_fft_size_pow2(int n) {         // src/cudaConvFFTData.h:67-94
     return (int)(1u << (hi + 1));
 }
 
+// Provenance of a spectrum for the overlap-save path (Ctx::SpecCache): keep a copy of the raw data behind `d_spec` and the
+// hash of the spectrum as it is NOW (stream order).  Called by fftconv_fft_data for the spectrum it just wrote, and by
+// fftconv_spectrum_bind_raw for a spectrum the caller assembled elsewhere.
+static int spec_cache_record(Ctx& c, const void* d_spec, const float* d_data, int H, int W, int F, int FH, int FW, bool zero_pad,
+                             cudaStream_t st) {
+    Ctx::SpecCache& sc = c.sc;
+    const size_t raw_bytes = sizeof(float) * (size_t)H * W * F;
+    if (sc.spec == d_spec) { sc.valid = false; sc.b_valid = false; }
+    if (zero_pad && !g_capturing && !c.plan_pin && os_env().spec_cache && raw_bytes <= ((size_t)512 << 20)) {
+        sc.valid = false; sc.b_valid = false;
+        if (int e = dev_reserve(sc.raw, raw_bytes)) return e;
+        if (int e = dev_reserve(sc.hash, 2 * sizeof(unsigned long long))) return e;
+        CU(cudaMemcpyAsync(sc.raw.p, d_data, raw_bytes, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemsetAsync(sc.hash.p, 0, 2 * sizeof(unsigned long long), st));
+        const size_t n = (size_t)F * FW * (FH / 2 + 1);
+        os_hash64<<<os_hash_grid(c, n), 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_spec), n,
+                                                      (unsigned long long*)sc.hash.p);
+        LAUNCH_CHECK();
+        sc.valid = true; sc.spec = d_spec; sc.H = H; sc.W = W; sc.F = F; sc.FH = FH; sc.FW = FW;
+        // the last convolution fed by a spectrum of this geometry took the overlap-save path: transform the tiles now, on
+        // the data-side stream, next to whatever the caller does until it convolves
+        OsCfg og;
+        if (sc.want && sc.w_F == F && sc.w_FH == FH && sc.w_FW == FW && os_env().spec_cache > 1 &&
+            os_config(F, FH, FW, sc.w_maxkh, sc.w_maxkw, og)) {
+            CU(cudaEventRecord(c.evf[0], st));
+            CU(cudaStreamWaitEvent(c.side2, c.evf[0], 0));
+            if (int e = os_prepare_data(c, og, nullptr, (const float*)sc.raw.p, H, W, 0, c.side2)) return e;
+            sc.b_valid = true; sc.b_maxkh = sc.w_maxkh; sc.b_maxkw = sc.w_maxkw; sc.b_gen = c.osB_gen;
+        }
+    }
+    return 0;
+}
+
+int fftconv_spectrum_bind_raw(const fftconv_float2* d_spec, const float* d_raw, int H, int W, int F, int maxKH, int maxKW,
+                              int device, void* stream) {
+    g_err.clear();
+    if (!d_spec || !d_raw || H <= 0 || W <= 0 || F <= 0 || maxKH <= 0 || maxKW <= 0)
+        return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
+    const int FH = fftconv_fft_size16(H + maxKH - 1), FW = fftconv_fft_size16(W + maxKW - 1);
+    CtxScope cs(device, (cudaStream_t)stream);
+    if (cs.err) return cs.err;
+    return spec_cache_record(*cs.c, d_spec, d_raw, H, W, F, FH, FW, true, (cudaStream_t)stream);
+}
+
 static int fft_data_impl(const float* data, int data_on_device, int H, int W, int F, int KH, int KW,
                          int pad_mode, int kernel_y, int kernel_x, fftconv_float2* d_spec, int device, void* stream) {
     g_err.clear();
@@ -1615,33 +1659,7 @@ static int fft_data_impl(const float* data, int data_on_device, int H, int W, in
         d_data = (const float*)c->ddata.p;
     }
     if (int e = run_fft_data(*c, d_data, H, W, F, FH, FW, pad_mode, kernel_y, kernel_x, (cpx*)d_spec, st)) return e;
-    {   // provenance of this spectrum for the overlap-save path (Ctx::SpecCache)
-        Ctx::SpecCache& sc = c->sc;
-        const size_t raw_bytes = sizeof(float) * (size_t)H * W * F;
-        if (sc.spec == (const void*)d_spec) { sc.valid = false; sc.b_valid = false; }
-        if (pad_mode == PAD_ZERO && !g_capturing && !c->plan_pin && os_env().spec_cache && raw_bytes <= ((size_t)512 << 20)) {
-            sc.valid = false; sc.b_valid = false;
-            if (int e = dev_reserve(sc.raw, raw_bytes)) return e;
-            if (int e = dev_reserve(sc.hash, 2 * sizeof(unsigned long long))) return e;
-            CU(cudaMemcpyAsync(sc.raw.p, d_data, raw_bytes, cudaMemcpyDeviceToDevice, st));
-            CU(cudaMemsetAsync(sc.hash.p, 0, 2 * sizeof(unsigned long long), st));
-            const size_t n = (size_t)F * FW * (FH / 2 + 1);
-            os_hash64<<<os_hash_grid(*c, n), 256, 0, st>>>(reinterpret_cast<const unsigned long long*>(d_spec), n,
-                                                           (unsigned long long*)sc.hash.p);
-            LAUNCH_CHECK();
-            sc.valid = true; sc.spec = d_spec; sc.H = H; sc.W = W; sc.F = F; sc.FH = FH; sc.FW = FW;
-            // the last convolution fed by a spectrum of this geometry took the overlap-save path: transform the tiles now, on
-            // the data-side stream, next to whatever the caller does until it convolves
-            OsCfg og;
-            if (sc.want && sc.w_F == F && sc.w_FH == FH && sc.w_FW == FW && os_env().spec_cache > 1 &&
-                os_config(F, FH, FW, sc.w_maxkh, sc.w_maxkw, og)) {
-                CU(cudaEventRecord(c->evf[0], st));
-                CU(cudaStreamWaitEvent(c->side2, c->evf[0], 0));
-                if (int e = os_prepare_data(*c, og, nullptr, (const float*)sc.raw.p, H, W, 0, c->side2)) return e;
-                sc.b_valid = true; sc.b_maxkh = sc.w_maxkh; sc.b_maxkw = sc.w_maxkw; sc.b_gen = c->osB_gen;
-            }
-        }
-    }
+    if (int e = spec_cache_record(*c, d_spec, d_data, H, W, F, FH, FW, pad_mode == PAD_ZERO, st)) return e;
     if (!data_on_device) CU(cudaStreamSynchronize(st));    // src/cudaFFTData.cu:147
     return 0;
 }

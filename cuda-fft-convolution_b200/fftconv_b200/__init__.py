@@ -44,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "fftconv_bank_destroy", "fftconv_modulate_and_normalize", "fftconv_launch_count",
     "fftconv_workspace_bytes", "fftconv_release", "fftconv_last_error", "fftconv_version",
     "fftconv_profile_enable", "fftconv_profile_kinds", "fftconv_profile_name", "fftconv_profile_read",
-    "fftconv_spectrum_ready_event", "fftconv_query_path",
+    "fftconv_spectrum_ready_event", "fftconv_spectrum_bind_raw", "fftconv_query_path",
     "fftconv_peer_alloc", "fftconv_peer_open", "fftconv_peer_close", "fftconv_peer_free", "fftconv_peer_signal",
     "fftconv_peer_wait", "fftconv_peer_wait_all", "fftconv_peer_pull", "fftconv_peer_status", "fftconv_peer_allgather",
 ]
@@ -117,6 +117,7 @@ def lib() -> ctypes.CDLL:
                                               c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp]
         L.fftconv_conv_batch.argtypes = [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                          c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp]
+        L.fftconv_spectrum_bind_raw.argtypes = [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]
         L.fftconv_conv_pyramid.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                            c_vp, c_vp, c_vp, c_vp, c_int, c_vp]
         L.fftconv_bank_create.argtypes = [c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp]

@@ -234,7 +234,7 @@ class PeerAllGatherSpectrum:
 
     Falls back to per-slice NCCL / gloo broadcasts when CUDA IPC is unavailable (`enabled` False)."""
 
-    def __init__(self, shape, group=None):
+    def __init__(self, shape, group=None, bind_raw: bool = True):
         import ctypes
         import torch
         import torch.distributed as dist
@@ -252,6 +252,8 @@ class PeerAllGatherSpectrum:
         self._owned = None
         self._mapped = {}
         self.enabled = False
+        self._bind = None
+        self.bind_raw = bind_raw
         cuda = torch.cuda.is_available()
         self.dev = torch.cuda.current_device() if cuda else None
         ok, handle = 0, b""
@@ -308,6 +310,7 @@ class PeerAllGatherSpectrum:
         """cudaFFTData on this rank's channel range of data_t [F][W][H], written into its slice of self.spec.
         fft_fn(data_slice, n_channels, spec_slice) replaces the CUDA call in the CPU tests."""
         f0, f1 = self.my_channels()
+        self._bind = (data_t, H, W, kh, kw) if (fft_fn is None and self.enabled and self.bind_raw) else None
         if f1 <= f0:
             return
         if fft_fn is not None:
@@ -321,6 +324,12 @@ class PeerAllGatherSpectrum:
         if self.enabled:
             self._chk(self._L.fftconv_peer_allgather(self._bases, self.world, self.rank, self._offs, self.flag_off, self.step,
                                                      self.dev, self._stream()))
+            if self._bind is not None:
+                # every rank holds the whole (replicated) image: declare it as the source of the assembled spectrum, so the
+                # overlap-save path tiles it directly instead of inverting the spectrum (fftconv_spectrum_bind_raw)
+                data_t, H, W, kh, kw = self._bind
+                self._chk(self._L.fftconv_spectrum_bind_raw(self.spec.data_ptr(), data_t.data_ptr(), H, W, self.shape[0], kh, kw,
+                                                            self.dev, self._stream()))
             return self.spec
         if self.world > 1:
             import torch

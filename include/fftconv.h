@@ -120,6 +120,17 @@ int fftconv_conv_bank(const fftconv_float2* d_spec, int CH, int FW, int F,
                       int K, const float* d_bank, int kh, int kw,
                       float* d_out, const fftconv_options* opt, int device, void* stream);
 
+/* Extension (multi-GPU spectrum delivery): declares that the COMPLETE spectrum at d_spec (as of this point in stream
+ * order) is the fftconv_fft_data transform -- zero pad, same maxKH x maxKW -- of the raw data d_raw [F][W][H] on the same
+ * device.  For a spectrum this library did not produce in one piece: channel slices transformed on several GPUs and
+ * all-gathered over NVLink (the one-process-per-GPU form of the peer copy in src/cudaConvFFTDataStreams.cu:279-289, see
+ * sharding.PeerAllGatherSpectrum).  The overlap-save path then tiles the raw data instead of inverting the spectrum back
+ * to a plane.  The spectrum is hashed now and re-hashed by the convolution on the device, so a buffer that changed after
+ * the declaration is never served from the raw data; the declaration itself is the caller's contract.  The raw data is
+ * copied (the caller may reuse d_raw at once).  Stream-ordered. */
+int fftconv_spectrum_bind_raw(const fftconv_float2* d_spec, const float* d_raw, int H, int W, int F,
+                              int maxKH, int maxKW, int device, void* stream);
+
 /* Extension (BASELINE config "exemplar-SVM scale": feature pyramid x template bank): L levels of different sizes
  * against ONE bank in one call -- what a caller of the reference does with one cudaFFTData + one cudaConvFFTData per
  * level (demoCudaConvolutionFFT.m:111-129 is one level of it).  Level l is either raw data level_data[l] =

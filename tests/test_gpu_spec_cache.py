@@ -108,3 +108,41 @@ def test_second_convolution_with_the_same_spectrum(fc, oracle):
     torch.cuda.synchronize()
     _check(fc, oracle, o1, data, bank)
     _check(fc, oracle, o2, data, bank)
+
+
+def _bind(fc, spec, d_t):
+    import torch
+    rc = fc.lib().fftconv_spectrum_bind_raw(spec.data_ptr(), d_t.data_ptr(), H, W, F, KH, KW, 0,
+                                            torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, fc.last_error()
+
+
+def test_bind_raw_spectrum_assembled_from_channel_slices(fc, oracle):
+    """fftconv_spectrum_bind_raw: a spectrum assembled from channel slices (what the multi-GPU all-gather delivers) is
+    declared as the transform of the replicated raw data; the convolution then tiles the raw data."""
+    import torch
+    data, bank, d_t, b_t = _mk(20)
+    FH, FW = fc.computeFFTsize16(H + KH - 1), fc.computeFFTsize16(W + KW - 1)
+    spec = torch.empty((F, FW, FH // 2 + 1), dtype=torch.complex64, device="cuda")
+    for f0, f1 in ((0, 2), (2, 3), (3, F)):
+        fc.fft_data_device(d_t[f0:f1], H, W, f1 - f0, KH, KW, spec_t=spec[f0:f1])
+    _bind(fc, spec, d_t)
+    d_t.zero_()                                        # the library kept its own copy of the raw data
+    out = fc.conv_bank(spec, b_t, KH, KW)
+    torch.cuda.synchronize()
+    _check(fc, oracle, out, data, bank)
+
+
+def test_bind_raw_then_modified_spectrum_is_inverted_not_trusted(fc, oracle):
+    import torch
+    data, bank, d_t, b_t = _mk(21)
+    spec = fc.fft_data_device(d_t, H, W, F, KH, KW).clone()
+    _bind(fc, spec, d_t)
+    spec.mul_(-3.0)                                    # changed after the declaration: the device-side hash no longer matches
+    out = fc.conv_bank(spec, b_t, KH, KW)
+    torch.cuda.synchronize()
+    _check(fc, oracle, out, data, bank, scale=-3.0)
+
+
+def test_bind_raw_rejects_bad_arguments(fc):
+    assert fc.lib().fftconv_spectrum_bind_raw(None, None, H, W, F, KH, KW, 0, None) != 0
