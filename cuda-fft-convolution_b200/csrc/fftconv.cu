@@ -541,7 +541,7 @@ struct OsCfg {
     int Sh, Sw, nth, ntw, NT;     // valid outputs per tile side, tile grid, tiles of the whole batch
     int nimg, NTimg;              // images in the batch, tiles per image
     int NKS, KC;                  // K stages per item, 16-byte k units per stage (even)
-    int NNB, NTn, NMMA, RS;       // tile blocks, tiles per block, MMA N, P row stride (floats)
+    int NNB, NTn, NMMA, RS, RSP;  // tile blocks, tiles per block, MMA N, P row length and row pitch (floats)
     int nsta;                     // A ring depth
     size_t gemm_smem, inv_smem;
     size_t a_stage, b_buf, p_blk; // bytes
@@ -572,9 +572,15 @@ static bool os_config_tiles(OsCfg& g) {
     g.NTn = (g.NT + g.NNB - 1) / g.NNB;
     g.NMMA = (2 * g.NTn + 15) & ~15;
     g.RS = (2 * g.NTn + 7) & ~7;
+    // Row pitch of P.  pitch/4 odd makes the epilogue staging of os_gemm conflict-free (rows of 80 floats put the 8 lanes of
+    // a 128-bit store wavefront on 2 bank groups), but rows then start on odd 16-byte offsets and the 32-byte boxes the inverse
+    // gathers straddle two sectors.  Measured (B200): config 4 (29 tile blocks, A fed from L2, os_gemm bound by its epilogue)
+    // os_gemm 7.09 -> 5.56 ms, inverse 6.75 -> 7.19 ms; config 5 (4 tile blocks) 4.41 -> 3.96 / 5.02 -> 5.40 ms; config 2
+    // (1 tile block, os_gemm HBM-bound) 0.197 -> 0.198 / 0.220 -> 0.239 ms.  Padded only where it wins.
+    g.RSP = (g.NNB >= 8 && !((g.RS >> 2) & 1)) ? g.RS + 4 : g.RS;
     g.a_stage = (size_t)2 * g.KC * OS_TM * 16;
     g.b_buf = (size_t)g.NKS * g.KC * g.NMMA * 16;                       // fp32 B image of one (tile block, bin)
-    g.p_blk = (size_t)OS_TM * g.RS * 4;
+    g.p_blk = (size_t)OS_TM * g.RSP * 4;
     if (g.b_buf >= (1u << 20) || g.a_stage >= (1u << 20)) return false;       // mbarrier tx-count range
     g.nsta = 0;                                                           // raw A ring depth (fp32 K-stages in flight)
     for (int ns = 8; ns >= 2; --ns) {
@@ -627,7 +633,7 @@ static const OsEnv& os_env() {
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nbins, OsTensorMap* out) {
+static int os_make_p_tensor_map(const float* P, int RS, int RSP, unsigned long long nbins, OsTensorMap* out) {
     static PFN_tmapEncodeTiled encode = nullptr;
     if (!encode) {
         void* fn = nullptr;
@@ -638,7 +644,7 @@ static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nbins
     }
     static_assert(sizeof(CUtensorMap) == sizeof(OsTensorMap), "tensor map size");
     const cuuint64_t gdim[3] = {(cuuint64_t)RS, OS_TM, (cuuint64_t)nbins};
-    const cuuint64_t gstride[2] = {(cuuint64_t)RS * 4, (cuuint64_t)RS * 4 * OS_TM};
+    const cuuint64_t gstride[2] = {(cuuint64_t)RSP * 4, (cuuint64_t)RSP * 4 * OS_TM};
     const cuuint32_t box[3] = {8, 1, 64}, estride[3] = {1, 1, 1};
     const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P), gdim,
                               gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -646,7 +652,7 @@ static int os_make_p_tensor_map(const float* P, int RS, unsigned long long nbins
     if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
 }
-static int os_make_p_tensor_map5(const float* P, int RS, unsigned long long nblk, unsigned vbox, OsTensorMap* out) {
+static int os_make_p_tensor_map5(const float* P, int RS, int RSP, unsigned long long nblk, unsigned vbox, OsTensorMap* out) {
     static PFN_tmapEncodeTiled encode = nullptr;   // P as {RS floats, 128 templates, 64 v, 33 u, template block x tile block}, box {8, 1, vbox, 33, 1}
     if (!encode) {
         void* fn = nullptr;
@@ -656,7 +662,7 @@ static int os_make_p_tensor_map5(const float* P, int RS, unsigned long long nblk
         encode = (PFN_tmapEncodeTiled)fn;
     }
     static_assert(sizeof(CUtensorMap) == sizeof(OsTensorMap), "tensor map size");
-    const cuuint64_t row = (cuuint64_t)RS * 4;
+    const cuuint64_t row = (cuuint64_t)RSP * 4;
     const cuuint64_t gdim[5] = {(cuuint64_t)RS, OS_TM, OS_T, OS_CH, (cuuint64_t)nblk};
     const cuuint64_t gstride[4] = {row, row * OS_TM, row * OS_TM * OS_T, row * OS_TM * OS_NBIN};
     const cuuint32_t box[5] = {8, 1, vbox, OS_CH, 1}, estride[5] = {1, 1, 1, 1, 1};
@@ -788,7 +794,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
     {
         OsGemmArgs a{};
         a.Aimg = bankA ? bankA : (const float*)c.osA.p; a.Bimg = (const float*)c.osB.p; a.P = (float*)c.osP.p;
-        a.NTBLK = ntblk; a.NNB = g.NNB; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.RS = g.RS;
+        a.NTBLK = ntblk; a.NNB = g.NNB; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.RS = g.RS; a.RSP = g.RSP;
         a.nitems = (long long)g.NNB * OS_NBIN * ntblk;
         a.nsta = g.nsta;
         if (const char* v = getenv("FFTCONV_OS_NSTA")) a.nsta = std::max(2, std::min(g.nsta, atoi(v)));   // timing experiments
@@ -809,7 +815,7 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
     {
         OsInvArgs a{};
         a.levels = g.d_levels; a.nlevels = g.nlevels;
-        a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS;
+        a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS; a.RSP = g.RSP;
         a.NT = g.NT; a.NTimg = g.NTimg; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
         a.peak_keys = peak_keys; a.khw = khw; a.H = H; a.W = W;
@@ -828,12 +834,12 @@ static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStr
     OsTensorMap tm;
     const int ntb = (nk + OS_TM - 1) / OS_TM;
     // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
-    if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
+    if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, g.RSP, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
         const long long nitems = (long long)g.NNB * (g.RS / 8) * nk;      // (template, tile block, group of 4 tiles)
         static const int use_z = []{ const char* v = getenv("FFTCONV_OS_INV_Z"); return v && *v ? atoi(v) : 1; }();
         OsTensorMap tm8, tm1;
-        if (use_z && os_make_p_tensor_map5(a.P, g.RS, (unsigned long long)ntb * g.NNB, 8, &tm8) == 0 &&
-            os_make_p_tensor_map5(a.P, g.RS, (unsigned long long)ntb * g.NNB, 1, &tm1) == 0) {
+        if (use_z && os_make_p_tensor_map5(a.P, g.RS, g.RSP, (unsigned long long)ntb * g.NNB, 8, &tm8) == 0 &&
+            os_make_p_tensor_map5(a.P, g.RS, g.RSP, (unsigned long long)ntb * g.NNB, 1, &tm1) == 0) {
             // One CTA per item by default.  FFTCONV_OS_INV_PERSIST=1 runs 3 persistent CTAs per SM that request the boxes of
             // their next item while they store the current one: the wait for the boxes disappears (5 % of the stall samples
             // instead of 34 %), but with all 24 warps of an SM busy the 38 KB of live code thrash the 32 KB instruction cache

@@ -640,6 +640,7 @@ struct OsGemmArgs {
     const float* Bimg;
     float* P;
     int NTBLK, NNB, NKS, KC, NMMA, RS;
+    int RSP;          // row pitch of P and of the staging tile in floats (RS, or RS + 4 when RS/4 is even: see os_config_tiles)
     long long nitems;
     int nsta;
     int lbo_swap;     // debug: swap the LBO / SBO fields of the smem descriptors
@@ -684,8 +685,8 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
     unsigned char* lo_sm = a_sm + (size_t)g.nsta * a_half;      // lo ring [2][a_half]
     unsigned char* b_sm = lo_sm + 2 * (size_t)a_half;           // [2][b_buf] raw B of the current / next key
     unsigned char* blo_sm = b_sm + 2 * (size_t)b_buf;           // [2][b_buf] b - tf32(b)
-    float* stage_sm = reinterpret_cast<float*>(blo_sm + 2 * (size_t)b_buf);   // [128][RS] epilogue staging
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage_sm) + (size_t)OS_TM * g.RS * 4u);
+    float* stage_sm = reinterpret_cast<float*>(blo_sm + 2 * (size_t)b_buf);   // [128][RSP] epilogue staging
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(stage_sm) + (size_t)OS_TM * g.RSP * 4u);
     uint64_t* a_full = bars;                 // [nsta]  TMA -> splitter
     uint64_t* a_empty = bars + 8;            // [nsta]  MMA -> TMA
     uint64_t* a_ready = bars + 16;           // [nsta]  splitter -> MMA
@@ -884,7 +885,10 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
             mbar_wait(&acc_full[acc], (nit >> 1) & 1);
             os_tc_fence_after();
             const uint32_t taddr = tmem_base + acc * OS_ACC_COLS + ((uint32_t)(q * 32) << 16);
-            float* srow = stage_sm + (size_t)row * g.RS;
+            // row pitch RSP with RSP/4 odd: the 8 lanes of a 128-bit store wavefront (rows 4 RSP words apart) hit 8 different
+            // bank groups; with the dense pitch RS = 80 they hit 2 (ncu r02b: 48 % of the kernel's shared-memory wavefronts were
+            // bank conflicts, the staging of one item took ~1.3 us and bounded the item rate of the whole pipeline)
+            float* srow = stage_sm + (size_t)row * g.RSP;
             uint32_t r[80];                           // all TMEM loads of the row in flight, one wait (RS <= 80 columns)
 #pragma unroll
             for (int i = 0; i < 10; ++i)
@@ -906,13 +910,13 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
                     o[1] = make_float4(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]), __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
                 }
             fence_proxy_async();                      // this thread's staging writes -> visible to the bulk-copy engine
-            // P[tblk][nblk][bin][template][RS]: the staging tile is ONE contiguous run of global memory
-            float* dst = g.P + (((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * ((size_t)OS_TM * g.RS);
+            // P[tblk][nblk][bin][template][RSP]: the staging tile is ONE contiguous run of global memory
+            float* dst = g.P + (((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * ((size_t)OS_TM * g.RSP);
             if (g.use_tmap) {
                 os_named_bar_sync(1, 128);
-                if (leader && !(g.dbg & 1)) os_bulk_s2g(dst, stage_sm, (uint32_t)(OS_TM * g.RS * 4));
+                if (leader && !(g.dbg & 1)) os_bulk_s2g(dst, stage_sm, (uint32_t)(OS_TM * g.RSP * 4));
             } else {
-                os_bulk_s2g(dst + (size_t)row * g.RS, srow, (uint32_t)g.RS * 4u);     // one bulk copy per template row
+                os_bulk_s2g(dst + (size_t)row * g.RSP, srow, (uint32_t)g.RS * 4u);     // one bulk copy per template row
             }
         }
         os_bulk_wait0();
@@ -938,7 +942,7 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
     const float* A = g.Aimg + ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
     const float* B = g.Bimg + ((size_t)nblk * OS_NBIN + bin) * g.NKS * b_stage;
     const int t = threadIdx.x;
-    float* P = g.P + ((((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM + t) * (size_t)g.RS;
+    float* P = g.P + ((((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM + t) * (size_t)g.RSP;
     for (int n = 0; n < g.RS; ++n) {
         float acc = 0.f;
         for (int ks = 0; ks < g.NKS; ++ks)
@@ -973,6 +977,7 @@ struct OsInvArgs {
     const float* P;
     float* const* outs;
     int nk, NNB, NTn, RS, NT, NTimg, nth, Sh, Sw, oy0, ox0;
+    int RSP;                // row pitch of P in floats (>= RS)
     int FH, FW, crop_h, crop_w, out_ld;
     int out_img_stride;     // plane of (image n, template t) = outs[n * out_img_stride + t]
     // fused reduction (fftconv_bank_conv_max): when peak_keys != nullptr no plane is written; every template keeps the
@@ -1219,9 +1224,9 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         cpx* dst = buf + gq * OS_ITILE + os_icol(v);
         if (m < a.NT) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
-            const size_t ustride = (size_t)64 * OS_TM * (a.RS / 2);        // cpx units; P[tblk][nblk][u*64 + v][template][RS]
+            const size_t ustride = (size_t)64 * OS_TM * (a.RSP / 2);       // cpx units; P[tblk][nblk][u*64 + v][template][RSP]
             const cpx* pp = reinterpret_cast<const cpx*>(
-                a.P + ((((size_t)tblk * a.NNB + nblk) * OS_NBIN + v) * OS_TM + tl) * (size_t)a.RS + 2 * ml);
+                a.P + ((((size_t)tblk * a.NNB + nblk) * OS_NBIN + v) * OS_TM + tl) * (size_t)a.RSP + 2 * ml);
             const uint32_t d0 = smem_u32(dst);
 #pragma unroll
             for (int u = 0; u <= 32; ++u) {
