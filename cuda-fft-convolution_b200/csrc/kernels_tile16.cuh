@@ -54,6 +54,9 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -235,14 +238,15 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
     const size_t bar_off = ((pipe_bytes > y_bytes ? pipe_bytes : y_bytes) + 15) & ~(size_t)15;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + bar_off);          // [nstage] "slab landed"
     uint32_t* done = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 32);     // [nstage] warps finished with the slab
-    uint32_t* seq = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 48);      // [E][4] passes done per accumulator copy
-    cpx* Racc = reinterpret_cast<cpx*>(smem_raw + bar_off + 160);              // [E][4][16][32]
+    uint64_t* empty = reinterpret_cast<uint64_t*>(smem_raw + bar_off + 48);    // [nstage] "every warp is done with the slab"
+    uint32_t* seq = reinterpret_cast<uint32_t*>(smem_raw + bar_off + 80);      // [E][4] passes done per accumulator copy
+    cpx* Racc = reinterpret_cast<cpx*>(smem_raw + bar_off + 192);              // [E][4][16][32]
 
     const cpx* dp_src = P.Dp + (size_t)t * F * (dp_bytes / sizeof(cpx));
     const cpx* a_src = P.Ag + ((size_t)t * P.NG + kg) * F * (a_bytes / sizeof(cpx));
 
     if (tid == 0) {
-        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); done[s] = 0; }
+        for (int s = 0; s < nstage; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (int)blockDim.x); done[s] = 0; }
         for (int e = 0; e < 4 * E; ++e) seq[e] = 0;
         fence_barrier_init();
         fence_proxy_async();
@@ -330,11 +334,17 @@ __global__ void __launch_bounds__(T16_THREADS, 1) tile16_conv(const Tile16Params
             if (++xw == nwarps) xw = 0;
         }
         // No block barrier in the channel loop: the LAST warp to finish with slab s refills it, so the
-        // warps drift apart and their shared-memory and FMA phases overlap.
+        // warps drift apart and their shared-memory and FMA phases overlap.  Every thread arrives on the slab's "empty"
+        // mbarrier before its warp counts itself out; the counter only elects the refilling warp, which then passes through the
+        // (already complete) empty barrier: the reads of all warps are ordered before the bulk copy by the barrier itself,
+        // the edge compute-sanitizer's racecheck models (round 1 reported the refill against the reads of the slab because
+        // the acq_rel counter was the only ordering).
+        mbar_arrive(&empty[s]);                     // every thread that read the slab arrives itself
         __syncwarp();
         if (lane == 0) {
             if (atom_add_acq_rel_shared(&done[s], 1u) == (uint32_t)nwarps - 1u) {
                 done[s] = 0;
+                mbar_wait(&empty[s], phase);
                 if (f + nstage < F) {
                     unsigned char* dst = smem_raw + (size_t)s * stage_bytes;
                     mbar_expect_tx(&full[s], stage_bytes);
