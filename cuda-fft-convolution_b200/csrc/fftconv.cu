@@ -576,19 +576,18 @@ static bool os_config_tiles(OsCfg& g) {
     g.NTn = (g.NT + g.NNB - 1) / g.NNB;
     g.NMMA = (2 * g.NTn + 15) & ~15;
     g.RS = (2 * g.NTn + 7) & ~7;
-    // Row pitch of P.  pitch/4 odd makes the epilogue staging of os_gemm conflict-free (rows of 80 floats put the 8 lanes of
-    // a 128-bit store wavefront on 2 bank groups), but rows then start on odd 16-byte offsets and the 32-byte boxes the inverse
-    // gathers straddle two sectors.  Measured (B200): config 4 (29 tile blocks, A fed from L2, os_gemm bound by its epilogue)
-    // os_gemm 7.09 -> 5.56 ms, inverse 6.75 -> 7.19 ms; config 5 (4 tile blocks) 4.41 -> 3.96 / 5.02 -> 5.40 ms; config 2
-    // (1 tile block, os_gemm HBM-bound) 0.197 -> 0.198 / 0.220 -> 0.239 ms.  Padded only where it wins.
-    g.RSP = (g.NNB >= 8 && !((g.RS >> 2) & 1)) ? g.RS + 4 : g.RS;
+    // Row pitch of the epilogue staging tile of os_gemm: pitch/4 odd puts the 8 lanes of a 128-bit store wavefront on 8 bank
+    // groups (dense rows of 80 floats: 2).  P itself stays dense: the tile leaves through a TMA tensor store whose box is
+    // RSP wide while the tensor is RS wide, so the pad columns are clipped.  (A padded P was tried first: os_gemm 7.09 ->
+    // 5.56 ms at config 4, but the 32-byte boxes of the inverse then straddle sectors: 6.75 -> 7.19 ms.)
+    g.RSP = ((g.RS >> 2) & 1) ? g.RS : g.RS + 4;
     g.a_stage = (size_t)2 * g.KC * OS_TM * 16;
     g.b_buf = (size_t)g.NKS * g.KC * g.NMMA * 16;                       // fp32 B image of one (tile block, bin)
-    g.p_blk = (size_t)OS_TM * g.RSP * 4;
+    g.p_blk = (size_t)OS_TM * g.RS * 4;
     if (g.b_buf >= (1u << 20) || g.a_stage >= (1u << 20)) return false;       // mbarrier tx-count range
     g.nsta = 0;                                                           // raw A ring depth (fp32 K-stages in flight)
     for (int ns = 8; ns >= 2; --ns) {
-        const size_t tot = (size_t)(ns + 2) * (g.a_stage / 2) + 4 * g.b_buf + g.p_blk + 512;   // + raw and lo images of B, double-buffered
+        const size_t tot = (size_t)(ns + 2) * (g.a_stage / 2) + 4 * g.b_buf + (size_t)OS_TM * g.RSP * 4 + 512;   // + raw and lo images of B, double-buffered
         if (tot <= kMaxSmem) { g.nsta = ns; g.gemm_smem = tot; break; }
     }
     if (!g.nsta) return false;
@@ -654,6 +653,26 @@ static int os_make_p_tensor_map(const float* P, int RS, int RSP, unsigned long l
                               gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);   // (L2 promotion 64/128/256 B: no effect measured)
     if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+// P as the os_gemm epilogue stores it: {RS floats, 128 templates, items}, box {RSP, 128, 1} (RSP >= RS: the pad columns of
+// the staging tile are outside the tensor and clipped)
+static int os_make_p_store_map(float* P, int RS, int RSP, unsigned long long nitems, OsTensorMap* out) {
+    static PFN_tmapEncodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !fn) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = (PFN_tmapEncodeTiled)fn;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)RS, OS_TM, (cuuint64_t)nitems};
+    const cuuint64_t gstride[2] = {(cuuint64_t)RS * 4, (cuuint64_t)RS * 4 * OS_TM};
+    const cuuint32_t box[3] = {(cuuint32_t)RSP, OS_TM, 1}, estride[3] = {1, 1, 1};
+    const CUresult r = encode(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, P, gdim, gstride, box, estride,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FFTCONV_ERR_CUDA, "cuTensorMapEncodeTiled (P store) failed (%d)", (int)r);
     return 0;
 }
 static int os_make_p_tensor_map5(const float* P, int RS, int RSP, unsigned long long nblk, unsigned vbox, OsTensorMap* out) {
@@ -811,15 +830,19 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
             os_gemm_simt<<<(unsigned)a.nitems, 128, 0, st>>>(a);
         } else {
             a.use_tmap = os_env().gemm_tmap;
+            OsTensorMap pmap{};
+            static const int use_pmap = []{ const char* v = getenv("FFTCONV_OS_GEMM_PMAP"); return v && *v ? atoi(v) : 1; }();
+            a.use_pmap = (a.use_tmap && use_pmap && g.RSP != g.RS && os_make_p_store_map(a.P, g.RS, g.RSP, (unsigned long long)a.nitems, &pmap) == 0) ? 1 : 0;
+            if (!a.use_pmap) { a.RSP = g.RS; g_err.clear(); }        // dense staging tile, plain bulk store
             const unsigned grid = (unsigned)std::min<long long>(a.nitems, (long long)c.sm_count);
-            os_gemm<<<grid, 320, g.gemm_smem, st>>>(a);
+            os_gemm<<<grid, 320, g.gemm_smem, st>>>(a, pmap);
         }
         LAUNCH_CHECK();
     }
     {
         OsInvArgs a{};
         a.levels = g.d_levels; a.nlevels = g.nlevels;
-        a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS; a.RSP = g.RSP;
+        a.P = (const float*)c.osP.p; a.outs = d_outptrs; a.nk = nk; a.NNB = g.NNB; a.NTn = g.NTn; a.RS = g.RS;
         a.NT = g.NT; a.NTimg = g.NTimg; a.nth = g.nth; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = g.FH; a.FW = g.FW; a.out_img_stride = out_img_stride;
         a.peak_keys = peak_keys; a.khw = khw; a.H = H; a.W = W;
@@ -838,12 +861,12 @@ static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStr
     OsTensorMap tm;
     const int ntb = (nk + OS_TM - 1) / OS_TM;
     // (a driver without cuTensorMapEncodeTiled leaves the per-thread cp.async gather of os_inverse)
-    if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, g.RSP, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
+    if (os_env().inv_tma && os_make_p_tensor_map(a.P, g.RS, g.RS, (unsigned long long)ntb * g.NNB * OS_NBIN, &tm) == 0) {
         const long long nitems = (long long)g.NNB * (g.RS / 8) * nk;      // (template, tile block, group of 4 tiles)
         static const int use_z = []{ const char* v = getenv("FFTCONV_OS_INV_Z"); return v && *v ? atoi(v) : 1; }();
         OsTensorMap tm8, tm1;
-        if (use_z && os_make_p_tensor_map5(a.P, g.RS, g.RSP, (unsigned long long)ntb * g.NNB, 8, &tm8) == 0 &&
-            os_make_p_tensor_map5(a.P, g.RS, g.RSP, (unsigned long long)ntb * g.NNB, 1, &tm1) == 0) {
+        if (use_z && os_make_p_tensor_map5(a.P, g.RS, g.RS, (unsigned long long)ntb * g.NNB, 8, &tm8) == 0 &&
+            os_make_p_tensor_map5(a.P, g.RS, g.RS, (unsigned long long)ntb * g.NNB, 1, &tm1) == 0) {
             // One CTA per item by default.  FFTCONV_OS_INV_PERSIST=1 runs 3 persistent CTAs per SM that request the boxes of
             // their next item while they store the current one: the wait for the boxes disappears (5 % of the stall samples
             // instead of 34 %), but with all 24 warps of an SM busy the 38 KB of live code thrash the 32 KB instruction cache

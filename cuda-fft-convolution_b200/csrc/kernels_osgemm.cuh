@@ -640,7 +640,8 @@ struct OsGemmArgs {
     const float* Bimg;
     float* P;
     int NTBLK, NNB, NKS, KC, NMMA, RS;
-    int RSP;          // row pitch of P and of the staging tile in floats (RS, or RS + 4 when RS/4 is even: see os_config_tiles)
+    int RSP;          // row pitch of the epilogue staging tile in floats (RS + 4 when RS/4 is even, see os_config_tiles; P itself is dense)
+    int use_pmap;     // epilogue: TMA tensor store of the padded staging tile, the pad columns clipped by the tensor bounds
     long long nitems;
     int nsta;
     int lbo_swap;     // debug: swap the LBO / SBO fields of the smem descriptors
@@ -675,7 +676,7 @@ struct OsItemIter {
     __device__ __forceinline__ size_t b_block() const { return (size_t)nblk * OS_NBIN + bin; }     // index of the B image block
 };
 
-__global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
+__global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g, const __grid_constant__ OsTensorMap pmap)
 {
     extern __shared__ __align__(128) unsigned char os_smem_raw[];
     const uint32_t a_half = (uint32_t)g.KC * OS_TM * 16u;       // one K-stage of A (fp32 as it travels; one hi or lo image)
@@ -885,9 +886,10 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
             mbar_wait(&acc_full[acc], (nit >> 1) & 1);
             os_tc_fence_after();
             const uint32_t taddr = tmem_base + acc * OS_ACC_COLS + ((uint32_t)(q * 32) << 16);
-            // row pitch RSP with RSP/4 odd: the 8 lanes of a 128-bit store wavefront (rows 4 RSP words apart) hit 8 different
+            // row pitch RSP with RSP/4 odd: the 8 lanes of a 128-bit store wavefront (rows RSP words apart) hit 8 different
             // bank groups; with the dense pitch RS = 80 they hit 2 (ncu r02b: 48 % of the kernel's shared-memory wavefronts were
-            // bank conflicts, the staging of one item took ~1.3 us and bounded the item rate of the whole pipeline)
+            // bank conflicts, and the kernel is bound by shared-memory bandwidth: TMA in, split, 3 operand reads per MMA,
+            // staging, store)
             float* srow = stage_sm + (size_t)row * g.RSP;
             uint32_t r[80];                           // all TMEM loads of the row in flight, one wait (RS <= 80 columns)
 #pragma unroll
@@ -910,13 +912,19 @@ __global__ void __launch_bounds__(320, 1) os_gemm(OsGemmArgs g)
                     o[1] = make_float4(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5]), __uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7]));
                 }
             fence_proxy_async();                      // this thread's staging writes -> visible to the bulk-copy engine
-            // P[tblk][nblk][bin][template][RSP]: the staging tile is ONE contiguous run of global memory
-            float* dst = g.P + (((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * ((size_t)OS_TM * g.RSP);
+            // P[tblk][nblk][bin][template][RS]: the item's 128 x RS block is ONE contiguous run of global memory
+            const size_t item_index = ((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin;
+            float* dst = g.P + item_index * ((size_t)OS_TM * g.RS);
             if (g.use_tmap) {
                 os_named_bar_sync(1, 128);
-                if (leader && !(g.dbg & 1)) os_bulk_s2g(dst, stage_sm, (uint32_t)(OS_TM * g.RSP * 4));
+                if (leader && !(g.dbg & 1)) {
+                    // padded staging tile (pitch RSP): P seen as {RS, 128, items}, box {RSP, 128, 1} -- the RSP - RS pad
+                    // columns lie outside the tensor and are clipped by the TMA engine, P stays dense
+                    if (g.use_pmap) os_tma_store_3d(&pmap, stage_sm, 0, 0, (int)item_index);
+                    else os_bulk_s2g(dst, stage_sm, (uint32_t)(OS_TM * g.RS * 4));
+                }
             } else {
-                os_bulk_s2g(dst + (size_t)row * g.RSP, srow, (uint32_t)g.RS * 4u);     // one bulk copy per template row
+                os_bulk_s2g(dst + (size_t)row * g.RS, srow, (uint32_t)g.RS * 4u);     // one bulk copy per template row
             }
         }
         os_bulk_wait0();
@@ -942,7 +950,7 @@ __global__ void __launch_bounds__(128) os_gemm_simt(OsGemmArgs g)
     const float* A = g.Aimg + ((size_t)tblk * OS_NBIN + bin) * g.NKS * a_stage;
     const float* B = g.Bimg + ((size_t)nblk * OS_NBIN + bin) * g.NKS * b_stage;
     const int t = threadIdx.x;
-    float* P = g.P + ((((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM + t) * (size_t)g.RSP;
+    float* P = g.P + ((((size_t)tblk * g.NNB + nblk) * OS_NBIN + bin) * OS_TM + t) * (size_t)g.RS;
     for (int n = 0; n < g.RS; ++n) {
         float acc = 0.f;
         for (int ks = 0; ks < g.NKS; ++ks)
@@ -977,7 +985,6 @@ struct OsInvArgs {
     const float* P;
     float* const* outs;
     int nk, NNB, NTn, RS, NT, NTimg, nth, Sh, Sw, oy0, ox0;
-    int RSP;                // row pitch of P in floats (>= RS)
     int FH, FW, crop_h, crop_w, out_ld;
     int out_img_stride;     // plane of (image n, template t) = outs[n * out_img_stride + t]
     // fused reduction (fftconv_bank_conv_max): when peak_keys != nullptr no plane is written; every template keeps the
@@ -1224,9 +1231,9 @@ __global__ void __launch_bounds__(OS_IG * 64, 12 / OS_IG) os_inverse(OsInvArgs a
         cpx* dst = buf + gq * OS_ITILE + os_icol(v);
         if (m < a.NT) {
             const int nblk = m / a.NTn, ml = m - nblk * a.NTn;
-            const size_t ustride = (size_t)64 * OS_TM * (a.RSP / 2);       // cpx units; P[tblk][nblk][u*64 + v][template][RSP]
+            const size_t ustride = (size_t)64 * OS_TM * (a.RS / 2);        // cpx units; P[tblk][nblk][u*64 + v][template][RS]
             const cpx* pp = reinterpret_cast<const cpx*>(
-                a.P + ((((size_t)tblk * a.NNB + nblk) * OS_NBIN + v) * OS_TM + tl) * (size_t)a.RSP + 2 * ml);
+                a.P + ((((size_t)tblk * a.NNB + nblk) * OS_NBIN + v) * OS_TM + tl) * (size_t)a.RS + 2 * ml);
             const uint32_t d0 = smem_u32(dst);
 #pragma unroll
             for (int u = 0; u <= 32; ++u) {

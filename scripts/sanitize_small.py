@@ -38,3 +38,14 @@ print("batch:", tuple(out.shape), flush=True)
 bank = fc.Bank(ks[:70]); pk = bank.conv_max(data); bank.close()
 print("peaks:", float(pk[0][0]), int(pk[1][0]), int(pk[2][0]), flush=True)
 print("sanitize_small done", fc.launch_count())
+# round 2: size-specialised large-plane kernels (1152-point lines), pyramid batch (levels of different sizes in one call)
+d6 = rng.random((60, 1152 - 20 + 1 - 2, 1), dtype=np.float32)
+k6 = [(rng.standard_normal((5, 20, 1)) / 8).astype(np.float32)]
+check("path 4 size-specialised w pass", fc.cudaConvolutionFFT(d6, 5, 20, k6, options=fc.Options(path=4)), d6, k6, 64, 1152)
+d7 = rng.random((1152 - 9 + 1 - 3, 30, 2), dtype=np.float32)
+k7 = [(rng.standard_normal((9, 7, 2)) / 8).astype(np.float32)]
+check("path 4 size-specialised h pass", fc.cudaConvolutionFFT(d7, 9, 7, k7, options=fc.Options(path=4)), d7, k7, 1152, 48)
+lv = [torch.from_numpy(np.ascontiguousarray(rng.random((s, s + 3, 5), dtype=np.float32).transpose(2, 1, 0))).cuda() for s in (70, 41, 23)]
+po = fc.conv_pyramid(lv, bt, 11, 9); torch.cuda.synchronize()
+print("pyramid:", [tuple(o.shape) for o in po], flush=True)
+print("sanitize_small round-2 done", fc.launch_count())
