@@ -347,7 +347,9 @@ def config_c5(fc, torch, peak, dist, world, rank):
     r = _record(nout, ms, a, float(rel.item()), peak * world, None,
                 workload="10-level 31-channel HOG pyramid (sides 256..74) x 20000 templates 16x16x31 (BASELINE configs[4])",
                 scaling="strong", n_gpus=world, templates_per_gpu=e - b,
-                collective="NCCL broadcast of the 10 level spectra" if world > 1 else "none (1 GPU)")
+                collective="NCCL broadcast of the 10 level spectra" if world > 1 else "none (1 GPU)",
+                api="fftconv_conv_pyramid: all ten levels x the rank's shard of the bank in one call (the tiles of all levels share "
+                    "the per-bin GEMM); the level spectra come from cudaFFTData on rank 0")
     del outs, bank, levels
     fc.lib().fftconv_release()
     torch.cuda.empty_cache()
@@ -400,7 +402,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"), pg_options=opts)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    numa_cpus = bind_host_to_gpu(local) if world > 1 else None     # before any pinned allocation
+    numa_cpus = bind_host_to_gpu(local) if (world > 1 and not os.environ.get("FFTCONV_BENCH_NOBIND")) else None     # before any pinned allocation
     H, W, F, kh, kw, K, desc = WORKLOADS[args.workload]
     FH, FW = fft16(H + kh - 1), fft16(W + kw - 1)
     CH = FH // 2 + 1
@@ -417,9 +419,24 @@ def run_ours(args):
     # spectrum delivery at N > 1: "peer" = CUDA IPC + NVLink pull ordered by device flags (fftconv_peer_*),
     # "sync" = NCCL broadcast on the step's stream, "async" = NCCL broadcast on a side stream (A/B switches)
     # "allgather" (default) = every rank transforms its slice of the channels, slices pulled through the peer mappings
-    bcast_mode = os.environ.get("FFTCONV_BENCH_BCAST", "allgather") if world > 1 else "local"
+    # default: the ONE-SHOT entry point (cudaConvolutionFFT, src/cudaConvolutionFFT.cu:27-311) with everything resident on the
+    # device -- "oneshot" on one GPU; "rawbcast" on N GPUs: the raw image of rank 0 reaches every rank by scatter + all-gather
+    # over CUDA IPC + NVLink (sharding.PeerBroadcastRaw), then every rank runs the one-shot call on its shard of the bank.
+    # The two-call sequence cudaFFTData -> [spectrum delivery] -> cudaConvFFTData stays available for A/B: "twocall" (1 GPU),
+    # "allgather" / "peer" / "sync" / "async" (N GPUs); extras.two_call reports it next to the default on one GPU.
+    bcast_mode = os.environ.get("FFTCONV_BENCH_BCAST", "rawbcast" if world > 1 else "oneshot")
+    if world == 1 and bcast_mode not in ("oneshot", "twocall"):
+        bcast_mode = "oneshot"
+    if world > 1 and bcast_mode in ("oneshot", "twocall") and not os.environ.get("FFTCONV_BENCH_NODELIVERY"):
+        bcast_mode = "rawbcast"          # (FFTCONV_BENCH_NODELIVERY=1: diagnosis only -- N independent one-shot replicas)
+    if bcast_mode == "twocall":
+        bcast_mode = "local"
     peer = None
     ag = None
+    bc = None
+    if bcast_mode == "rawbcast":
+        from fftconv_b200.sharding import PeerBroadcastRaw
+        bc = PeerBroadcastRaw(4 * F * W * H, scheme=os.environ.get("FFTCONV_BENCH_RAW_SCHEME", "pull"))
     if bcast_mode == "allgather":
         ag = PeerAllGatherSpectrum((F, FW, CH))
         if ag.enabled:
@@ -434,9 +451,27 @@ def run_ours(args):
         else:
             peer, bcast_mode = None, "sync"
     stream = torch.cuda.current_stream()
+    side_stream = torch.cuda.Stream(device=dev) if bc is not None else None
+    delivered = torch.cuda.Event() if bc is not None else None
 
     def step():
-        """data FFT (rank 0, or one channel slice per rank) -> spectrum delivery -> bank convolution on every rank"""
+        """one-shot: [image delivery from rank 0 ->] cudaConvolutionFFT on the device.  two-call modes: data FFT (rank 0, or one
+        channel slice per rank) -> spectrum delivery -> bank convolution on every rank"""
+        if bcast_mode == "oneshot":
+            fc.convolution_fft_device(data, bank, out)
+            return
+        if bc is not None:
+            # the delivery runs on a side stream; only the data-side work of the call (the tile transforms) waits for it
+            # (fftconv_spectrum_ready_event), the template transforms start at once on the step's stream
+            side_stream.wait_stream(stream)
+            with torch.cuda.stream(side_stream):
+                bc.begin()
+                if rank == 0:
+                    bc.publish(data)
+                img = bc.fetch().view(torch.float32).view(F, W, H)
+                delivered.record(side_stream)
+            fc.convolution_fft_device(img, bank, out, data_ready=delivered)
+            return
         if ag is not None:
             ag.begin_fill()
             ag.fill(data, H, W, kh, kw)
@@ -479,8 +514,10 @@ def run_ours(args):
         t_wall0 = time.perf_counter()
         for i in range(args.steps):
             flush.zero_()
-            if dist is not None:
-                dist.barrier()
+            # (no per-step host barrier: dist.barrier() synchronises the host with the device, so every step would start on
+            # an idle GPU and expose the launch latency of its first dozen small kernels -- 0.07-0.10 ms per step at N > 1,
+            # which the single-GPU run, whose host runs ahead of the device, never pays.  The ranks are ordered on the device
+            # by the delivery itself; the timed region as a whole is bracketed by barrier + synchronize as the contract asks.)
             ev[i][0].record(stream)
             step()
             ev[i][1].record(stream)
@@ -522,7 +559,7 @@ def run_ours(args):
     # algorithmic (compulsory) bytes per (image, template) pair, SURVEY 8(d): read the template once,
     # write its plane once (+ the data spectrum amortised over the launch)
     bytes_per_unit = 4 * kh * kw * F + 4 * FH * FW
-    alg_bytes_launch = bytes_per_unit * kernels_per_launch + 8 * CH * FW * F
+    alg_bytes_launch = bytes_per_unit * kernels_per_launch + (4 * H * W * F if bcast_mode in ("oneshot", "rawbcast") else 8 * CH * FW * F)
     dur_s = dom_ms / dom_n * 1e-3
     achieved = alg_bytes_launch / dur_s / 1e9
     traffic = None
@@ -557,6 +594,14 @@ def run_ours(args):
     def e2e_step():
         if world == 1:
             rc = L.fftconv_convolution_fft(h_data.data_ptr(), 0, H, W, F, kh, kw, K, kp, khs, kws, None, None,
+                                           op, 0, None, 0, None, local, st)
+        elif bc is not None:
+            # the frame enters at rank 0 (host -> its IPC buffer), travels over NVLink, every rank convolves its shard
+            bc.begin()
+            if rank == 0:
+                bc.buf.view(torch.float32).copy_(h_data.reshape(-1), non_blocking=True)
+            img = bc.fetch()
+            rc = L.fftconv_convolution_fft(img.data_ptr(), 1, H, W, F, kh, kw, K, kp, khs, kws, None, None,
                                            op, 0, None, 0, None, local, st)
         else:
             rc = 0
@@ -600,7 +645,8 @@ def run_ours(args):
            "h2d_bytes_per_step": int(4 * H * W * F + world * 4 * K * F * kh * kw),
            "d2h_bytes_per_step": int(world * 4 * K * FH * FW),
            "api": "fftconv_convolution_fft (cudaConvolutionFFT) host->host" if world == 1 else
-                  f"fftconv_fft_data + spectrum delivery ({bcast_mode}) + fftconv_conv_fft_data, host->host",
+                  ("image H2D on rank 0 + NVLink scatter/all-gather + fftconv_convolution_fft on every rank, host->host" if bc is not None
+                   else f"fftconv_fft_data + spectrum delivery ({bcast_mode}) + fftconv_conv_fft_data, host->host"),
            "bound": "PCIe D2H of the output planes"}
 
     # ---- e2e as a MEX caller sees it: K SEPARATE PAGEABLE output planes (mex/mex_common.h alloc_out_cell hands the library
@@ -658,6 +704,17 @@ def run_ours(args):
             bank_step(); peak_step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the two-call sequence cudaFFTData -> cudaConvFFTData on the same device-resident inputs (the `value` of rounds 1-2b)
+        def two_call_step():
+            fc.fft_data_device(data, H, W, F, kh, kw, spec_t=spec)
+            fc.conv_bank(spec, bank, kh, kw, out)
+        for _ in range(3):
+            two_call_step()
+        tc = []
+        for _ in range(20):
+            flush.zero_(); e0.record(stream); two_call_step(); e1.record(stream); torch.cuda.synchronize()
+            tc.append(e0.elapsed_time(e1))
+        two_call_rel = float((out[:3].double() - ref).norm() / ref.norm())
         ts = []
         for _ in range(10):
             flush.zero_(); e0.record(stream); bank_step(); e1.record(stream); torch.cuda.synchronize()
@@ -682,7 +739,11 @@ def run_ours(args):
         topk_ms = (time.perf_counter() - t0) * 1e2
         topk_ok = bool(np.array_equal(h_top[:, 0, 0], h_peaks.numpy()[:, 0]))        # best of the top-5 == fused maximum
         L.fftconv_bank_destroy(hb)
-        extras = {"prepared_bank": {"one_off_transform_ms": prep_ms, "ms_per_step": float(np.median(ts)),
+        extras = {"two_call": {"ms_per_step": float(np.median(tc)), "value": outputs_per_step / (float(np.median(tc)) * 1e-3),
+                               "unit": UNIT, "rel_l2_vs_fp64": two_call_rel,
+                               "note": "fftconv_fft_data + fftconv_conv_fft_data (cudaFFTData -> cudaConvFFTData) on the same "
+                                       "device-resident inputs: the step rounds 1-2b reported as `value`"},
+                  "prepared_bank": {"one_off_transform_ms": prep_ms, "ms_per_step": float(np.median(ts)),
                                     "value": outputs_per_step / (float(np.median(ts)) * 1e-3), "unit": UNIT,
                                     "rel_l2_vs_fp64": bank_rel,
                                     "note": "fftconv_bank_conv: template spectra resident in HBM, raw data in, planes out (device)"},
@@ -757,8 +818,14 @@ def run_ours(args):
             "config": {"workload": desc, "templates_per_gpu": K, "fft_plane": [FH, FW], "outputs_per_step": outputs_per_step,
                        "l2": "flushed between steps by an untimed 256 MiB memset; each step also writes "
                              f"{4 * K * FH * FW / 1e6:.0f} MB of outputs (> 126 MB L2)",
-                       "parallelism": f"template bank sharded over {world} GPU(s), data spectrum "
-                                      + ({"allgather": "all-gathered inside the step: every rank transforms its channel slice of the (replicated) image, "
+                       "api": ("fftconv_convolution_fft (cudaConvolutionFFT), data / templates / planes resident on the device"
+                               if bcast_mode in ("oneshot", "rawbcast") else "fftconv_fft_data + fftconv_conv_fft_data (two-call), device-resident"),
+                       "parallelism": f"template bank sharded over {world} GPU(s), "
+                                      + (("raw image of rank 0 delivered inside the step over CUDA IPC + NVLink (device flags; "
+                                          + ("every rank pulls it out of rank 0's buffer" if bc.scheme == "pull" else "scatter + all-gather")
+                                          + "), on a side stream next to the template transforms; one-shot call on every rank") if bcast_mode == "rawbcast"
+                                         else "one-shot call, nothing to deliver" if bcast_mode == "oneshot" else "data spectrum "
+                                      + {"allgather": "all-gathered inside the step: every rank transforms its channel slice of the (replicated) image, "
                                                        "one kernel per rank pulls the other slices over CUDA IPC + NVLink (device flags)",
                                           "peer": "pulled from rank 0 over CUDA IPC + NVLink inside the step (device flags, no collective kernel)",
                                           "sync": "broadcast by NCCL inside the step", "async": "broadcast by NCCL on a side stream inside the step",
@@ -779,6 +846,10 @@ def run_ours(args):
         if ag.status() != 0:
             raise SystemExit("peer all-gather wait timed out: " + fc.last_error())
         ag.close()
+    if bc is not None:
+        if bc.status() != 0:
+            raise SystemExit("peer broadcast wait timed out: " + fc.last_error())
+        bc.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -1288,6 +1288,23 @@ struct PeerAgArgs {
 };
 __device__ unsigned int g_peer_ag_done[16];
 
+// One warp waits for the ready flags of all peers (lane p <-> rank p).  Runs in front of peer_allgather_kernel on the same
+// stream: the 128 copy CTAs then start on flags that are already up instead of spinning -- while they spun they held a third
+// of the GPU's thread slots and slowed the template transforms running next to them down (2 GPUs: +0.06 ms per step).
+__global__ void peer_ag_wait_kernel(PeerAgArgs a) {
+    const int p = threadIdx.x;
+    if (p >= a.n || p == a.rank) return;
+    const unsigned long long* flag = reinterpret_cast<const unsigned long long*>(a.base[p] + a.flag_off);
+    const long long t0 = clock64();
+    unsigned long long v;
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+        if (v >= a.step) break;
+        if (clock64() - t0 > 4000000000ll) { atomicAdd(&g_peer_timeouts, 1u); break; }
+        __nanosleep(200);
+    }
+}
+
 __global__ void __launch_bounds__(512) peer_allgather_kernel(PeerAgArgs a) {
     const int p = blockIdx.x / a.bpg, b = blockIdx.x - p * a.bpg;
     if (p == a.rank) return;
@@ -2752,6 +2769,8 @@ int fftconv_peer_allgather(void* const* bases, int n, int rank, const unsigned l
     LAUNCH_CHECK();
     if (n > 1) {
         a.bpg = std::max(1, 128 / n);                       // all blocks resident at once: a waiting group never starves another
+        peer_ag_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+        LAUNCH_CHECK();
         peer_allgather_kernel<<<n * a.bpg, 512, 0, (cudaStream_t)stream>>>(a);
         LAUNCH_CHECK();
     }

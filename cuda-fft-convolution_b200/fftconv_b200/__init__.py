@@ -460,6 +460,38 @@ def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Op
     return out_t
 
 
+def convolution_fft_device(data_t, bank_t, out_t=None, options: Optional[Options] = None, stream=None, data_ready=None):
+    """cudaConvolutionFFT with everything resident on the device (fftconv_convolution_fft, src/cudaConvolutionFFT.cu:27-311
+    is its host-buffer original): data_t float32 [F][W][H], bank_t float32 [K][F][kw][kh] (kh x kw is also the declared
+    maximum template size) -> out_t [K][FW][FH].  One call: on the overlap-save path the raw data is tiled directly and
+    no full-plane spectrum is ever formed.  Stream-ordered, no host sync.
+    data_ready: torch.cuda.Event recorded behind whatever is still filling data_t on ANOTHER stream (a peer delivery over
+    NVLink, fftconv_spectrum_ready_event): only the data-side work waits for it, the template transforms start at once."""
+    torch = _torch()
+    F, W, H = (int(x) for x in data_t.shape)
+    K, Fk, kw, kh = (int(x) for x in bank_t.shape)
+    if Fk != F:
+        raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+    FH, FW = computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)
+    dev = int(data_t.device.index or 0)
+    if out_t is None:
+        out_t = torch.empty((K, FW, FH), dtype=torch.float32, device=data_t.device)
+    ks = np.arange(K, dtype=np.uint64)
+    kp = np.uint64(bank_t.data_ptr()) + np.uint64(4 * F * kw * kh) * ks
+    op = np.uint64(out_t.data_ptr()) + np.uint64(4 * FW * FH) * ks
+    khs = np.full(K, kh, dtype=np.int32)
+    kws = np.full(K, kw, dtype=np.int32)
+    ond = np.ones(K, dtype=np.uint8)
+    st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
+    o = ctypes.byref(options) if options is not None else None
+    if data_ready is not None:
+        _check(lib().fftconv_spectrum_ready_event(dev, ctypes.c_void_p(data_ready.cuda_event)), ERRID_CONV)
+    rc = lib().fftconv_convolution_fft(data_t.data_ptr(), 1, H, W, F, kh, kw, K, kp.ctypes.data, khs.ctypes.data, kws.ctypes.data,
+                                       None, ond.ctypes.data, op.ctypes.data, 1, None, 0, o, dev, st)
+    _check(rc, ERRID_CONV)
+    return out_t
+
+
 def conv_batch(data_t, bank_t, out_t=None, options: Optional[Options] = None, stream=None):
     """Batched images against one device-resident bank (fftconv_conv_batch): data_t float32 [N][F][W][H],
     bank_t float32 [K][F][kw][kh] (torch, cuda) -> out_t [N][K][FW][FH].  Stream-ordered, no host sync."""

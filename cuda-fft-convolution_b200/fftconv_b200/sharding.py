@@ -366,6 +366,153 @@ class PeerAllGatherSpectrum:
         self.enabled = False
 
 
+class PeerBroadcastRaw:
+    """The raw image of rank 0 delivered to EVERY rank over CUDA IPC + NVLink -- scheme "pull" (default): every rank pulls
+    the whole image out of rank 0's buffer; scheme "scatter": scatter + all-gather, rank r first pulls slice r out of rank 0's
+    buffer (rank 0 sends each byte once: no single-source fan-out), then one kernel per rank pulls the other slices from the
+    ranks that hold them (fftconv_peer_allgather).  Measured on 2 x B200 inside the bench step: scatter + all-gather 0.657 ms,
+    pull see profiles/ (the chain of small dependent kernels, not the bytes, sets the delivery time at 8 MB).  The one-process-per-GPU form of the
+    reference's cudaMemcpyPeerAsync GPU 0 -> GPU i (src/cudaConvFFTDataStreams.cu:279-289) for the ONE-SHOT entry point,
+    which tiles raw data and never forms a spectrum.  Ordered on the device by 64-bit flags, no host synchronisation.
+
+        bc = PeerBroadcastRaw(nbytes)                # collective; nbytes = size of the image
+        each step:  bc.begin()                        # every peer has pulled what it needed from my buffer
+                    rank 0: bc.publish(image_t)       # copy the image into the IPC buffer (stream-ordered)
+                    data = bc.fetch()                 # uint8 view of the whole image on this rank (stream-ordered)
+
+    Falls back to an NCCL / gloo broadcast when CUDA IPC is unavailable (`enabled` False)."""
+
+    def __init__(self, nbytes: int, group=None, scheme: str = "pull"):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import lib
+        self.group = group
+        self.scheme = scheme
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.nbytes = int(nbytes)
+        per = -(-self.nbytes // self.world)
+        per = (per + 255) // 256 * 256
+        self.bounds = [min(r * per, self.nbytes) for r in range(self.world + 1)]
+        self.bounds[-1] = self.nbytes
+        self.flag_off = (self.nbytes + 255) // 256 * 256
+        self.root_flag = self.flag_off + 8 * (1 + self.world)          # after [ready][ack x world]
+        self.step = 0
+        self._L = None
+        self._owned = None
+        self._mapped = {}
+        self.enabled = False
+        cuda = torch.cuda.is_available()
+        self.dev = torch.cuda.current_device() if cuda else None
+        ok, handle = 0, b""
+        if cuda and self.world <= 16 and self.nbytes % 16 == 0:
+            self._L = L = lib()
+            p, h = ctypes.c_void_p(0), (ctypes.c_ubyte * 64)()
+            if L.fftconv_peer_alloc(self.root_flag + 8, self.dev, ctypes.byref(p), h) == 0:
+                self._owned, handle, ok = p.value, bytes(h), 1
+        if self.world > 1:
+            got = [None] * self.world
+            dist.all_gather_object(got, (ok, handle), group=group)
+            ok = min(g[0] for g in got)
+            if ok:
+                for r, (_, hb) in enumerate(got):
+                    if r == self.rank:
+                        continue
+                    p = ctypes.c_void_p(0)
+                    if self._L.fftconv_peer_open((ctypes.c_ubyte * 64)(*hb), self.dev, ctypes.byref(p)) == 0:
+                        self._mapped[r] = p.value
+                    else:
+                        ok = 0
+            oks = [None] * self.world
+            dist.all_gather_object(oks, int(ok), group=group)
+            ok = min(oks)
+        self.enabled = bool(ok)
+        if self.enabled:
+            self.buf = torch.as_tensor(_RawCuda(self._owned, self.nbytes), device=f"cuda:{self.dev}")
+            bases = [self._owned if r == self.rank else self._mapped[r] for r in range(self.world)]
+            self._bases = (ctypes.c_void_p * self.world)(*bases)
+            self._offs = (ctypes.c_ulonglong * (self.world + 1))(*self.bounds)
+        else:
+            self._release()
+            self.buf = torch.empty(self.nbytes, dtype=torch.uint8, device=(f"cuda:{self.dev}" if cuda else "cpu"))
+
+    def _stream(self):
+        import torch
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _chk(self, rc):
+        if rc != 0:
+            from . import last_error
+            raise RuntimeError("peer broadcast: " + last_error())
+
+    def begin(self):
+        if self.enabled and self.step > 0 and (self.scheme != "pull" or self.rank == 0):
+            self._chk(self._L.fftconv_peer_wait_all(self._owned + self.flag_off + 8, self.world, self.step, self.dev, self._stream()))
+
+    def publish(self, image_t):
+        """rank 0: the image (any dtype, nbytes bytes, on this device) into the IPC buffer."""
+        self.buf.copy_(image_t.reshape(-1).view(self.buf.dtype), non_blocking=True)
+
+    def fetch(self):
+        self.step += 1
+        if self.enabled and self.scheme == "pull":
+            # every rank pulls the whole image out of rank 0: rank 0 sends it N - 1 times, but the dependency chain is two hops
+            # (publish -> flag -> pull) instead of six small kernels across two flag exchanges -- and the call that consumes the
+            # image hides the delivery behind its template transforms (data_ready event), so the chain length is what counts
+            if self.world > 1:
+                if self.rank == 0:
+                    self._chk(self._L.fftconv_peer_signal(self._owned + self.root_flag, self.step, self.dev, self._stream()))
+                    self._chk(self._L.fftconv_peer_signal(self._owned + self.flag_off + 8, self.step, self.dev, self._stream()))
+                else:
+                    self._chk(self._L.fftconv_peer_wait(self._mapped[0] + self.root_flag, self.step, self.dev, self._stream()))
+                    self._chk(self._L.fftconv_peer_pull(self._owned, self._mapped[0], self.nbytes, self.dev, self._stream()))
+                    self._chk(self._L.fftconv_peer_signal(self._mapped[0] + self.flag_off + 8 * (1 + self.rank), self.step,
+                                                          self.dev, self._stream()))
+            return self.buf
+        if self.enabled:
+            if self.world > 1:
+                if self.rank == 0:
+                    self._chk(self._L.fftconv_peer_signal(self._owned + self.root_flag, self.step, self.dev, self._stream()))
+                else:
+                    b0, b1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+                    self._chk(self._L.fftconv_peer_wait(self._mapped[0] + self.root_flag, self.step, self.dev, self._stream()))
+                    if b1 > b0:
+                        self._chk(self._L.fftconv_peer_pull(self._owned + b0, self._mapped[0] + b0, b1 - b0, self.dev, self._stream()))
+            self._chk(self._L.fftconv_peer_allgather(self._bases, self.world, self.rank, self._offs, self.flag_off, self.step,
+                                                     self.dev, self._stream()))
+            return self.buf
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.broadcast(self.buf, src=0, group=self.group)
+        return self.buf
+
+    def status(self) -> int:
+        return self._L.fftconv_peer_status(self.dev) if self.enabled else 0
+
+    def _release(self):
+        for p in self._mapped.values():
+            self._L.fftconv_peer_close(p, self.dev)
+        self._mapped = {}
+
+    def close(self):
+        """Collective: every rank unmaps its peers before any owner frees."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        if self.enabled:
+            import torch
+            torch.cuda.synchronize(self.dev)
+            self._release()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)
+        if self._owned is not None:
+            self._L.fftconv_peer_free(self._owned, self.dev)
+            self._owned = None
+        self.enabled = False
+
+
 def bind_host_to_gpu(device_index: int) -> Optional[List[int]]:
     """Pin the calling process to the CPU cores NVML reports as local to the GPU (same NUMA node / PCIe root), BEFORE
     pinned host buffers are allocated: first touch then places them next to the GPU's PCIe link.  With one process per
