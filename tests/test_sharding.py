@@ -209,3 +209,47 @@ def test_allgather_spectrum_fallback_world2():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(r[1] for r in res), res
+
+
+def _bc_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "cuda-fft-convolution_b200")]
+    import torch
+    import torch.distributed as dist
+    from fftconv_b200.sharding import PeerBroadcastRaw
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(6)
+        bc = PeerBroadcastRaw(4 * 3 * 30 * 40)                        # no CUDA here: broadcast fallback through the process group
+        ok = not bc.enabled
+        for step in range(3):
+            img = torch.from_numpy(rng.random((3, 30, 40), dtype=np.float32) + step)     # same stream of draws on both ranks
+            bc.begin()
+            if rank == 0:
+                bc.publish(img)                                       # only rank 0 contributes its copy
+            got = bc.fetch().view(torch.float32).view(3, 30, 40)
+            ok = ok and bool(torch.equal(got, img))
+        bc.close()
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_raw_fallback_world2():
+    """sharding.PeerBroadcastRaw without CUDA IPC: the image of rank 0 reaches every rank through the process group."""
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bc_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(r[1] for r in res), res
