@@ -54,7 +54,7 @@ with open(os.path.join(P, f"{R}_hot_kernels_ncu.md"), "w") as f:
         def mb(x, u): return float(x.replace(",", "")) * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}[u]
         ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         key = name.split("<")[0]
-        key = {"os_inverse_tma": "os_inverse"}.get(key, key)       # bench.py names kernels by role
+        key = {"os_inverse_tma": "os_inverse", "os_inverse_z": "os_inverse"}.get(key, key)       # bench.py names kernels by role
         traffic[key] = mb(r[ir], units[ir]) + mb(r[iw], units[iw])
 json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, f"{R}_hot_kernels_ncu.md")).read()[:3000])
