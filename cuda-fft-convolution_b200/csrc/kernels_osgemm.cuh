@@ -498,7 +498,10 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
         }
     }
     __syncthreads();
-    // ---- w step: thread = (spectrum row u, task pair); both channels, then the operand-image stores
+    // ---- w step: thread = (spectrum row u, task pair); both channels, then the operand-image stores.
+    // (Tried: warp = (channel, task pair), lane = row, rows 0 and 32 packed into one complex transform -- all 128 threads busy
+    // instead of 66, but each thread then owns 8 of the 16 bytes of an operand unit: twice the store instructions, half-written
+    // sectors meeting in L2.  Config 4 at quarter scale 3.27 -> 5.35 ms, C2 45 -> 62 us: the kernel is bound by its stores.)
     {
         const int u = threadIdx.x & 63;
         if (u < OS_CH) {
