@@ -1943,6 +1943,8 @@ static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh,
             nspec_planes += F;
         }
     }
+    // same scratch bound as the image groups of fftconv_conv_batch: beyond it the levels go one by one
+    if (NT > 1280) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch: %d tiles exceed one GEMM problem", NT);
     og.FH = 0; og.FW = 0; og.nimg = L; og.nth = 1; og.ntw = 1; og.NT = NT; og.NTimg = NT;
     if (!os_config_tiles(og)) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch outside the range of the overlap-save path");
 

@@ -113,6 +113,25 @@ def test_conv_pyramid_one_call_equals_level_by_level(fc, oracle, feed):
             assert oracle.rel_l2(got[k].T, ref) < TOL, (l, k)
 
 
+def test_conv_pyramid_too_many_tiles_goes_level_by_level(fc, oracle):
+    """more than 1280 overlap-save tiles (the scratch bound of one GEMM problem): the levels are convolved one by one."""
+    import torch
+    rng = np.random.default_rng(59)
+    F, K, kh, kw = 2, 64, 16, 16
+    sides = (800, 790, 780, 770, 760)                          # 17 x 17 tiles each
+    lt = [torch.from_numpy(rng.random((F, s, s), dtype=np.float32)).cuda() for s in sides]
+    bt = torch.from_numpy((rng.standard_normal((K, F, kw, kh)) * 0.05).astype(np.float32)).cuda()
+    fc.profile(True); fc.profile_read(True)
+    outs = fc.conv_pyramid(lt, bt, kh, kw)
+    torch.cuda.synchronize()
+    prof = fc.profile_read(True)
+    fc.profile(False)
+    assert prof["os_gemm"][1] == len(sides), prof              # one GEMM launch per level
+    for l in (0, 4):
+        want = fc.convolution_fft_device(lt[l], bt)
+        assert oracle.rel_l2(outs[l].cpu().numpy(), want.cpu().numpy()) < TOL
+
+
 def test_conv_pyramid_falls_back_level_by_level(fc, oracle):
     """templates above 32 x 32 (no overlap-save tiles) and correlation mode: the call is L single-image calls."""
     import torch
