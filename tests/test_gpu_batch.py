@@ -113,6 +113,27 @@ def test_conv_pyramid_one_call_equals_level_by_level(fc, oracle, feed):
             assert oracle.rel_l2(got[k].T, ref) < TOL, (l, k)
 
 
+@pytest.mark.parametrize("L,K,F,kh,kw", [(1, 1, 1, 1, 1), (2, 3, 1, 5, 32), (3, 129, 2, 32, 3)])
+def test_conv_pyramid_edge_shapes(fc, oracle, L, K, F, kh, kw):
+    """one level / one template / one channel, 1 x 1 and 32-wide templates, a bank one past a block of 128, ragged level sizes."""
+    import torch
+    rng = np.random.default_rng(60 + K)
+    shapes = [(33 + 17 * l, 70 - 9 * l) for l in range(L)]
+    levels = [rng.random((H, W, F), dtype=np.float32) for (H, W) in shapes]
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.1).astype(np.float32)
+    lt = [torch.from_numpy(np.ascontiguousarray(lv.transpose(2, 1, 0))).cuda() for lv in levels]
+    bt = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    outs = fc.conv_pyramid(lt, bt, kh, kw)
+    torch.cuda.synchronize()
+    for l, (H, W) in enumerate(shapes):
+        FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+        got = outs[l].cpu().numpy()
+        assert got.shape == (K, FW, FH)
+        for k in sorted({0, K // 2, K - 1}):
+            ref = oracle.direct_conv64_c(levels[l], bank[k], FH, FW)
+            assert oracle.rel_l2(got[k].T, ref) < TOL, (l, k)
+
+
 def test_conv_pyramid_too_many_tiles_goes_level_by_level(fc, oracle):
     """more than 1280 overlap-save tiles (the scratch bound of one GEMM problem): the levels are convolved one by one."""
     import torch
