@@ -365,9 +365,9 @@ def config_c5(fc, torch, peak, dist, world, rank):
                 a_flops=sum(nominal_flops_of(1, K, F, fh, fw) for fh, fw in planes) / world,
                 workload="10-level 31-channel HOG pyramid (sides 256..74) x 20000 templates 16x16x31 (BASELINE configs[4])",
                 scaling="strong", n_gpus=world, templates_per_gpu=e - b,
-                collective="NCCL broadcast of the 10 level spectra" if world > 1 else "none (1 GPU)",
-                api="fftconv_conv_pyramid: all ten levels x the rank's shard of the bank in one call (the tiles of all levels share "
-                    "the per-bin GEMM); the level spectra come from cudaFFTData on rank 0")
+                collective="NCCL broadcast of the raw pyramid (ten levels, one packed buffer of 19.7 MB)" if world > 1 else "none (1 GPU)",
+                api="fftconv_conv_pyramid: all ten raw levels x the rank's shard of the bank in one call (the tiles of all levels "
+                    "share the per-bin GEMM; no full-plane spectrum is formed)")
     del outs, bank, levels
     fc.lib().fftconv_release()
     torch.cuda.empty_cache()

@@ -60,11 +60,13 @@ def pyramid_convolution(levels: Optional[Sequence], max_kh: int, max_kw: int, n_
 
 def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Sequence[Tuple[int, int, int]],
                              bank_t, kh: int, kw: int, outs: Optional[List] = None, options=None, group=None,
-                             one_call: bool = True):
+                             one_call: bool = True, raw: bool = True):
     """CUDA instance of the schedule: level_tensors[l] float32 [F][W][H] on this rank's device (rank 0),
     bank_t float32 [K][F][kw][kh] — the FULL bank, identical on every rank; each rank convolves its shard.
     one_call (default): all levels x the shard through fftconv_conv_pyramid; False: one cudaConvFFTData-style call per
-    level (the reference caller's loop).  Returns (begin, end, [out_l float32 [end-begin][FW_l][FH_l]])."""
+    level (the reference caller's loop).  raw (default, with one_call): the raw levels are broadcast as one packed buffer and
+    tiled directly; False: rank 0 runs cudaFFTData per level and the ten spectra are broadcast (the two-call form).
+    Returns (begin, end, [out_l float32 [end-begin][FW_l][FH_l]])."""
     import torch
     import fftconv_b200 as fc
     K = int(bank_t.shape[0])
@@ -77,6 +79,32 @@ def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Se
     def alloc_spec(H, W, F):
         FH, FW = level_plane(H, W, kh, kw)
         return torch.empty((F, FW, FH // 2 + 1), dtype=torch.complex64, device=dev)
+
+    if one_call and raw:
+        # the overlap-save path tiles raw data, so what travels is the raw pyramid: ONE packed buffer (smaller than the ten
+        # spectra, one collective instead of ten), and no level is transformed to a full-plane spectrum anywhere
+        import torch.distributed as dist
+        from .sharding import shard_bank
+        on = dist.is_initialized()
+        world = dist.get_world_size(group) if on else 1
+        rank = dist.get_rank(group) if on else 0
+        b, e = shard_bank([1.0] * K, world)[rank]
+        sizes = [H * W * F for (H, W, F) in level_shapes]
+        if world > 1:
+            if rank == 0:
+                packed = torch.cat([t.reshape(-1) for t in level_tensors])
+            else:
+                packed = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
+            dist.broadcast(packed, src=0, group=group)
+            offs = [0]
+            for n in sizes:
+                offs.append(offs[-1] + n)
+            lv = [packed[offs[l]:offs[l + 1]].view(F, W, H) for l, (H, W, F) in enumerate(level_shapes)]
+        else:
+            lv = list(level_tensors)
+        if e == b:
+            return b, e, [outs[i] if outs is not None else None for i in range(len(level_shapes))]
+        return b, e, fc.conv_pyramid(lv, bank_t[b:e], kh, kw, outs=outs, options=options)
 
     if one_call:
         # fftconv_conv_pyramid: the spectra of all levels (transformed / received below) and the shard of the bank go
