@@ -15,10 +15,13 @@
 //                              code serves all four residues), operand-image store in plain fp32
 //   os_data_fft                overlap-save window gather (zero fill, circular wrap) -> 2-D spectrum -> B images
 //   os_gemm                    TMA bulk copies -> smem operand images -> tcgen05.mma (kind::tf32,
-//                              M=128 templates, N=2*tiles, K=2*F) -> TMEM -> bulk store of P
-//   os_inverse_tma             per (template, 4 tiles): TMA tensor copies gather the product spectra (box = 4 tiles x
-//                              64 columns), 2-D C2R inverse, valid-region store (crop / peak / correlation shift fused)
-//   os_inverse                 the same with a per-thread cp.async gather (fallback when no tensor map can be built)
+//                              M=128 templates, N=2*tiles, K=2*F) -> TMEM -> conflict-free padded staging tile -> one TMA
+//                              tensor store of P per item (pad columns clipped by the tensor bounds)
+//   os_inverse_z               per (template, 4 tiles): TMA tensor copies gather the product spectra into four independent
+//                              column zones, 2-D C2R inverse, valid-region store (crop / peak, threshold, top-k detection /
+//                              correlation shift / per-level geometry of a pyramid batch fused)
+//   os_inverse_tma, os_inverse earlier forms of the same kernel (one mbarrier for all boxes; per-thread cp.async gather):
+//                              fallbacks when the 5-D tensor maps / any tensor map cannot be built
 //   inv_w_pass                 (spectrum -> plane, when the caller hands in a cudaFFTData spectrum)
 //
 // Replaces the same reference rows as kernels_tile16.cuh (padData, cufftExecR2C,
