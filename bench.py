@@ -285,6 +285,39 @@ def config_c1(fc, torch, peak):
                    note="launch-latency bound: parity config, microseconds per call")
 
 
+def config_c2_ragged(fc, torch, peak):
+    """config 2, secondary run of SURVEY 8(d): template sizes differ per cell, kh, kw ~ U{6..16} iid, declared maximum
+    16 x 16; device-resident, one-shot entry point (the cell is marshalled once: fftconv_b200.DeviceCells)."""
+    H = W = 256; F = 31; K = 1000
+    rng = np.random.default_rng(2)
+    khs, kws = rng.integers(6, 17, K), rng.integers(6, 17, K)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    data = torch.rand((F, W, H), device="cuda", generator=g) * 0.2
+    pack = torch.randn((int((khs * kws).sum()) * F,), device="cuda", generator=g) * 0.05
+    offs = np.concatenate([[0], np.cumsum(khs * kws * F)])
+    cells = [pack[int(offs[k]):int(offs[k + 1])].view(F, int(kws[k]), int(khs[k])) for k in range(K)]
+    dc = fc.DeviceCells(cells, F)
+    FH, FW = fft16(H + 15), fft16(W + 15)
+    out = torch.empty((K, FW, FH), device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    step = lambda: fc.convolution_fft_device(data, dc, out, max_kh=16, max_kw=16)
+    ms = _median_ms(torch, step, 20, flush=flush)
+    rel = 0.0
+    for k in (0, 517, 999):
+        kk = torch.zeros((1, F, 16, 16), device="cuda")
+        kk[0, :, :int(kws[k]), :int(khs[k])] = cells[k]
+        ref = _ref64(torch, data, kk, FW, FH)
+        rel = max(rel, float((out[k:k + 1].double() - ref).norm() / ref.norm()))
+    a = 4 * H * W * F + 4 * F * int((khs * kws).sum()) + 4 * K * FH * FW
+    r = _record(K * FH * FW, ms, a, rel, peak, None, a_flops=nominal_flops_of(1, K, F, FH, FW),
+                workload="HOG-DPM secondary run: 256x256x31 x 1000 templates of kh, kw ~ U{6..16} iid (SURVEY 8d), declared maximum 16x16",
+                mean_template_area=float((khs * kws).mean()))
+    del data, pack, cells, dc, out, flush
+    fc.lib().fftconv_release()
+    torch.cuda.empty_cache()
+    return r
+
+
 def config_c3(fc, torch, peak):
     H = W = 4096; F = 1; kh = kw = 512; K = 64
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -803,7 +836,7 @@ def run_ours(args):
         torch.cuda.empty_cache()
         if world == 1 and args.workload == "c2":
             configs = {}
-            for name, fn in (("c1", config_c1), ("c3", config_c3), ("c4", config_c4)):
+            for name, fn in (("c1", config_c1), ("c2_ragged", config_c2_ragged), ("c3", config_c3), ("c4", config_c4)):
                 try:
                     configs[name] = fn(fc, torch, peak)
                 except Exception as ex:                              # a failing side config must not void the headline

@@ -135,7 +135,7 @@ struct Ctx {
     cudaStream_t side = nullptr;         // copy stream for the chunk pipeline
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaStream_t side2 = nullptr;        // data-side transforms of the overlap-save path run here, next to os_kern_fft
-    cudaEvent_t evf[2] = {nullptr, nullptr};
+    cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};   // [0..1] data side; [2..3] template transforms run ahead (OsAhead)
     int sm_count = 148;
     // Provenance of the last spectrum fftconv_fft_data produced on this device.  The overlap-save path works from the raw
     // data, not from the compat spectrum; a caller of the two-call interface hands the spectrum back, and inverting it to a
@@ -608,8 +608,10 @@ static bool os_config_tiles(OsCfg& g) {
 //                         1 (default): reuse the raw data; 2: also transform the tiles next to the forward transform
 //   FFTCONV_BP_CT         -1: large-plane path on the run-time-plan kernels only; v >= 0 (default 0): variant v of the
 //                         size-specialised kernels where one is instantiated for the line length (kernels_bigplane_ct.cuh)
+//   FFTCONV_OS_AHEAD      1 / 2: with several chunks of device-resident templates, os_kern_fft of chunk i + 1 runs on a side stream
+//                         (1: the high-priority one, 2: the copy stream) next to os_inverse_z of chunk i (default 0)
 //   FFTCONV_OS_PF         L2 prefetch distance of os_gemm's TMA producer in work items (default 0 = off: measured 0.21 -> 0.30 ms at config 2 with 6 items ahead, the prefetched lines fight the P stores for L2)
-struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache, bp_ct; };
+struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache, bp_ct, ahead; };
 static const OsEnv& os_env() {
     static const OsEnv e = [] {
         auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
@@ -626,6 +628,7 @@ static const OsEnv& os_env() {
         x.pf = geti("FFTCONV_OS_PF", 0);
         x.spec_cache = geti("FFTCONV_SPEC_CACHE", 1);
         x.bp_ct = geti("FFTCONV_BP_CT", 0);
+        x.ahead = geti("FFTCONV_OS_AHEAD", 0);
         return x;
     }();
     return e;
@@ -797,21 +800,39 @@ struct OsDetect {
     const float* bias = nullptr;           // [K] or nullptr
 };
 static int os_chunk_inverse(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, cudaStream_t st);
+// Template transforms of the NEXT chunk, run ahead of it: os_kern_fft(i + 1) only needs the A scratch, which is free as soon
+// as os_gemm(i) has finished -- so it is enqueued on a side stream behind os_gemm(i) and shares the SMs with os_inverse_z(i)
+// (one writes A at HBM speed, the other is bound by instruction issue and the wait for its boxes), and os_gemm(i + 1)
+// finds its A images ready.  Only for templates that are already resident on the device.
+struct OsAhead {
+    bool kern_done = false;              // this chunk's A images were produced by the previous chunk's run-ahead
+    const SrcDesc* next_descs = nullptr; // run ahead for the next chunk (nullptr: none)
+    int next_nk = 0;
+    cudaStream_t side = nullptr;
+};
+static int os_launch_kern_fft(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, const fftconv_options& opt, cudaStream_t st) {
+    const int ntblk = (nk + OS_TM - 1) / OS_TM;
+    OsKArgs a{};
+    a.descs = d_descs; a.nk = nk; a.F = g.F; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
+    a.flip = opt.correlate ? 1 : 0;
+    dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
+    ProfScope ps(PK_OS_KERN, st);
+    if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);
+    else os_kern_fft<2><<<grid, 256, os_kern_smem(2), st>>>(a);
+    LAUNCH_CHECK();
+    return 0;
+}
 static int os_chunk_detect(Ctx& c, const OsCfg& g, OsInvArgs a, int nk, const OsDetect& det, int k0, cudaStream_t st);
 static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, float* const* d_outptrs,
                     const fftconv_options& opt, cudaStream_t st, int out_img_stride = 0, const float* bankA = nullptr,
                     unsigned long long* peak_keys = nullptr, const int2* khw = nullptr, int H = 0, int W = 0,
-                    cudaEvent_t data_ready = nullptr, const OsDetect* det = nullptr, int det_k0 = 0) {
+                    cudaEvent_t data_ready = nullptr, const OsDetect* det = nullptr, int det_k0 = 0,
+                    const OsAhead* ahead = nullptr) {
     const int ntblk = (nk + OS_TM - 1) / OS_TM;
-    if (!bankA) {
-        OsKArgs a{};
-        a.descs = d_descs; a.nk = nk; a.F = g.F; a.img = (float*)c.osA.p; a.NKS = g.NKS; a.KC = g.KC;
-        a.flip = opt.correlate ? 1 : 0;
-        dim3 grid(ntblk * OS_TM / OS_KSL, g.NKS * g.KC);
-        ProfScope ps(PK_OS_KERN, st);
-        if (g.NFK == 1) os_kern_fft<1><<<grid, 256, os_kern_smem(1), st>>>(a);
-        else os_kern_fft<2><<<grid, 256, os_kern_smem(2), st>>>(a);
-        LAUNCH_CHECK();
+    if (!bankA && ahead && ahead->kern_done) {
+        CU(cudaStreamWaitEvent(st, c.evf[3], 0));                    // the A images of this chunk were transformed ahead
+    } else if (!bankA) {
+        if (int e = os_launch_kern_fft(c, g, d_descs, nk, opt, st)) return e;
     }
     if (data_ready) CU(cudaStreamWaitEvent(st, data_ready, 0));      // B images of this call are complete
     {
@@ -838,6 +859,12 @@ static int os_chunk(Ctx& c, const OsCfg& g, const SrcDesc* d_descs, int nk, floa
             os_gemm<<<grid, 320, g.gemm_smem, st>>>(a, pmap);
         }
         LAUNCH_CHECK();
+    }
+    if (ahead && ahead->next_descs && !bankA) {
+        CU(cudaEventRecord(c.evf[2], st));                           // os_gemm(i) done: the A scratch is free
+        CU(cudaStreamWaitEvent(ahead->side, c.evf[2], 0));
+        if (int e = os_launch_kern_fft(c, g, ahead->next_descs, ahead->next_nk, opt, ahead->side)) return e;
+        CU(cudaEventRecord(c.evf[3], ahead->side));                  // joined by the next chunk before its os_gemm
     }
     {
         OsInvArgs a{};
@@ -1531,6 +1558,9 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
     CU(cudaMemcpyAsync(c.desc.p, h_desc, desc_bytes, cudaMemcpyHostToDevice, st));
     if (int e = pinned_done(c, st)) return e;
 
+    // template transforms of chunk i + 1 next to the inverse of chunk i (OsAhead): device-resident templates, device outputs
+    const int ahead_mode = (osg && !a.bankA && a.out_on_device && host_kernel_bytes == 0 && !a.det.mode && bounds.size() > 2)
+                               ? os_env().ahead : 0;
     // ---- chunk loop.  Device outputs: one stream.  Host outputs: the D2H of chunk i runs on the
     // side stream while chunk i+1 uploads its kernels and computes (double-buffered out staging).
     for (size_t chunk = 0; chunk + 1 < bounds.size(); ++chunk) {
@@ -1549,11 +1579,18 @@ static int run_conv(Ctx& c, const ConvArgs& a, cudaStream_t st) {
         }
         if (!a.out_on_device && chunk >= 2) CU(cudaStreamWaitEvent(st, c.ev[chunk & 1], 0));   // staging half free?
         int e;
-        if (osg)
+        if (osg) {
+            OsAhead ah;
+            if (ahead_mode) {
+                ah.kern_done = chunk > 0;
+                ah.side = ahead_mode == 2 ? c.side : c.side2;
+                if (chunk + 2 < bounds.size()) { ah.next_descs = d_desc + bounds[chunk + 1]; ah.next_nk = bounds[chunk + 2] - bounds[chunk + 1]; }
+            }
             e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, a.opt, st, K,
                          a.bankA ? a.bankA + (size_t)(k0 / OS_TM) * OS_NBIN * og.NKS * (og.a_stage / 8) : nullptr,
                          a.peak_keys ? a.peak_keys + k0 : nullptr, (a.bank_khw ? a.bank_khw : d_khw) + k0, a.rawH, a.rawW,
-                         (chunk == 0 && !a.bankA) ? c.evf[1] : nullptr, &a.det, k0);
+                         (chunk == 0 && !a.bankA) ? c.evf[1] : nullptr, &a.det, k0, ahead_mode ? &ah : nullptr);
+        }
         else if (tile16)
             e = tile16_chunk(c, FH, FW, F, maxkh, maxkw, d_desc + k0, nk, d_outp + k0, a.opt, st);
         else if (bigp)

@@ -460,28 +460,60 @@ def conv_bank(spec_t, bank_t, kh: int, kw: int, out_t=None, options: Optional[Op
     return out_t
 
 
-def convolution_fft_device(data_t, bank_t, out_t=None, options: Optional[Options] = None, stream=None, data_ready=None):
+class DeviceCells:
+    """A kernel cell resident on the device, marshalled once: K float32 tensors [F][kw_k][kh_k] whose sizes may differ per
+    template (the gpuArray cells of src/cudaConvFFTData.cu:204-231).  Holds the pointer / size arrays of the C ABI so that a
+    repeated call costs no per-template Python work."""
+
+    def __init__(self, cells, F: int):
+        for t in cells:
+            if t.dim() != 3 or int(t.shape[0]) != F or not t.is_contiguous() or str(t.dtype) != "torch.float32" or not t.is_cuda:
+                raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        self.K = len(cells)
+        self.F = F
+        self.keep = list(cells)
+        self.kws = np.array([int(t.shape[1]) for t in cells], dtype=np.int32).reshape(-1)
+        self.khs = np.array([int(t.shape[2]) for t in cells], dtype=np.int32).reshape(-1)
+        self.ptrs = np.array([t.data_ptr() for t in cells], dtype=np.uint64).reshape(-1)
+        self.max_kh = int(self.khs.max(initial=1))
+        self.max_kw = int(self.kws.max(initial=1))
+
+
+def convolution_fft_device(data_t, bank_t, out_t=None, options: Optional[Options] = None, stream=None, data_ready=None,
+                           max_kh: Optional[int] = None, max_kw: Optional[int] = None):
     """cudaConvolutionFFT with everything resident on the device (fftconv_convolution_fft, src/cudaConvolutionFFT.cu:27-311
     is its host-buffer original): data_t float32 [F][W][H], bank_t float32 [K][F][kw][kh] (kh x kw is also the declared
     maximum template size) -> out_t [K][FW][FH].  One call: on the overlap-save path the raw data is tiled directly and
     no full-plane spectrum is ever formed.  Stream-ordered, no host sync.
+    bank_t may also be a DeviceCells (or a list of K device tensors [F][kw_k][kh_k]): template sizes that differ per cell,
+    as the reference's kernel cell allows; max_kh x max_kw is then the declared maximum (default: the largest template).
     data_ready: torch.cuda.Event recorded behind whatever is still filling data_t on ANOTHER stream (a peer delivery over
     NVLink, fftconv_spectrum_ready_event): only the data-side work waits for it, the template transforms start at once."""
     torch = _torch()
     F, W, H = (int(x) for x in data_t.shape)
-    K, Fk, kw, kh = (int(x) for x in bank_t.shape)
-    if Fk != F:
-        raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+    if isinstance(bank_t, (list, tuple)):
+        bank_t = DeviceCells(bank_t, F)
+    if isinstance(bank_t, DeviceCells):
+        if bank_t.F != F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        K, kp, khs, kws = bank_t.K, bank_t.ptrs, bank_t.khs, bank_t.kws
+        kh = int(max_kh) if max_kh is not None else bank_t.max_kh
+        kw = int(max_kw) if max_kw is not None else bank_t.max_kw
+    else:
+        K, Fk, kw, kh = (int(x) for x in bank_t.shape)
+        if Fk != F:
+            raise FFTConvError(ERRID_CONV, MSG_KERNEL_SHAPE, -5)
+        kp = np.uint64(bank_t.data_ptr()) + np.uint64(4 * F * kw * kh) * np.arange(K, dtype=np.uint64)
+        khs = np.full(K, kh, dtype=np.int32)
+        kws = np.full(K, kw, dtype=np.int32)
+        kh = int(max_kh) if max_kh is not None else kh
+        kw = int(max_kw) if max_kw is not None else kw
     FH, FW = computeFFTsize16(H + kh - 1), computeFFTsize16(W + kw - 1)
     dev = int(data_t.device.index or 0)
     if out_t is None:
         out_t = torch.empty((K, FW, FH), dtype=torch.float32, device=data_t.device)
-    ks = np.arange(K, dtype=np.uint64)
-    kp = np.uint64(bank_t.data_ptr()) + np.uint64(4 * F * kw * kh) * ks
-    op = np.uint64(out_t.data_ptr()) + np.uint64(4 * FW * FH) * ks
-    khs = np.full(K, kh, dtype=np.int32)
-    kws = np.full(K, kw, dtype=np.int32)
-    ond = np.ones(K, dtype=np.uint8)
+    op = np.uint64(out_t.data_ptr()) + np.uint64(4 * FW * FH) * np.arange(K, dtype=np.uint64)
+    ond = np.ones(max(K, 1), dtype=np.uint8)
     st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
     o = ctypes.byref(options) if options is not None else None
     if data_ready is not None:

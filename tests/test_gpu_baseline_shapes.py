@@ -51,6 +51,33 @@ def test_c2_full_bank_device_outputs(fc, oracle):
         assert oracle.rel_l2(out[k].cpu().numpy().T, ref) < TOL, k
 
 
+def test_c2_ragged_bank_device_cells(fc, oracle):
+    """config 2, secondary run of SURVEY 8(d): 1000 templates whose sizes differ per cell, kh, kw ~ U{6..16} iid
+    (src/cudaConvFFTData.cu:204-231 reads the size of every cell), declared maximum 16 x 16, everything on the device,
+    one-shot entry point on the overlap-save / tcgen05 pipeline."""
+    import torch
+    rng = np.random.default_rng(22)
+    data = (rng.random((256, 256, 31), dtype=np.float32) * 0.2).astype(np.float32)
+    khs, kws = rng.integers(6, 17, 1000), rng.integers(6, 17, 1000)
+    khs[0], kws[0], khs[999], kws[999] = 6, 16, 16, 6
+    cells = [(rng.standard_normal((int(a), int(b), 31)) * 0.05).astype(np.float32) for a, b in zip(khs, kws)]
+    d_t = torch.from_numpy(np.ascontiguousarray(data.transpose(2, 1, 0))).cuda()
+    c_t = [torch.from_numpy(np.ascontiguousarray(k.transpose(2, 1, 0))).cuda() for k in cells]
+    dc = fc.DeviceCells(c_t, 31)
+    assert (dc.max_kh, dc.max_kw) == (16, 16)
+    out = torch.full((1000, 272, 272), float("nan"), device="cuda")
+    prof = _profiled_kernels(fc, lambda: fc.convolution_fft_device(d_t, dc, out, max_kh=16, max_kw=16))
+    assert {"os_data_fft(tiles)", "os_kern_fft(templates)", "os_gemm", "os_inverse"} <= set(prof), prof
+    assert not bool(torch.isnan(out).any())
+    for k in C2_PLANES:
+        ref = oracle.direct_conv64_c(data, cells[k], 272, 272)
+        assert oracle.rel_l2(out[k].cpu().numpy().T, ref) < TOL, (k, cells[k].shape)
+    # the same cell through the reference-facing host entry point gives the same planes (bit for bit: same pipeline)
+    outs = fc.cudaConvolutionFFT(data, 16, 16, [cells[k] for k in (0, 500, 999)] * 22)      # 66 templates: overlap-save path
+    for i, k in enumerate((0, 500, 999)):
+        assert oracle.rel_l2(outs[i], oracle.direct_conv64_c(data, cells[k], 272, 272)) < TOL
+
+
 @pytest.mark.parametrize("entry", ["cudaConvolutionFFT", "cudaConvFFTData", "cudaConvFFTDataStreams"])
 def test_c2_full_bank_host_outputs(fc, oracle, entry):
     """config 2 as bench.py's `e2e` leg runs it: host kernels in, 1000 pageable host planes out (the MEX contract,
