@@ -199,3 +199,24 @@ def test_c5_all_pyramid_levels(fc, oracle, prepared):
             assert oracle.rel_l2(outs[k], ref) < TOL, (side, k)
     if bank is not None:
         bank.close()
+
+
+@pytest.mark.parametrize("ntblk,ahead", [(2, 0), (2, 1), (3, 2)])
+def test_c2_chunked_schedules_in_a_fresh_process(ntblk, ahead):
+    """Several chunks of device-resident templates, with and without the template transforms of chunk i + 1 running ahead
+    on a side stream (OsAhead in csrc/fftconv.cu; FFTCONV_OS_NTBLK / FFTCONV_OS_AHEAD are read once per process, hence the
+    subprocess).  scripts/oneshot_time.py checks planes at every chunk boundary against the float64 FFT convolution."""
+    import os
+    import re
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FFTCONV_OS_NTBLK=str(ntblk), FFTCONV_OS_AHEAD=str(ahead))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "oneshot_time.py"), "1000", "2"], env=env,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    m = re.search(r"max rel-L2 over \d+ planes ([0-9.e+-]+) nan=(\w+)", r.stdout)
+    assert m, r.stdout[-2000:]
+    assert float(m.group(1)) < TOL and m.group(2) == "False", r.stdout[-500:]
+    nchunks = -(-1000 // (128 * ntblk))
+    assert re.search(rf"os_gemm=[0-9.]+x{nchunks}\b", r.stdout), r.stdout[-500:]      # one per-bin GEMM per chunk
