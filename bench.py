@@ -382,7 +382,7 @@ def config_c5(fc, torch, peak, dist, world, rank):
     levels = [torch.rand((F, s, s), device="cuda", generator=g) * 0.2 for s in sides]     # same seed on every rank
     bank = torch.randn((K, F, kw, kh), device="cuda", generator=g) * 0.05
     shapes = [(s, s, F) for s in sides]
-    b, e = shard_bank([1.0] * K, world)[rank]
+    b, e = shard_bank(None, world, K)[rank]
     outs = [torch.empty((e - b,) + level_plane(s, s, kh, kw)[::-1], device="cuda") for s in sides]
     step = lambda: pyramid_convolution_cuda(levels if rank == 0 else None, shapes, bank, kh, kw, outs)
     ms = _median_ms(torch, step, 3, dist if world > 1 else None)
@@ -398,7 +398,8 @@ def config_c5(fc, torch, peak, dist, world, rank):
                 a_flops=sum(nominal_flops_of(1, K, F, fh, fw) for fh, fw in planes) / world,
                 workload="10-level 31-channel HOG pyramid (sides 256..74) x 20000 templates 16x16x31 (BASELINE configs[4])",
                 scaling="strong", n_gpus=world, templates_per_gpu=e - b,
-                collective="NCCL broadcast of the raw pyramid (ten levels, one packed buffer of 19.7 MB)" if world > 1 else "none (1 GPU)",
+                collective=(f"NCCL broadcast of the raw pyramid (ten levels, one packed buffer of {sum(4 * s * s * F for s in sides) / 1e6:.1f} MB) "
+                            "on a side stream, next to the first chunk's template transforms") if world > 1 else "none (1 GPU)",
                 api="fftconv_conv_pyramid: all ten raw levels x the rank's shard of the bank in one call (the tiles of all levels "
                     "share the per-bin GEMM; no full-plane spectrum is formed)")
     del outs, bank, levels

@@ -1958,7 +1958,7 @@ int fftconv_conv_batch(const float* data, int data_on_device, int N, int H, int 
 struct PyrLevel { const float* d_raw; const cpx* d_spec; int H, W, FH, FW; };
 
 static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh, int maxkw, int K, const KernelRef* kernels,
-                            float* const* outs, const fftconv_options& opt, cudaStream_t st) {
+                            float* const* outs, const fftconv_options& opt, cudaStream_t st, cudaEvent_t data_ready = nullptr) {
     OsCfg og;
     if (!os_config(F, 64, 64, maxkh, maxkw, og)) return fail(FFTCONV_ERR_UNSUPPORTED, "pyramid batch needs templates of at most 32 x 32");
     std::vector<OsLevel> hl((size_t)L);
@@ -2042,7 +2042,13 @@ static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh,
     og.d_levels = reinterpret_cast<const OsLevel*>(d_tab);
     og.nlevels = L;
 
-    // ---- data side: spectrum -> plane for the levels that arrive as cudaFFTData spectra, then one tiling launch
+    // ---- data side: spectrum -> plane for the levels that arrive as cudaFFTData spectra, then one tiling launch.  None of it
+    // depends on the bank: it runs on the side stream next to the first os_kern_fft (as in run_conv) and is the only work
+    // that waits for a pyramid still in flight on another stream (data_ready: fftconv_spectrum_ready_event).
+    cudaStream_t ds = c.side2;
+    CU(cudaEventRecord(c.evf[0], st));                                 // the descriptor tables are on their way
+    CU(cudaStreamWaitEvent(ds, c.evf[0], 0));
+    if (data_ready) CU(cudaStreamWaitEvent(ds, data_ready, 0));
     {
         float** d_pl = reinterpret_cast<float**>(d_tab + off_pl);
         int pi = 0;
@@ -2050,19 +2056,19 @@ static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh,
             if (lv[l].d_raw) continue;
             const int FH = lv[l].FH, FW = lv[l].FW, CH = FH / 2 + 1;
             const cpx *twH, *twW;
-            if (int e = get_twiddles(c, FH, st, &twH)) return e;
-            if (int e = get_twiddles(c, FW, st, &twW)) return e;
+            if (int e = get_twiddles(c, FH, ds, &twH)) return e;
+            if (int e = get_twiddles(c, FW, ds, &twW)) return e;
             const LinePlan pH = make_line_plan(FH), pW = make_line_plan(FW);
             const int ldH = odd_ld(FH), ldW = odd_ld(FW);
-            ProfScope ps(PK_OS_PLANE, st);
+            ProfScope ps(PK_OS_PLANE, ds);
             int TU = (int)((96 * 1024) / (2 * (size_t)ldW * sizeof(cpx)));
             TU = TU < 1 ? 1 : (TU > 16 ? 16 : TU);
             dim3 g2((CH + TU - 1) / TU, F);
-            inv_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), st>>>(lv[l].d_spec, FW, CH, pW, twW, (cpx*)c.osZ.p, TU, ldW, nullptr);
+            inv_w_pass<<<g2, 256, 2 * (size_t)TU * ldW * sizeof(cpx), ds>>>(lv[l].d_spec, FW, CH, pW, twW, (cpx*)c.osZ.p, TU, ldW, nullptr);
             LAUNCH_CHECK();
             const int NL = pick_lines(FH, 8);
             const long long nlines = (long long)F * (FW / 2);
-            inv_h_pass<<<(unsigned)((nlines + NL - 1) / NL), 256, 2 * (size_t)NL * ldH * sizeof(cpx), st>>>(
+            inv_h_pass<<<(unsigned)((nlines + NL - 1) / NL), 256, 2 * (size_t)NL * ldH * sizeof(cpx), ds>>>(
                 (const cpx*)c.osZ.p, F, FH, FW, CH, pH, twH, 1.0f / ((float)FW * (float)FH), d_pl + pi, FH, FW, FH, NL, ldH, nullptr);
             LAUNCH_CHECK();
             pi += F;
@@ -2074,17 +2080,19 @@ static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh,
         a.correlate = 0;
         c.sc.b_valid = false; ++c.osB_gen;                             // the B images now belong to this call
         const unsigned grid = (unsigned)NT * (unsigned)(og.NKS * og.KC);
-        ProfScope ps(PK_OS_DATA, st);
-        os_data_fft<<<grid, 128, OS_DATA_SMEM, st>>>(a);
+        ProfScope ps(PK_OS_DATA, ds);
+        os_data_fft<<<grid, 128, OS_DATA_SMEM, ds>>>(a);
         LAUNCH_CHECK();
     }
+    CU(cudaEventRecord(c.evf[1], ds));                                 // joined by the first chunk in front of its os_gemm
     // ---- template chunks
     const SrcDesc* d_desc = reinterpret_cast<const SrcDesc*>(d_tab + off_desc);
     float* const* d_outp = reinterpret_cast<float* const*>(d_tab + off_outp);
     const int2* d_khw = reinterpret_cast<const int2*>(d_tab + off_khw);
     for (int k0 = 0; k0 < K; k0 += KC) {
         const int nk = std::min(KC, K - k0);
-        if (int e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, opt, st, K, nullptr, nullptr, d_khw + k0, 0, 0, nullptr, nullptr, 0))
+        if (int e = os_chunk(c, og, d_desc + k0, nk, d_outp + k0, opt, st, K, nullptr, nullptr, d_khw + k0, 0, 0,
+                             k0 == 0 ? c.evf[1] : nullptr, nullptr, 0))
             return e;
     }
     return 0;
@@ -2095,6 +2103,14 @@ int fftconv_conv_pyramid(int L, const float* const* level_data, const fftconv_fl
                          const int* kw, const int* kf, const unsigned char* kernel_on_device, float* const* outs,
                          const fftconv_options* opt, int device, void* stream) {
     g_err.clear();
+    // one-shot event of fftconv_spectrum_ready_event: the levels are still arriving on another stream (an NCCL broadcast of
+    // the packed pyramid); it belongs to THIS call whatever its outcome
+    cudaEvent_t data_ready = nullptr;
+    {
+        Ctx* c0 = nullptr;
+        { std::lock_guard<std::mutex> lk(g_mu); auto it = g_ctx.find(device); if (it != g_ctx.end()) c0 = &it->second; }
+        if (c0) { std::lock_guard<std::recursive_mutex> lkc(c0->mu); data_ready = c0->spec_ready; c0->spec_ready = nullptr; }
+    }
     if (L <= 0 || L > OS_MAX_LEVELS || !H || !W || F <= 0 || maxKH <= 0 || maxKW <= 0 || (!level_data && !level_spec))
         return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid data input");
     if (K > 0 && (!kernels || !kh || !kw || !outs)) return fail(FFTCONV_ERR_INVALID_INPUT, "Invalid input to MEX file.");
@@ -2126,10 +2142,11 @@ int fftconv_conv_pyramid(int L, const float* const* level_data, const fftconv_fl
                          o.crop_h <= 0 && o.crop_w <= 0 && o.out_ld <= 0 && maxkh <= maxKH && maxkw <= maxKW &&
                          os_config(F, 64, 64, maxkh, maxkw, g1);
     if (batched) {
-        const int e = run_conv_pyramid(*cs.c, L, lv.data(), F, maxkh, maxkw, K, refs.data(), outs, o, (cudaStream_t)stream);
+        const int e = run_conv_pyramid(*cs.c, L, lv.data(), F, maxkh, maxkw, K, refs.data(), outs, o, (cudaStream_t)stream, data_ready);
         if (e != FFTCONV_ERR_UNSUPPORTED) return e;
         g_err.clear();
     }
+    if (data_ready) CU(cudaStreamWaitEvent((cudaStream_t)stream, data_ready, 0));   // level by level: everything waits
     for (int l = 0; l < L; ++l) {                   // level by level through the single-image entry points
         const PyrLevel& p = lv[(size_t)l];
         int e;

@@ -552,13 +552,16 @@ def conv_batch(data_t, bank_t, out_t=None, options: Optional[Options] = None, st
 
 
 def conv_pyramid(levels, bank_t, kh: int, kw: int, outs=None, specs=None, shapes=None,
-                 options: Optional[Options] = None, stream=None):
+                 options: Optional[Options] = None, stream=None, data_ready=None):
     """Feature pyramid x one device-resident bank in ONE call (fftconv_conv_pyramid, BASELINE config 5).
 
     levels   list of float32 torch tensors [F][W_l][H_l] on the device -- or None when every level arrives as a spectrum
     specs    optional list of complex64 [F][FW_l][CH_l] spectra from fft_data_device (used where levels is None / levels[l] is None);
              `shapes` = [(H_l, W_l)] is then required
     bank_t   float32 [K][F][kw][kh] on the device; kh x kw is also the declared maximum template size
+    data_ready: torch.cuda.Event recorded behind whatever is still filling the levels on ANOTHER stream (the NCCL broadcast
+             of the packed pyramid, fftconv_spectrum_ready_event): only the data-side work waits for it, the template
+             transforms of the first chunk start at once.
     Returns [out_l float32 [K][FW_l][FH_l]] (allocated here unless `outs` is given).  Stream-ordered, no host sync."""
     torch = _torch()
     K, F, kw_, kh_ = (int(x) for x in bank_t.shape)
@@ -588,6 +591,8 @@ def conv_pyramid(levels, bank_t, kh: int, kw: int, outs=None, specs=None, shapes
     ond = np.ones(K, dtype=np.uint8)
     st = _stream_ptr(stream) if stream is not None else torch.cuda.current_stream(dev).cuda_stream
     o = ctypes.byref(options) if options is not None else None
+    if data_ready is not None:
+        _check(lib().fftconv_spectrum_ready_event(dev, ctypes.c_void_p(data_ready.cuda_event)), ERRID_CONV)
     rc = lib().fftconv_conv_pyramid(L, dp if levels is not None else None, sp, Hs, Ws, F, kh, kw, K, kp.ctypes.data,
                                     khs.ctypes.data, kws.ctypes.data, None, ond.ctypes.data, op.ctypes.data, o, dev, st)
     _check(rc, ERRID_CONV)

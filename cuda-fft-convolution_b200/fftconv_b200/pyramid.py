@@ -43,7 +43,7 @@ def pyramid_convolution(levels: Optional[Sequence], max_kh: int, max_kw: int, n_
     on = dist.is_initialized()
     world = dist.get_world_size(group) if on else 1
     rank = dist.get_rank(group) if on else 0
-    b, e = shard_bank(list(costs) if costs is not None else [1.0] * n_templates, world)[rank]
+    b, e = shard_bank(list(costs) if costs is not None else None, world, n_templates)[rank]
     specs, pending = [], []
     for l, (H, W, F) in enumerate(level_shapes):
         spec = fft_fn(levels[l], max_kh, max_kw) if rank == 0 else alloc_spec(H, W, F)
@@ -56,6 +56,18 @@ def pyramid_convolution(levels: Optional[Sequence], max_kh: int, max_kw: int, n_
             pending[l].wait()             # stream-ordered on CUDA: later levels keep arriving during compute
         results.append(conv_fn(l, spec, b, e))
     return b, e, results
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev):
+    """One side stream per device for collectives that run next to the template transforms."""
+    import torch
+    key = str(dev)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
+    return _SIDE_STREAMS[key]
 
 
 def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Sequence[Tuple[int, int, int]],
@@ -88,14 +100,24 @@ def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Se
         on = dist.is_initialized()
         world = dist.get_world_size(group) if on else 1
         rank = dist.get_rank(group) if on else 0
-        b, e = shard_bank([1.0] * K, world)[rank]
+        b, e = shard_bank(None, world, K)[rank]
         sizes = [H * W * F for (H, W, F) in level_shapes]
+        ready = None
         if world > 1:
             if rank == 0:
                 packed = torch.cat([t.reshape(-1) for t in level_tensors])
             else:
                 packed = torch.empty(sum(sizes), dtype=torch.float32, device=dev)
-            dist.broadcast(packed, src=0, group=group)
+            # the broadcast runs behind a side stream: the call below makes only its data-side work wait for it, so the
+            # pyramid travels over NVLink while the first chunk of templates is being transformed
+            cur = torch.cuda.current_stream(dev)
+            side = _side_stream(dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                dist.broadcast(packed, src=0, group=group)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            packed.record_stream(side)
             offs = [0]
             for n in sizes:
                 offs.append(offs[-1] + n)
@@ -103,8 +125,10 @@ def pyramid_convolution_cuda(level_tensors: Optional[Sequence], level_shapes: Se
         else:
             lv = list(level_tensors)
         if e == b:
+            if ready is not None:
+                torch.cuda.current_stream(dev).wait_event(ready)
             return b, e, [outs[i] if outs is not None else None for i in range(len(level_shapes))]
-        return b, e, fc.conv_pyramid(lv, bank_t[b:e], kh, kw, outs=outs, options=options)
+        return b, e, fc.conv_pyramid(lv, bank_t[b:e], kh, kw, outs=outs, options=options, data_ready=ready)
 
     if one_call:
         # fftconv_conv_pyramid: the spectra of all levels (transformed / received below) and the shard of the bank go

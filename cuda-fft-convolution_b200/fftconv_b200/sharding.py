@@ -12,25 +12,26 @@ from __future__ import annotations
 from typing import Callable, List, Optional, Sequence, Tuple
 
 
-def shard_bank(costs: Sequence[float], world: int) -> List[Tuple[int, int]]:
+def shard_bank(costs: Optional[Sequence[float]], world: int, K: Optional[int] = None) -> List[Tuple[int, int]]:
     """Split templates 0..K-1 into `world` contiguous ranges of near-equal total cost.
 
-    costs[k] ~ kh*kw of template k (uniform costs give K/world each).  Returns [(begin, end)] per rank;
-    ranges are contiguous, ordered, cover 0..K exactly, and may be empty when K < world."""
-    K = len(costs)
+    costs[k] ~ kh*kw of template k (uniform costs give K/world each; costs=None with K given means uniform).  Returns
+    [(begin, end)] per rank; ranges are contiguous, ordered, cover 0..K exactly, and may be empty when K < world.
+    Rank r ends at the first template whose cost midpoint lies beyond r/world of the total.  Vectorised: the schedule calls
+    this inside its step, and a Python loop over a bank of 20 000 templates cost more than the NCCL broadcast next to it."""
+    import numpy as np
     if world <= 0:
         raise ValueError("world must be positive")
-    total = float(sum(costs))
-    bounds = [0]
-    acc = 0.0
-    k = 0
-    for r in range(1, world):
-        target = total * r / world
-        while k < K and acc + costs[k] / 2.0 <= target:
-            acc += costs[k]
-            k += 1
-        bounds.append(k)
-    bounds.append(K)
+    c = np.ones(int(K), dtype=np.float64) if costs is None else np.asarray(costs, dtype=np.float64).reshape(-1)
+    K = int(c.size)
+    if K == 0:
+        return [(0, 0)] * world
+    prefix = np.cumsum(c)
+    total = float(prefix[-1])
+    mid = prefix - c / 2.0                                   # cost below template k plus half of its own
+    targets = total * np.arange(1, world, dtype=np.float64) / world
+    inner = np.searchsorted(mid, targets, side="right")      # mid is non-decreasing for non-negative costs
+    bounds = [0] + [int(b) for b in np.maximum.accumulate(inner)] + [K]
     return [(bounds[r], bounds[r + 1]) for r in range(world)]
 
 

@@ -21,7 +21,7 @@ levels = [torch.rand((F, s, s), device="cuda", generator=g) * 0.2 for s in sides
 bank = torch.randn((K, F, kw, kh), device="cuda", generator=g) * 0.05                       # the full bank on every rank
 shapes = [(s, s, F) for s in sides]
 from fftconv_b200.sharding import shard_bank
-b, e = shard_bank([1.0] * K, world)[rank]
+b, e = shard_bank(None, world, K)[rank]
 outs = [torch.empty((e - b,) + level_plane(s, s, kh, kw)[::-1], device="cuda") for s in sides]
 
 def step():

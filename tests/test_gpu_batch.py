@@ -134,6 +134,46 @@ def test_conv_pyramid_edge_shapes(fc, oracle, L, K, F, kh, kw):
             assert oracle.rel_l2(got[k].T, ref) < TOL, (l, k)
 
 
+@pytest.mark.parametrize("fallback", [False, True])
+def test_conv_pyramid_waits_for_levels_still_in_flight(fc, oracle, fallback):
+    """data_ready (fftconv_spectrum_ready_event): the levels are filled on ANOTHER stream behind a long-running kernel -- the
+    NCCL broadcast of the packed pyramid in the multi-GPU schedule -- and only the data side of the call waits for them.
+    The level buffers hold NaN until that stream writes them, so a call that did not wait cannot pass.
+    fallback: 40-wide templates, which take the level-by-level route (there the whole call waits)."""
+    import torch
+    rng = np.random.default_rng(61)
+    F, K = 5, 130
+    kh, kw = (40, 9) if fallback else (16, 12)
+    shapes = [(90, 75), (64, 64), (47, 53)]
+    levels = [rng.random((H, W, F), dtype=np.float32) for (H, W) in shapes]
+    bank = (rng.standard_normal((K, kh, kw, F)) * 0.1).astype(np.float32)
+    src = [torch.from_numpy(np.ascontiguousarray(lv.transpose(2, 1, 0))).cuda() for lv in levels]
+    bt = torch.from_numpy(np.ascontiguousarray(bank.transpose(0, 3, 2, 1))).cuda()
+    lt = [torch.full_like(t, float("nan")) for t in src]
+    side = torch.cuda.Stream()
+    busy = torch.empty(64 << 20, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        for _ in range(40):                                   # some milliseconds of work in front of the fill
+            busy.mul_(1.0001)
+        for d, t in zip(lt, src):
+            d.copy_(t, non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(side)
+    outs = fc.conv_pyramid(lt, bt, kh, kw, data_ready=ready)
+    torch.cuda.synchronize()
+    for l, (H, W) in enumerate(shapes):
+        FH, FW = fc.computeFFTsize16(H + kh - 1), fc.computeFFTsize16(W + kw - 1)
+        got = outs[l].cpu().numpy()
+        assert not np.isnan(got).any(), l
+        for k in (0, K - 1):
+            assert oracle.rel_l2(got[k].T, oracle.direct_conv64_c(levels[l], bank[k], FH, FW)) < TOL, (l, k)
+    # the event was one-shot: the next call does not wait for (or touch) it
+    outs2 = fc.conv_pyramid(src, bt, kh, kw)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(outs, outs2))
+
+
 def test_conv_pyramid_too_many_tiles_goes_level_by_level(fc, oracle):
     """more than 1280 overlap-save tiles (the scratch bound of one GEMM problem): the levels are convolved one by one."""
     import torch
