@@ -1,7 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 50 --warmup 3 > gpurun_out/r02d_bench_n8.json 2> gpurun_out/r02d_bench_n8.err
+R=${1:-r02e}
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 8 --steps 50 --warmup 3 > gpurun_out/${R}_bench_n8.json 2> gpurun_out/${R}_bench_n8.err
 python -c "
-import json; d=json.loads(open('gpurun_out/r02d_bench_n8.json').read().strip().splitlines()[-1]); print('n8', d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['config'].get('parallelism')); print(json.dumps((d.get('extras') or {}).get('c5'))[:500])" || tail -12 gpurun_out/r02d_bench_n8.err
-CUDA_VISIBLE_DEVICES=0 python bench.py --no-cpu --no-configs --no-extras 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('single gpu same box', d['ms_per_step'], d['value'])"
+import json; d=json.loads(open('gpurun_out/${R}_bench_n8.json').read().strip().splitlines()[-1]); print('n8', d['value'], d['ms_per_step'], d['e2e']['ms_per_step'], d['config'].get('parallelism')); print(json.dumps((d.get('extras') or {}).get('c5'))[:700])" || tail -12 gpurun_out/${R}_bench_n8.err
