@@ -139,7 +139,10 @@ int fftconv_spectrum_bind_raw(const fftconv_float2* d_spec, const float* d_raw, 
  * outs[l*K + k], a device buffer of FW_l*FH_l floats (FH_l = computeFFTsize16(H[l] + maxKH - 1), ...).  With templates
  * up to 32 x 32 the overlap-save tiles of ALL levels form one N dimension of the per-frequency-bin complex GEMM: the
  * template spectra are computed and streamed once per call instead of once per level.  Otherwise (or with
- * correlate / crop options) the call is L calls of the single-image entry points.  Stream-ordered. */
+ * correlate / crop options) the call is L calls of the single-image entry points.  Stream-ordered.
+ * Levels that are still being delivered on another stream (the NCCL broadcast of the packed pyramid in the multi-GPU
+ * schedule, fftconv_b200/pyramid.py): hand the delivery's event to fftconv_spectrum_ready_event first -- only the data
+ * side of this call waits for it, the template transforms of the first chunk start at once. */
 int fftconv_conv_pyramid(int L, const float* const* level_data, const fftconv_float2* const* level_spec,
                          const int* H, const int* W, int F, int maxKH, int maxKW,
                          int K, const float* const* kernels, const int* kh, const int* kw,
@@ -226,7 +229,8 @@ int fftconv_modulate_and_normalize(fftconv_float2* d_a, const fftconv_float2* d_
  * cudaMemcpyPeerAsync): when the spectrum is being delivered by a collective on ANOTHER stream (an NCCL broadcast),
  * hand its completion event (cudaEvent_t) to the library.  The next convolution call on `device` then makes only its
  * data-side work wait for the event; the template transforms, which do not depend on the image, start at once on the
- * call stream, so the broadcast travels over NVLink in their shadow.  One-shot: consumed by that call. */
+ * call stream, so the broadcast travels over NVLink in their shadow.  One-shot: consumed by that call
+ * (fftconv_conv_fft_data / fftconv_conv_bank / fftconv_convolution_fft / fftconv_conv_pyramid). */
 int fftconv_spectrum_ready_event(int device, void* cuda_event);
 
 /* PEER SPECTRUM — the multi-GPU plans of src/cudaConvFFTDataStreams.cu:279-289 copy the spectrum GPU 0 -> GPU i with
