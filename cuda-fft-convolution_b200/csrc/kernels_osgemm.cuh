@@ -505,6 +505,10 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
     // (Tried: warp = (channel, task pair), lane = row, rows 0 and 32 packed into one complex transform -- all 128 threads busy
     // instead of 66, but each thread then owns 8 of the 16 bytes of an operand unit: twice the store instructions, half-written
     // sectors meeting in L2.  Config 4 at quarter scale 3.27 -> 5.35 ms, C2 45 -> 62 us: the kernel is bound by its stores.)
+    // (Tried, round 2e: rows 0 and 32 packed as H[0] + i H[32] in row 0, lane 0 leaves the transform in shared memory and warps
+    // 1 and 3 -- which otherwise run this whole step for ONE lane each -- only unpack and store the two rows: a quarter fewer
+    // warp instructions, 153 registers instead of 167, parity green, and no change in time (config 4: 13.3 vs 13.2 ms, C2 53 vs
+    // 50 us): the kernel waits for its window gather and its stores, not for issue slots.  scripts/exp_datafft.sh.)
     {
         const int u = threadIdx.x & 63;
         if (u < OS_CH) {
