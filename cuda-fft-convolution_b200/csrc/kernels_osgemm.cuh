@@ -1547,6 +1547,9 @@ __global__ void __launch_bounds__(256, 3) os_inverse_z(OsInvArgs a, const __grid
     const int NX = a.NNB * NG;                                             // items per template
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int par = warp >> 2, zq = warp & 3;                              // pass 1: zone zq; pass 2: tile zq
+    // (Tried, round 2e: parity = warp & 1, so that the warps of one scheduler partition (warp index mod 4) all run the same
+    // parity's specialised first stages and its L0 instruction cache sees one copy of the pass code: 0.244 vs 0.240 ms at
+    // config 2, 28.5 vs 27.8 ms at config 4 -- slower.  scripts/exp_invpar.sh.)
     auto request = [&](int item) {                                         // one thread: 9 tensor copies
         const int t = item / NX, bx = item - t * NX;
         const int nblk = bx / NG, g = bx - nblk * NG;
