@@ -929,6 +929,15 @@ def main():
                                                                "(profiling runs: keeps the launch list to the step's own kernels)")
     args = ap.parse_args()
     if args.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1 to every rank, and the thread pools under numpy / scipy are sized from it when
+        # the libraries load: the host arm then runs on a fraction of the cores it is supposed to use (fft2 path 2.7x slower,
+        # which flatters every ratio taken against it).  Rank 0 restarts itself with the variable set to the core count.
+        want = str(os.cpu_count() or 1)
+        if (int(os.environ.get("RANK", "0")) == 0 and os.environ.get("OMP_NUM_THREADS") not in (None, want)
+                and not os.environ.get("FFTCONV_BENCH_REEXEC")):
+            sys.stdout.flush()
+            os.execvpe(sys.executable, [sys.executable, os.path.abspath(__file__)] + sys.argv[1:],
+                       dict(os.environ, OMP_NUM_THREADS=want, FFTCONV_BENCH_REEXEC="1"))
         run_reference(args)
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
