@@ -78,6 +78,22 @@ def test_python_mirror_argument_errors(fc):
     assert "CUDA Thread Size must be 4 integers" in str(e.value)
 
 
+def test_device_cells_refuse_host_tensors_and_wrong_shapes(fc):
+    """fc.DeviceCells marshals a DEVICE-resident kernel cell (the gpuArray kernels of src/cudaConvFFTData.cu:204-231) for the
+    one-shot entry point: host tensors, a channel count that differs from the data's (:229), non-contiguous or non-float32
+    cells are refused with the reference's message before anything reaches the library -- there is no CPU fallback."""
+    import torch
+    ok = torch.zeros((3, 4, 5))
+    for bad in ([ok],                                                       # on the host
+                [torch.zeros((2, 4, 5))],                                   # F differs
+                [torch.zeros((3, 4, 5), dtype=torch.float64)],              # not single
+                [torch.zeros((3, 5, 4)).transpose(1, 2)],                   # not contiguous
+                [torch.zeros((3, 4))]):                                     # not 3-D
+        with pytest.raises(fc.FFTConvError) as e:
+            fc.DeviceCells(bad, 3)
+        assert "same number of features" in str(e.value)
+
+
 def test_no_product_import_of_oracle():
     """The product path must not route through the oracle (or any CPU fallback)."""
     pkg = os.path.join(ROOT, "cuda-fft-convolution_b200")
