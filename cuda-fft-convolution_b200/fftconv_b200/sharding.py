@@ -22,7 +22,17 @@ def shard_bank(costs: Optional[Sequence[float]], world: int, K: Optional[int] = 
     import numpy as np
     if world <= 0:
         raise ValueError("world must be positive")
-    c = np.ones(int(K), dtype=np.float64) if costs is None else np.asarray(costs, dtype=np.float64).reshape(-1)
+    if costs is None:
+        # uniform costs in closed form: template k has its midpoint at k + 0.5, rank r ends at the first k with
+        # k + 0.5 > K r / world  (the same comparison the general case makes, without building the arrays)
+        K = int(K)
+        bounds = [0]
+        for r in range(1, world):
+            t = float(K) * r / world
+            bounds.append(min(K, max(0, int(np.floor(t - 0.5)) + 1)))
+        bounds.append(K)
+        return [(bounds[r], bounds[r + 1]) for r in range(world)]
+    c = np.asarray(costs, dtype=np.float64).reshape(-1)
     K = int(c.size)
     if K == 0:
         return [(0, 0)] * world
