@@ -3,6 +3,7 @@ declares, and the argument checks that do not need a device behave like the refe
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -172,3 +173,21 @@ def test_in_place_plans_cover_every_supported_size(fc):
                 assert r in (2, 3, 4, 5, 7, 8, 9, 11, 13, 16, 17, 32), (n, rh)
         else:
             assert path != 4, n
+
+
+def test_reference_arm_restarts_with_all_host_threads():
+    """`bench.py --impl reference` under torchrun inherits OMP_NUM_THREADS=1; rank 0 restarts itself with the core count so the
+    host arm uses the threads it reports (`cpu_baseline.cores`), other ranks print nothing and exit 0."""
+    import json
+    import subprocess
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    env.pop("FFTCONV_BENCH_REEXEC", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1"], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-1000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                         "--warmup", "1"], env=dict(env, RANK="1"), capture_output=True, text=True, timeout=600)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
