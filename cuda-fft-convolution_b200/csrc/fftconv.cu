@@ -610,8 +610,11 @@ static bool os_config_tiles(OsCfg& g) {
 //                         size-specialised kernels where one is instantiated for the line length (kernels_bigplane_ct.cuh)
 //   FFTCONV_OS_AHEAD      1 / 2: with several chunks of device-resident templates, os_kern_fft of chunk i + 1 runs on a side stream
 //                         (1: the high-priority one, 2: the copy stream) next to os_inverse_z of chunk i (default 0)
+//   FFTCONV_OS_DATA       2: os_data_fft_occ (rows overlay the raw windows, channels of the w step one after the other) instead of os_data_fft
+//   FFTCONV_OS_DATA_ST256 0: two 128-bit stores per 32-byte unit of the B image in os_data_fft instead of one 256-bit store (default 1:
+//                         config 4 os_data_fft 13.2 -> 9.9 ms, the kernel was bound by its store requests)
 //   FFTCONV_OS_PF         L2 prefetch distance of os_gemm's TMA producer in work items (default 0 = off: measured 0.21 -> 0.30 ms at config 2 with 6 items ahead, the prefetched lines fight the P stores for L2)
-struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache, bp_ct, ahead; };
+struct OsEnv { int min_k, ntblk, inv_tma, gemm_simt, gemm_tmap, hi_inplace, lbo_swap, dbg, pf, spec_cache, bp_ct, ahead, data_occ, data_st256; };
 static const OsEnv& os_env() {
     static const OsEnv e = [] {
         auto geti = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
@@ -629,6 +632,8 @@ static const OsEnv& os_env() {
         x.spec_cache = geti("FFTCONV_SPEC_CACHE", 1);
         x.bp_ct = geti("FFTCONV_BP_CT", 0);
         x.ahead = geti("FFTCONV_OS_AHEAD", 0);
+        x.data_occ = geti("FFTCONV_OS_DATA", 0) == 2;
+        x.data_st256 = geti("FFTCONV_OS_DATA_ST256", 1);
         return x;
     }();
     return e;
@@ -755,13 +760,15 @@ static int os_prepare_data(Ctx& c, const OsCfg& g, const cpx* d_spec, const floa
         a.src = src; a.F = F; a.nth = g.nth; a.NTimg = g.NTimg; a.Sh = g.Sh; a.Sw = g.Sw; a.oy0 = g.maxkh - 1; a.ox0 = g.maxkw - 1;
         a.FH = FH; a.FW = FW; a.img = (float*)c.osB.p; a.NKS = g.NKS; a.KC = g.KC; a.NMMA = g.NMMA; a.NTn = g.NTn;
         a.correlate = correlate;
+        a.st256 = os_env().data_st256;
         if (prov && !d_raw) { a.hsel = prov->hsel; a.alt = prov->alt; a.alt_done = prov->alt_done; }
         ++c.osB_gen;
         // channel pair fastest: the CTAs resident at any time complete whole (tile block, bin) blocks of the B image
         // together (tile-fastest order left every 16-byte row pair of a block to be written at 16 different times)
         const unsigned grid = (unsigned)g.NT * (unsigned)(g.NKS * g.KC);
         ProfScope ps(PK_OS_DATA, st);
-        os_data_fft<<<grid, 128, OS_DATA_SMEM, st>>>(a);
+        if (os_env().data_occ) os_data_fft_occ<<<grid, 128, OS_DATA_SMEM_OCC, st>>>(a);
+        else os_data_fft<<<grid, 128, OS_DATA_SMEM, st>>>(a);
         LAUNCH_CHECK();
     }
     return 0;
@@ -2078,10 +2085,12 @@ static int run_conv_pyramid(Ctx& c, int L, const PyrLevel* lv, int F, int maxkh,
         a.F = F; a.nth = 1; a.NTimg = NT; a.Sh = og.Sh; a.Sw = og.Sw; a.oy0 = maxkh - 1; a.ox0 = maxkw - 1;
         a.FH = 64; a.FW = 64; a.img = (float*)c.osB.p; a.NKS = og.NKS; a.KC = og.KC; a.NMMA = og.NMMA; a.NTn = og.NTn;
         a.correlate = 0;
+        a.st256 = os_env().data_st256;
         c.sc.b_valid = false; ++c.osB_gen;                             // the B images now belong to this call
         const unsigned grid = (unsigned)NT * (unsigned)(og.NKS * og.KC);
         ProfScope ps(PK_OS_DATA, ds);
-        os_data_fft<<<grid, 128, OS_DATA_SMEM, ds>>>(a);
+        if (os_env().data_occ) os_data_fft_occ<<<grid, 128, OS_DATA_SMEM_OCC, ds>>>(a);
+        else os_data_fft<<<grid, 128, OS_DATA_SMEM, ds>>>(a);
         LAUNCH_CHECK();
     }
     CU(cudaEventRecord(c.evf[1], ds));                                 // joined by the first chunk in front of its os_gemm

@@ -391,6 +391,7 @@ struct OsDArgs {
     float* img;
     int NKS, KC, NMMA, NTn;
     int correlate;
+    int st256;              // one 256-bit store per (tile, channel pair, bin) instead of two 128-bit ones (FFTCONV_OS_DATA_ST256)
     // provenance of a caller-supplied spectrum (SpecCache in fftconv.cu): hsel[0] = hash of the spectrum when
     // fftconv_fft_data produced it, hsel[1] = hash of what the caller handed to the convolution.  Equal: the raw data
     // kept from that call (`alt`) is tiled directly -- or, when the tile spectra were already computed next to the
@@ -536,7 +537,13 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
             // the 1/(64*64) of the inverse transform rides here: a power of two, so the scaling is exact
             const float sc = 1.0f / 4096.0f, sg = a.correlate ? -sc : sc;
             // plain fp32 (re-row, im-row): os_gemm splits hi / lo on chip, as it does for the A images
+            const bool st256 = a.st256 != 0;
             auto emit = [&](float* o, float c0x, float c0y, float c1x, float c1y) {
+                if (st256) {                       // the 32 bytes of a (tile, channel pair, bin) unit as ONE whole-sector store
+                    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(sc * c0x), "f"(-sg * c0y),
+                                 "f"(sc * c1x), "f"(-sg * c1y), "f"(sc * c0y), "f"(sg * c0x), "f"(sc * c1y), "f"(sg * c1x) : "memory");
+                    return;
+                }
                 float4* oh = reinterpret_cast<float4*>(o);
                 oh[0] = make_float4(sc * c0x, -sg * c0y, sc * c1x, -sg * c1y);
                 oh[1] = make_float4(sc * c0y, sg * c0x, sc * c1y, sg * c1x);
@@ -545,6 +552,141 @@ __global__ void __launch_bounds__(128) os_data_fft(OsDArgs a)
             for (int j1 = 0; j1 < 16; ++j1) {
                 emit(base + (size_t)(4 * j1) * bin_stride, r0A[j1], i0A[j1], r1A[j1], i1A[j1]);
                 emit(base + (size_t)(4 * j1 + 2) * bin_stride, r0B[j1], i0B[j1], r1B[j1], i1B[j1]);
+            }
+        }
+    }
+}
+
+// os_data_fft_occ: the same transform laid out for occupancy (FFTCONV_OS_DATA=2, experiment of round 2e).  os_data_fft is
+// latency-bound (ncu at config-4 shapes: long_scoreboard on the window gather, 31 % issue active) and holds three CTAs per
+// SM: 167 registers (the w step keeps the spectra of BOTH channels of a row, 128 floats, in registers) and 68 KB.  Here
+//   * the h-transformed rows overlay the raw windows: a barrier separates the first radix-4 stage of the h step (which
+//     consumes every raw sample) from the register DFTs and their stores;
+//   * the w step runs the two channels one after the other: the spectrum of channel 0 is parked IN PLACE in its own row
+//     (a barrier lets both parities finish reading the row first) and read back while channel 1 is emitted.
+// 35 KB of shared memory and about half the live registers.
+constexpr size_t OS_DATA_SMEM_OCC = (2 * 64 * OS_DRAW * sizeof(float) > 2 * 33 * OS_IROW * sizeof(cpx))
+                                        ? 2 * 64 * OS_DRAW * sizeof(float) : 2 * 33 * OS_IROW * sizeof(cpx);
+
+__global__ void __launch_bounds__(128, 5) os_data_fft_occ(OsDArgs a)
+{
+    extern __shared__ __align__(128) unsigned char os_smem_raw[];
+    float* raw = reinterpret_cast<float*>(os_smem_raw);                              // [2][64][65]
+    cpx* Hs = reinterpret_cast<cpx*>(os_smem_raw);                                   // [2][33][66], overlays raw
+    SrcDesc src = a.src;
+    if (a.hsel && a.hsel[0] == a.hsel[1]) {                             // CTA-uniform (see OsDArgs)
+        if (a.alt_done) return;
+        src = a.alt;
+    }
+    const int npair = a.NKS * a.KC;
+    const int m = blockIdx.x / npair, fp = blockIdx.x - m * npair;      // channel pair fastest
+    int img = m / a.NTimg, mt = m - img * a.NTimg;
+    int nth = a.nth, FH = a.FH, FW = a.FW;
+    if (a.levels) {
+        const OsLevel lv = a.levels[os_level_of(a.levels, a.nlevels, m)];
+        src.ptr = lv.src; src.rows = lv.rows; src.cols = lv.cols;
+        FH = lv.FH; FW = lv.FW; nth = lv.nth; mt = m - lv.m0; img = 0;
+    }
+    const int tj = mt / nth, ti = mt - tj * nth;
+    const int oy = ti * a.Sh - a.oy0, ox = tj * a.Sw - a.ox0;
+    const int warp = threadIdx.x >> 5;
+    {   // ---- gather (as in os_data_fft)
+        const int y = threadIdx.x & 63;
+        const int gy = os_wrap(oy + y, FH);
+        const bool vy = gy < src.rows;
+        for (int ch = 0; ch < 2; ++ch) {
+            const int f = 2 * fp + ch;
+            const float* pl = src.ptr + ((size_t)img * a.F + f) * src.cols * src.rows + gy;
+            float* dst = raw + (size_t)ch * 64 * OS_DRAW + y + (threadIdx.x >> 6) * OS_DRAW;
+            int gx = os_wrap(ox + (threadIdx.x >> 6), FW);
+            const bool vf = vy && f < a.F;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+                if (vf && gx < src.cols)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(pl + (size_t)gx * src.rows) : "memory");
+                else
+                    *dst = 0.f;
+                dst += 2 * OS_DRAW;
+                gx += 2;
+                if (gx >= FW) gx -= FW;
+            }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    }
+    __syncthreads();
+    const int par = warp >> 1;                       // warp-uniform: tasks (par, par + 2)
+    {   // ---- h step: line = (channel, column pair)
+        const int line = threadIdx.x & 63;
+        const int ch = line >> 5, cp = line & 31;
+        const float* ca = raw + ((size_t)ch * 64 + 2 * cp) * OS_DRAW;
+        const float* cb = ca + OS_DRAW;
+        auto ld = [&](int j) { return make_float4(ca[j], cb[j], ca[j + 1], cb[j + 1]); };
+        float pr[16], pi[16], qr[16], qi[16];
+        if (par == 0) os_fft64_pair<0, false, decltype(ld)&, false>(ld, pr, pi, qr, qi);
+        else          os_fft64_pair<1, false, decltype(ld)&, false>(ld, pr, pi, qr, qi);
+        __syncthreads();                             // every raw sample has been consumed: the rows may overwrite the windows
+        dft_regs<16, false>(pr, pi);
+        dft_regs<16, false>(qr, qi);
+        float4* hcol = reinterpret_cast<float4*>(Hs + (size_t)ch * 33 * OS_IROW) + cp;       // + u * (OS_IROW/2)
+        auto put = [&](int u, float zr, float zi, float nr, float ni) {
+            hcol[u * (OS_IROW / 2)] = make_float4(0.5f * (zr + nr), 0.5f * (zi - ni), 0.5f * (zi + ni), -0.5f * (zr - nr));
+        };
+        if (par == 0) {
+#pragma unroll
+            for (int j1 = 0; j1 < 9; ++j1) put(4 * j1, pr[j1], pi[j1], pr[(16 - j1) & 15], pi[(16 - j1) & 15]);
+#pragma unroll
+            for (int j1 = 0; j1 < 8; ++j1) put(4 * j1 + 2, qr[j1], qi[j1], qr[15 - j1], qi[15 - j1]);
+        } else {
+#pragma unroll
+            for (int j1 = 0; j1 < 8; ++j1) {
+                put(4 * j1 + 1, pr[j1], pi[j1], qr[15 - j1], qi[15 - j1]);
+                put(4 * j1 + 3, qr[j1], qi[j1], pr[15 - j1], pi[15 - j1]);
+            }
+        }
+    }
+    __syncthreads();
+    {   // ---- w step: thread = (spectrum row u, task pair); channel 0 first, parked in place, then channel 1 and the stores
+        const int u = threadIdx.x & 63;
+        const bool active = u < OS_CH;
+        cpx* row0 = Hs + (size_t)(active ? u : 0) * OS_IROW;
+        float rA[16], iA[16], rB[16], iB[16];
+        if (active) {
+            auto ld = [&](int j) { return *reinterpret_cast<const float4*>(row0 + j); };
+            if (par == 0) os_fft64_pair<0, false, decltype(ld)&, false>(ld, rA, iA, rB, iB);
+            else          os_fft64_pair<1, false, decltype(ld)&, false>(ld, rA, iA, rB, iB);
+        }
+        __syncthreads();                             // both parities have read row u of channel 0
+        if (active) {
+            dft_regs<16, false>(rA, iA);
+            dft_regs<16, false>(rB, iB);
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                row0[4 * j1 + par] = make_float2(rA[j1], iA[j1]);
+                row0[4 * j1 + par + 2] = make_float2(rB[j1], iB[j1]);
+            }
+            {
+                const cpx* row = Hs + (size_t)(33 + u) * OS_IROW;
+                auto ld = [&](int j) { return *reinterpret_cast<const float4*>(row + j); };
+                if (par == 0) os_fft64_pair<0, false>(ld, rA, iA, rB, iB);
+                else          os_fft64_pair<1, false>(ld, rA, iA, rB, iB);
+            }
+            const int nblk = m / a.NTn, sl = m - nblk * a.NTn;
+            const int ks = fp / a.KC, kc = fp - ks * a.KC;
+            const size_t stage_stride = (size_t)a.KC * a.NMMA * 4;
+            const size_t bin_stride = (size_t)a.NKS * stage_stride;
+            float* base = a.img + ((size_t)nblk * OS_NBIN + (size_t)u * 64 + par) * bin_stride + (size_t)ks * stage_stride +
+                          (size_t)kc * a.NMMA * 4 + (size_t)(2 * sl) * 4;
+            const float sc = 1.0f / 4096.0f, sg = a.correlate ? -sc : sc;
+            auto emit = [&](float* o, float c0x, float c0y, float c1x, float c1y) {
+                float4* oh = reinterpret_cast<float4*>(o);
+                oh[0] = make_float4(sc * c0x, -sg * c0y, sc * c1x, -sg * c1y);
+                oh[1] = make_float4(sc * c0y, sg * c0x, sc * c1y, sg * c1x);
+            };
+#pragma unroll
+            for (int j1 = 0; j1 < 16; ++j1) {
+                const cpx c0a = row0[4 * j1 + par], c0b = row0[4 * j1 + par + 2];
+                emit(base + (size_t)(4 * j1) * bin_stride, c0a.x, c0a.y, rA[j1], iA[j1]);
+                emit(base + (size_t)(4 * j1 + 2) * bin_stride, c0b.x, c0b.y, rB[j1], iB[j1]);
             }
         }
     }
