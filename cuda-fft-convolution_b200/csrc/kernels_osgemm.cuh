@@ -677,7 +677,13 @@ __global__ void __launch_bounds__(128, 5) os_data_fft_occ(OsDArgs a)
             float* base = a.img + ((size_t)nblk * OS_NBIN + (size_t)u * 64 + par) * bin_stride + (size_t)ks * stage_stride +
                           (size_t)kc * a.NMMA * 4 + (size_t)(2 * sl) * 4;
             const float sc = 1.0f / 4096.0f, sg = a.correlate ? -sc : sc;
+            const bool st256 = a.st256 != 0;
             auto emit = [&](float* o, float c0x, float c0y, float c1x, float c1y) {
+                if (st256) {
+                    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o), "f"(sc * c0x), "f"(-sg * c0y),
+                                 "f"(sc * c1x), "f"(-sg * c1y), "f"(sc * c0y), "f"(sg * c0x), "f"(sc * c1y), "f"(sg * c1x) : "memory");
+                    return;
+                }
                 float4* oh = reinterpret_cast<float4*>(o);
                 oh[0] = make_float4(sc * c0x, -sg * c0y, sc * c1x, -sg * c1y);
                 oh[1] = make_float4(sc * c0y, sg * c0x, sc * c1y, sg * c1x);
